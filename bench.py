@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the marinenav hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one fused mnv_step launch over one batch of 65 536 environments per GPU (BASELINE configs[1]:
+8 obstacles / 4 vortex cores / 11 beams, synthetic randomly seeded maps).  Consecutive steps rotate over 8 independent
+env batches (8 x ~32 MB > 126 MB L2) so every step streams its state from HBM.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched env steps/sec and IQN updates/sec at 1/2/4/8 B200 vs CPU ref"
+UNIT = "env_steps/s"
+N_CORES, N_OBS, N_BEAMS = 4, 8, 11
+ENVS_PER_GPU = 65536
+N_BATCHES = 8
+
+
+def algorithmic_bytes_per_env_step(n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS, s=8):
+    """read = s*(4 state + 2 goal + 3 n_o + 3 n_c) + 4 (timestep) + 4 (action);
+    write = s*4 + 4 + 4*(4 + 2 n_b) + 4 (reward) + 2 (done, info).  fp64 tables -> s = 8 -> 490 B at C2."""
+    return s * (4 + 2 + 3 * n_o + 3 * n_c) + 8 + (s * 4 + 4 + 4 * (4 + 2 * n_b) + 4 + 2)
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle port; the only place besides tests/ and smoke() that executes oracle/)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_port_steps_per_s(n_envs, n_steps, n_threads, seed0=0):
+    import numpy as np
+    from oracle import marinenav_oracle as mo
+    op = mo.default_params(N_BEAMS)
+    w = mo.reset_batch(np.arange(n_envs, dtype=np.uint32) + seed0, N_CORES, N_OBS, 30.0, N_CORES, N_OBS, op, n_threads=n_threads)
+    rng = np.random.RandomState(1)
+    ep = np.zeros(n_envs, np.int32)
+    acts = [rng.randint(0, 9, size=n_envs).astype(np.int32) for _ in range(n_steps)]
+    t0 = time.perf_counter()
+    for a in acts:
+        mo.step_batch(w["state"], w["velocity"], w["goal"], w["cores"], w["obstacles"], a, ep, op, n_threads)
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference is pure Python and cannot travel to the GPU box, so this arm times the oracle
+    port (C restatement of MarineNavEnv.step, all host threads) on the same workload; each 'step' is a bounded sample."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_envs = 16384
+    per_step = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_port_steps_per_s(sample_envs, 1, cores, seed0=i)
+        if i >= args.warmup:
+            per_step.append((v, dt))
+    total = sum(sample_envs / v for v, _ in per_step)
+    value = sample_envs * len(per_step) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "marinenav fused env step, 8 obstacles / 4 vortex cores / 11 beams (BASELINE configs[1])",
+                   "envs_per_step_sample": sample_envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_envs} envs x 1 step per timed step, oracle/marinenav_oracle.c on {cores} threads "
+                                   "(the Python reference itself: 330-385 steps/s/core, SURVEY.md section 6)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from distributional_rl_navigation_b200 import _lib, env_ops
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, K, W = args.envs, args.steps, args.warmup
+    assert W >= 3, "timing rules: at least 3 warm-up steps"
+
+    # ---- synthetic workload: N_BATCHES independent env batches, maps from the device reset (seed = global env index)
+    batches = []
+    for b in range(N_BATCHES):
+        env = VecMarineNavEnv(E, seed=(rank * N_BATCHES + b) * E, device=dev, num_cores=N_CORES, num_obs=N_OBS,
+                              min_start_goal_dis=30.0, num_beams=N_BEAMS)
+        env.reset()
+        batches.append(env)
+    for env in batches[1:]:
+        env.rng_key = None                         # 164 MB each; only batch 0 is used for the e2e (auto-reset) leg
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    actions = torch.randint(0, 9, (W + K, E), generator=g, device=dev, dtype=torch.int32)
+    params = batches[0].params()
+    stream = torch.cuda.current_stream()
+
+    def one_step(i):
+        env_ops.step(batches[i % N_BATCHES].buf, params, action=actions[i % actions.shape[0]])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        one_step(i)
+    barrier()
+    # The step kernel lasts ~10 us, less than a Python-side launch: capture CHUNK consecutive steps (CHUNK launches of
+    # mnv_step through the C-ABI on the capturing stream) in a CUDA graph and replay it, so the timed region is
+    # back-to-back kernels.  K = n_rep * CHUNK + rem; the remainder is launched eagerly.
+    chunk = min(K, 8 * N_BATCHES)
+    chunk -= chunk % N_BATCHES if chunk >= N_BATCHES else 0
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(chunk):
+                one_step(W + i)
+    torch.cuda.current_stream().wait_stream(side)
+    n_rep, rem = K // chunk, K % chunk
+    stream = torch.cuda.current_stream()
+
+    def timed_region():
+        for _ in range(n_rep):
+            graph.replay()
+        for i in range(rem):
+            one_step(W + i)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        # ~1 s of the same kernels right before the timed region so that nvidia-smi sees the clocks under THIS load
+        # (the timed region itself may last only milliseconds); clocks are sampled across both.
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < args.preload:
+            timed_region()
+            torch.cuda.synchronize()
+        barrier()
+        ev0.record(stream)
+        timed_region()
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+    times = [ms_total]
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = world * E / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API with HOST buffers (H2D actions, D2H obs/reward/done/info, auto-reset) every step ----
+    env0 = batches[0]
+    host_actions = np.random.RandomState(7 + rank).randint(0, 9, size=(W + K, E)).astype(np.int32)
+    for i in range(W):
+        env0.step_host(host_actions[i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        obs, rew, done, info = env0.step_host(host_actions[i])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * K / float(te.item())
+    checksum = float(np.asarray(rew, np.float64).sum())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        abytes = algorithmic_bytes_per_env_step()
+        achieved = E * abytes / (ms_per_step * 1e-3) / 1e9
+        cpu_cores = os.cpu_count() or 1
+        cpu_v, cpu_dt = cpu_port_steps_per_s(E, 40, cpu_cores) if world == 1 else (None, None)
+        cpu1_v, _ = cpu_port_steps_per_s(E, 20, 1) if world == 1 else (None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "marinenav fused env step (mnv_step), 65536 envs/GPU, 8 obstacles / 4 vortex cores / "
+                                   "11 beams, random actions (BASELINE configs[1])",
+                       "envs_per_gpu": E, "l2": f"rotating {N_BATCHES} env batches ({N_BATCHES * E * abytes / 1e6:.0f} MB "
+                                                "> 126 MB L2), one batch per step",
+                       "auto_reset": "in e2e only", "parallelism": f"env-sharded x{world}, no collective in step",
+                       "launch": f"CUDA graph of {chunk} mnv_step launches x {n_rep} replays + {rem} eager",
+                       "timed_region_ms": round(times[0], 4)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
+                         "kernel": "mnv_env_kernel<4,8,true>"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env0.h2d_bytes_per_step() * world,
+                    "d2h_bytes_per_step": env0.d2h_bytes_per_step() * world, "checksum": checksum,
+                    "api": "VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset)"},
+            "gpu_launches": K,
+            "clocks": clk.summary(),
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                                    "value_1_thread": cpu1_v,
+                                    "sample": f"{E} envs x 40 steps of the same workload, oracle/marinenav_oracle.c "
+                                              f"({cpu_dt:.1f} s on {cpu_cores} threads; the Python reference itself: "
+                                              "330-385 steps/s/core, SURVEY.md section 6)"}
+        extra = getattr(sys.modules[__name__], "iqn_bench", None)
+        if extra is not None:
+            line["iqn"] = extra(args, dev, world)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--preload", type=float, default=1.0, help="seconds of untimed identical load before the timed region (clock sampling)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,339 @@
+// Fused batched MarineNavEnv.step / get_observation for sm_100a.
+//
+// One thread integrates one environment: fp64 state, N sub-steps of Rankine-vortex current + USV kinematics
+// (marinenav_env.py:422-465, robot.py:95-123), then an fp64 robot-frame ray cast of the sonar beams
+// (robot.py:125-198), the observation (marinenav_env.py:273-326), reward and termination priority
+// (marinenav_env.py:199-262).  Everything an environment needs (4 state + 2 goal + 3*max_c + 3*max_o doubles) is
+// read once with coalesced 8-byte loads from the SoA tables and kept in registers; observation rows are staged in
+// shared memory and written back as one contiguous float4 stream per CTA.
+//
+// Formulation differences against the reference (all below 1e-12 except where the reference itself is
+// ill-conditioned; tests/test_env_parity.py states the tolerances):
+//   * vortex velocity: tangent*speed = k*(-dy,dx)/d^2 outside the core and k*(-dy,dx)/r^2 inside (k = +-Gamma/2pi),
+//     i.e. no sqrt and one Newton reciprocal per core instead of normalise-then-scale (same value, Q1 kept: every
+//     core contributes; Q2: summation order is table order, ulp-level only);
+//   * heading: sincos(theta) once, then the sub-steps rotate (cos,sin) by the fixed yaw increment w*dt;
+//   * sonar: obstacle centres are rotated into the robot frame once, beams are the constant directions
+//     (cos b, sin b) there; ray/circle in direction form t = t_ca -+ sqrt(r^2 - cross^2) picking the reference's
+//     "nearer root first" (robot.py:184), range and behind tests (robot.py:185-190), the ordered break Q3
+//     (robot.py:192-195), and the vertical snap Q10 (robot.py:134-162: a beam within 1e-3 rad of +-pi/2 is
+//     intersected along exactly (0,+-1)).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "mnv_common.cuh"
+
+namespace {
+
+constexpr int kBlock = 64;      // E = 65536 -> 1024 CTAs = 6.9 per SM with 8 resident (<= 128 registers): one balanced wave
+
+struct KParams {
+    double dt;
+    double accel[3], wdt[3], cos_wdt[3], sin_wdt[3];
+    double k_drag, max_speed, robot_r, core_r2, inv_core_r2, goal_dis;
+    double pen_step, pen_coll, rew_goal;
+    double range, range_slack;
+    double width, height;
+    int n_substeps, n_beams, max_ep_steps, set_boundary;
+    int max_c, max_o, obs_dim, velocity_from_state;
+    long long E;
+    double beam_angle[MNV_MAX_BEAMS];
+    double beam_cos[MNV_MAX_BEAMS];
+    double beam_sin[MNV_MAX_BEAMS];
+};
+
+struct EnvPtrs {
+    double* state; double* velocity; const double* goal; const double* cores; const double* obst;
+    const int32_t* action; int32_t* ep_step; const uint8_t* mask;
+    float* obs; float* reward; uint8_t* done; uint8_t* info;
+};
+
+// 1/a to ~1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps; a is a squared distance in [1e-300, 1e300] here.
+__device__ __forceinline__ double fast_rcp(double a)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = fma(r, fma(-a, r, 1.0), r);
+    r = fma(r, fma(-a, r, 1.0), r);
+    return r;
+}
+
+template <int MAXC, int MAXO, bool STEP>
+__global__ void __launch_bounds__(kBlock, 8)
+mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
+{
+    extern __shared__ __align__(16) float s_obs[];           // [kBlock][obs_dim]
+    const long long E = K.E;
+    const long long e0 = (long long)blockIdx.x * kBlock;
+    const long long e = e0 + threadIdx.x;
+    const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
+    const int D = K.obs_dim;
+    float* my_obs = s_obs + threadIdx.x * D;
+
+    if (live) {
+        double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
+        const double gx = P.goal[e], gy = P.goal[E + e];
+        double c, s;
+        sincos(th, &s, &c);
+        double vx, vy, reward = 0.0;
+        int ep = 0;
+
+        // ---- vortex cores -> registers; k = Gs/(2pi) carries the spin in its sign ----
+        double cx[MAXC], cy[MAXC], ck[MAXC];
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            if (i < K.max_c) {
+                cx[i] = __ldg(P.cores + (long long)i * E + e);
+                cy[i] = __ldg(P.cores + (long long)(K.max_c + i) * E + e);
+                ck[i] = __ldg(P.cores + (long long)(2 * K.max_c + i) * E + e) * (1.0 / (2.0 * MNV_PI));
+            } else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+        }
+        auto current = [&](double px, double py, double& ux, double& uy) {
+            ux = 0.0; uy = 0.0;
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                const double dx = cx[i] - px, dy = cy[i] - py;
+                const double d2 = fma(dx, dx, dy * dy);
+                // compute_speed (marinenav_env.py:461-465): solid-body rotation inside the core radius
+                const double f = ck[i] * (d2 <= K.core_r2 ? K.inv_core_r2 : fast_rcp(d2));
+                ux = fma(-dy, f, ux);
+                uy = fma(dx, f, uy);
+            }
+        };
+
+        if (STEP) {
+            const int action = P.action[e];
+            ep = P.ep_step[e];
+            const int ai = action / 3, wi = action - 3 * ai;
+            const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
+            const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+            vx = 0.0; vy = 0.0;
+            for (int it = 0; it < K.n_substeps; ++it) {
+                double ux, uy;
+                current(x, y, ux, uy);
+                vx = fma(sp, c, ux);                          // robot.py:98-100 (pre-update speed / heading: Q6)
+                vy = fma(sp, s, uy);
+                x = fma(vx, K.dt, x);                         // robot.py:105-107
+                y = fma(vy, K.dt, y);
+                sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
+                sp = fmin(fmax(sp, 0.0), K.max_speed);        // robot.py:114
+                th = __dadd_rn(th, wdt);                      // robot.py:117
+                while (th < 0.0) th += 2.0 * MNV_PI;          // robot.py:120-123
+                while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
+                c = c2; s = s2;
+            }
+            const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+            reward = K.pen_step + (dis_before - dis_after);   // marinenav_env.py:220,229
+        } else {
+            if (K.velocity_from_state) {
+                double ux, uy;
+                current(x, y, ux, uy);
+                vx = fma(sp, c, ux); vy = fma(sp, s, uy);
+                P.velocity[e] = vx; P.velocity[E + e] = vy;
+            } else { vx = P.velocity[e]; vy = P.velocity[E + e]; }
+        }
+
+        // ---- observation head: R^T v, R^T (goal - pos)  (marinenav_env.py:278-293) ----
+        my_obs[0] = (float)fma(c, vx, s * vy);
+        my_obs[1] = (float)fma(c, vy, -s * vx);
+        my_obs[2] = (float)fma(c, gx - x, s * (gy - y));
+        my_obs[3] = (float)fma(c, gy - y, -s * (gx - x));
+
+        // ---- obstacles -> robot frame, registers ----
+        double qx[MAXO], qy[MAXO], r2[MAXO], lim[MAXO];
+        unsigned may_out = 0u, may_in = 0u;
+        double best_d2 = INFINITY, best_r = 0.0;               // Q4: nearest CENTRE only (marinenav_env.py:329-336)
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            double r = -1.0, ox = 0.0, oy = 0.0;
+            if (j < K.max_o) {
+                ox = __ldg(P.obst + (long long)j * E + e);
+                oy = __ldg(P.obst + (long long)(K.max_o + j) * E + e);
+                r = __ldg(P.obst + (long long)(2 * K.max_o + j) * E + e);
+            }
+            const double dx = ox - x, dy = oy - y;
+            const bool on = r > 0.0;
+            qx[j] = fma(c, dx, s * dy);
+            qy[j] = fma(c, dy, -s * dx);
+            r2[j] = on ? r * r : -1.0;                         // empty slot: discriminant always negative
+            lim[j] = K.range_slack + r;
+            const double d2 = fma(dx, dx, dy * dy);
+            if (on && d2 < best_d2) { best_d2 = d2; best_r = r; }
+            if (on && d2 >= r2[j] * (1.0 - 1e-9)) may_out |= 1u << j;   // robot (almost) outside this circle
+            if (on && d2 <= r2[j] * (1.0 + 1e-9)) may_in |= 1u << j;    // robot (almost) inside
+        }
+
+        // ---- sonar (robot.py:125-198) ----
+        for (int b = 0; b < K.n_beams; ++b) {
+            const double ang = th + K.beam_angle[b];           // robot.py:131 (not wrapped)
+            double bx = K.beam_cos[b], by = K.beam_sin[b];      // beam direction in the robot frame
+            if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }            // Q10: exactly (0,+1) in the world frame
+            else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }     // Q10: exactly (0,-1)
+            int cnt = 0;
+            double tc_s = 0.0, disc_s = 0.0;
+#pragma unroll
+            for (int j = 0; j < MAXO; ++j) {
+                const double tc = fma(qx[j], bx, qy[j] * by);
+                const double cr = fma(qx[j], by, -qy[j] * bx);
+                const double disc = fma(-cr, cr, r2[j]);
+                // conservative candidate filter (no sqrt): real roots, the nearer root can be >= 0 and <= range
+                const bool side = (tc > 0.0) ? ((may_out >> j) & 1u) : ((may_in >> j) & 1u);
+                if (disc >= 0.0 && side && tc <= lim[j]) { ++cnt; tc_s = tc; disc_s = disc; }
+            }
+            bool hit = false;
+            double t = 0.0;
+            if (cnt == 1) {
+                const double h = sqrt(disc_s);
+                t = tc_s > 0.0 ? tc_s - h : tc_s + h;           // nearer root first (robot.py:184)
+                hit = (t <= K.range) && (t >= 0.0);             // robot.py:185-190
+            } else if (cnt > 1) {
+                // several obstacles on this beam: replay the reference's ordered scan (Q3) exactly
+                double best = INFINITY;
+                for (int j = 0; j < K.max_o; ++j) {
+                    const double r = __ldg(P.obst + (long long)(2 * K.max_o + j) * E + e);
+                    if (!(r > 0.0)) continue;
+                    const double dx = __ldg(P.obst + (long long)j * E + e) - x;
+                    const double dy = __ldg(P.obst + (long long)(K.max_o + j) * E + e) - y;
+                    const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
+                    const double tc = fma(ax, bx, ay * by);
+                    const double cr = fma(ax, by, -ay * bx);
+                    const double disc = fma(-cr, cr, r * r);
+                    if (disc < 0.0) continue;                    // robot.py:172-174
+                    const double h = sqrt(disc);
+                    const double tj = tc > 0.0 ? tc - h : tc + h;
+                    if (fabs(tj) > K.range) continue;            // robot.py:185-187
+                    if (tj < 0.0) continue;                      // robot.py:188-190
+                    if (hit && tj >= best) break;                // robot.py:192-195
+                    best = tj; hit = true;
+                }
+                t = best;
+            }
+            my_obs[4 + 2 * b] = hit ? (float)(t * bx) : 0.0f;   // marinenav_env.py:314-320
+            my_obs[5 + 2 * b] = hit ? (float)(t * by) : 0.0f;
+        }
+
+        if (STEP) {
+            // ---- termination priority (marinenav_env.py:240-257, Q5) ----
+            int done = 0, info = MNV_INFO_NORMAL;
+            const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
+            if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
+            else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
+            else if (best_d2 < INFINITY && sqrt(best_d2) <= best_r + K.robot_r) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
+            else if (sqrt(fma(x - gx, x - gx, (y - gy) * (y - gy))) <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
+            P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
+            P.velocity[e] = vx; P.velocity[E + e] = vy;
+            P.ep_step[e] = ep + 1;                                // marinenav_env.py:259
+            P.reward[e] = (float)reward;
+            P.done[e] = (uint8_t)done;
+            P.info[e] = (uint8_t)info;
+        }
+    }
+
+    // ---- observation rows of this CTA: one contiguous block, float4 stores ----
+    __syncthreads();
+    const long long rows = (E - e0 < kBlock) ? (E - e0) : kBlock;
+    const long long n = rows * D;
+    float* dst = P.obs + e0 * D;                                  // e0*D*4 bytes: 16-byte aligned (kBlock*4 % 16 == 0)
+    if (!STEP && P.mask != nullptr) {                             // masked observe: only the selected rows
+        for (long long i = threadIdx.x; i < n; i += kBlock)
+            if (P.mask[e0 + i / D] != 0) dst[i] = s_obs[i];
+        return;
+    }
+    const long long n4 = n >> 2;
+    for (long long i = threadIdx.x; i < n4; i += kBlock)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_obs)[i];
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += kBlock) dst[i] = s_obs[i];
+}
+
+template <bool STEP>
+int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
+    const size_t smem = (size_t)kBlock * K.obs_dim * sizeof(float);
+#define MNV_LAUNCH(MC, MO)                                                                                   \
+    do {                                                                                                     \
+        auto kern = mnv_env_kernel<MC, MO, STEP>;                                                            \
+        if (smem > 48 * 1024) {                                                                              \
+            cudaError_t a = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (a != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(a)); return (int)a; } \
+        }                                                                                                    \
+        kern<<<grid, kBlock, smem, st>>>(P, K);                                                              \
+    } while (0)
+    if (K.max_c <= 4 && K.max_o <= 8) MNV_LAUNCH(4, 8);
+    else if (K.max_c <= 8 && K.max_o <= 10) MNV_LAUNCH(8, 10);
+    else if (K.max_c <= 8 && K.max_o <= 16) MNV_LAUNCH(8, 16);
+    else MNV_LAUNCH(8, 32);
+#undef MNV_LAUNCH
+    return mnv_launch_status(STEP ? "mnv_step" : "mnv_observe");
+}
+
+int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_o)
+{
+    if (p == nullptr) { mnv_set_error("params is null"); return MNV_E_NULL; }
+    if (E <= 0) { mnv_set_error("E must be > 0 (got %lld)", (long long)E); return MNV_E_SIZE; }
+    if (max_c < 0 || max_c > MNV_MAX_CORES || max_o < 0 || max_o > MNV_MAX_OBSTACLES) {
+        mnv_set_error("max_c=%d / max_o=%d exceed the compiled capacity (%d / %d)", max_c, max_o, MNV_MAX_CORES, MNV_MAX_OBSTACLES);
+        return MNV_E_CAPACITY;
+    }
+    if (p->n_beams < 2 || p->n_beams > MNV_MAX_BEAMS) { mnv_set_error("n_beams=%d outside [2,%d]", p->n_beams, MNV_MAX_BEAMS); return MNV_E_CAPACITY; }
+    if (p->n_substeps < 0 || !(p->dt > 0.0) || !(p->core_r > 0.0)) { mnv_set_error("bad dt / n_substeps / core_r"); return MNV_E_PARAM; }
+    memset(&K, 0, sizeof(K));
+    K.dt = p->dt; K.n_substeps = p->n_substeps;
+    for (int i = 0; i < 3; ++i) {
+        K.accel[i] = p->accel[i];
+        K.wdt[i] = p->yaw_rate[i] * p->dt;
+        K.cos_wdt[i] = cos(K.wdt[i]); K.sin_wdt[i] = sin(K.wdt[i]);
+    }
+    K.k_drag = p->k_drag; K.max_speed = p->max_speed; K.robot_r = p->robot_r;
+    K.core_r2 = p->core_r * p->core_r; K.inv_core_r2 = 1.0 / K.core_r2; K.goal_dis = p->goal_dis;
+    K.pen_step = p->timestep_penalty; K.pen_coll = p->collision_penalty; K.rew_goal = p->goal_reward;
+    K.range = p->sonar_range; K.range_slack = p->sonar_range * (1.0 + 1e-9) + 1e-9;
+    K.width = p->width; K.height = p->height;
+    K.n_beams = p->n_beams; K.max_ep_steps = p->max_episode_steps; K.set_boundary = p->set_boundary;
+    K.max_c = max_c; K.max_o = max_o; K.obs_dim = 4 + 2 * p->n_beams; K.E = E;
+    // Sonar.compute_phi / compute_beam_angles (robot.py:14-21)
+    const double phi = p->sonar_angle / (p->n_beams - 1), a0 = -p->sonar_angle / 2;
+    for (int i = 0; i < p->n_beams; ++i) {
+        K.beam_angle[i] = a0 + i * phi;
+        K.beam_cos[i] = cos(K.beam_angle[i]); K.beam_sin[i] = sin(K.beam_angle[i]);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mnv_step(double* d_state, double* d_velocity, const double* d_goal, const double* d_cores,
+                        const double* d_obstacles, const int32_t* d_action, int32_t* d_episode_step,
+                        float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_info,
+                        int64_t E, int32_t max_c, int32_t max_o, const mnv_params* p, void* stream)
+{
+    KParams K;
+    int rc = fill_kparams(K, p, E, max_c, max_o);
+    if (rc) return rc;
+    MNV_CHECK_PTR(d_state); MNV_CHECK_PTR(d_velocity); MNV_CHECK_PTR(d_goal);
+    if (max_c > 0) MNV_CHECK_PTR(d_cores);
+    if (max_o > 0) MNV_CHECK_PTR(d_obstacles);
+    MNV_CHECK_PTR(d_action); MNV_CHECK_PTR(d_episode_step); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_reward);
+    if (d_done == nullptr || d_info == nullptr) { mnv_set_error("mnv_step: null done/info"); return MNV_E_NULL; }
+    if ((E & 1) != 0 && E != 1) { /* fp64 rows stay 8-byte aligned for any E; nothing to do */ }
+    EnvPtrs P{d_state, d_velocity, d_goal, d_cores, d_obstacles, d_action, d_episode_step, nullptr, d_obs, d_reward, d_done, d_info};
+    return launch_env<true>(P, K, (cudaStream_t)stream);
+}
+
+extern "C" int mnv_observe(const double* d_state, double* d_velocity, const double* d_goal, const double* d_cores,
+                           const double* d_obstacles, const uint8_t* d_mask, float* d_obs, int64_t E, int32_t max_c, int32_t max_o,
+                           const mnv_params* p, int32_t velocity_from_state, void* stream)
+{
+    KParams K;
+    int rc = fill_kparams(K, p, E, max_c, max_o);
+    if (rc) return rc;
+    K.velocity_from_state = velocity_from_state ? 1 : 0;
+    MNV_CHECK_PTR(d_state); MNV_CHECK_PTR(d_velocity); MNV_CHECK_PTR(d_goal);
+    if (max_c > 0) MNV_CHECK_PTR(d_cores);
+    if (max_o > 0) MNV_CHECK_PTR(d_obstacles);
+    MNV_CHECK_PTR(d_obs);
+    EnvPtrs P{const_cast<double*>(d_state), d_velocity, d_goal, d_cores, d_obstacles, nullptr, nullptr, d_mask, d_obs, nullptr, nullptr, nullptr};
+    return launch_env<false>(P, K, (cudaStream_t)stream);
+}

@@ -1,0 +1,90 @@
+"""Thin tensor-level wrappers over the env entry points of libmarinenav_b200 (include/marinenav_b200.h).
+
+PyTorch tensors are the memory carrier only: every function takes CUDA tensors laid out as the header describes, passes
+raw device pointers + the current CUDA stream through the C-ABI and returns without synchronising.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, shape, name):
+    if t is None:
+        raise _lib.MarinenavError(f"{name} is None")
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+        raise _lib.MarinenavError(f"{name}: expected contiguous CUDA {dtype} {tuple(shape)}, got "
+                                  f"{t.device} {t.dtype} {tuple(t.shape)} contiguous={t.is_contiguous()}")
+
+
+def alloc_env_buffers(E, max_c, max_o, n_beams, device):
+    """All per-environment arrays of one env batch (layout: include/marinenav_b200.h)."""
+    f64 = dict(dtype=torch.float64, device=device)
+    return dict(
+        state=torch.zeros(4, E, **f64), velocity=torch.zeros(2, E, **f64), goal=torch.zeros(2, E, **f64),
+        cores=torch.zeros(3 * max_c, E, **f64), obstacles=torch.zeros(3 * max_o, E, **f64),
+        start_pose=torch.zeros(4, E, **f64),
+        action=torch.zeros(E, dtype=torch.int32, device=device), episode_step=torch.zeros(E, dtype=torch.int32, device=device),
+        obs=torch.zeros(E, 4 + 2 * n_beams, dtype=torch.float32, device=device),
+        reward=torch.zeros(E, dtype=torch.float32, device=device),
+        done=torch.zeros(E, dtype=torch.uint8, device=device), info=torch.zeros(E, dtype=torch.uint8, device=device),
+        n_placed=torch.zeros(2, E, dtype=torch.uint8, device=device),
+    )
+
+
+def step(buf, params, action=None, obs=None):
+    """MarineNavEnv.step for the whole batch (one kernel). Results land in buf['obs'|'reward'|'done'|'info']."""
+    E = buf["state"].shape[1]
+    max_c, max_o = buf["cores"].shape[0] // 3, buf["obstacles"].shape[0] // 3
+    action = buf["action"] if action is None else action
+    obs = buf["obs"] if obs is None else obs
+    _chk(buf["state"], torch.float64, (4, E), "state"); _chk(buf["velocity"], torch.float64, (2, E), "velocity")
+    _chk(buf["goal"], torch.float64, (2, E), "goal"); _chk(action, torch.int32, (E,), "action")
+    _chk(buf["episode_step"], torch.int32, (E,), "episode_step")
+    _chk(obs, torch.float32, (E, 4 + 2 * params.n_beams), "obs")
+    rc = _lib.load().mnv_step(_lib.ptr(buf["state"]), _lib.ptr(buf["velocity"]), _lib.ptr(buf["goal"]),
+                              _lib.ptr(buf["cores"]), _lib.ptr(buf["obstacles"]), _lib.ptr(action),
+                              _lib.ptr(buf["episode_step"]), _lib.ptr(obs), _lib.ptr(buf["reward"]),
+                              _lib.ptr(buf["done"]), _lib.ptr(buf["info"]), E, max_c, max_o, C.byref(params), _stream())
+    _lib.check(rc, "mnv_step")
+
+
+def observe(buf, params, mask=None, velocity_from_state=False, obs=None):
+    """MarineNavEnv.get_observation for the (masked) batch."""
+    E = buf["state"].shape[1]
+    max_c, max_o = buf["cores"].shape[0] // 3, buf["obstacles"].shape[0] // 3
+    obs = buf["obs"] if obs is None else obs
+    _chk(obs, torch.float32, (E, 4 + 2 * params.n_beams), "obs")
+    if mask is not None:
+        _chk(mask, torch.uint8, (E,), "mask")
+    rc = _lib.load().mnv_observe(_lib.ptr(buf["state"]), _lib.ptr(buf["velocity"]), _lib.ptr(buf["goal"]),
+                                 _lib.ptr(buf["cores"]), _lib.ptr(buf["obstacles"]), _lib.ptr(mask), _lib.ptr(obs),
+                                 E, max_c, max_o, C.byref(params), int(bool(velocity_from_state)), _stream())
+    _lib.check(rc, "mnv_observe")
+
+
+def seed(rng_key, rng_pos, seeds):
+    """RandomState(seed) per environment (MarineNavEnv.seed)."""
+    E = seeds.shape[0]
+    _chk(rng_key, torch.int32, (624, E), "rng_key"); _chk(rng_pos, torch.int32, (E,), "rng_pos")
+    _chk(seeds, torch.int32, (E,), "seeds")   # bit pattern of u32 seeds
+    rc = _lib.load().mnv_seed(_lib.ptr(rng_key), _lib.ptr(rng_pos), _lib.ptr(seeds), E, _stream())
+    _lib.check(rc, "mnv_seed")
+
+
+def reset(buf, rng_key, rng_pos, reset_params, mask=None):
+    """MarineNavEnv.reset (map generation + robot draws) for the (masked) batch; follow with observe(velocity_from_state=True)."""
+    E = buf["state"].shape[1]
+    max_c, max_o = buf["cores"].shape[0] // 3, buf["obstacles"].shape[0] // 3
+    if mask is not None:
+        _chk(mask, torch.uint8, (E,), "mask")
+    rc = _lib.load().mnv_reset(_lib.ptr(rng_key), _lib.ptr(rng_pos), _lib.ptr(mask), _lib.ptr(buf["state"]),
+                               _lib.ptr(buf["goal"]), _lib.ptr(buf["cores"]), _lib.ptr(buf["obstacles"]),
+                               _lib.ptr(buf["start_pose"]), _lib.ptr(buf["episode_step"]), _lib.ptr(buf["n_placed"]),
+                               E, max_c, max_o, C.byref(reset_params), _stream())
+    _lib.check(rc, "mnv_reset")

@@ -1,0 +1,174 @@
+"""VecMarineNavEnv: E independent marinenav environments resident on one B200, stepped by one fused kernel.
+
+The attribute names and defaults mirror the reference's MarineNavEnv / Robot / Sonar (marinenav_env.py:27-73,
+robot.py:5-49) so that code written against the reference env finds the same knobs; the per-environment state lives in
+device tensors laid out as include/marinenav_b200.h describes.  Environment e uses its own numpy-compatible MT19937
+stream seeded with ``seed + e`` -> its maps are the ones ``MarineNavEnv(seed=seed + e)`` of the reference generates.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, env_ops
+
+INFO_STRINGS = _lib.INFO_STRINGS
+
+
+class VecMarineNavEnv:
+    def __init__(self, num_envs, seed=0, schedule=None, device="cuda:0", num_cores=8, num_obs=5, min_start_goal_dis=25.0,
+                 num_beams=11, max_cores=None, max_obstacles=None):
+        if not torch.cuda.is_available():
+            raise _lib.MarinenavError("VecMarineNavEnv needs a CUDA device (there is no CPU fallback)")
+        _lib.load()
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.sd = seed
+        self.schedule = schedule
+        # --- MarineNavEnv.__init__ (marinenav_env.py:40-73) ---
+        self.width, self.height, self.r = 50.0, 50.0, 0.5
+        self.v_rel_max, self.p = 1.0, 0.8
+        self.v_range, self.obs_r_range, self.clear_r = [5, 10], [1, 3], 10.0
+        self.reset_start_and_goal = True
+        self.start, self.goal = np.array([5.0, 5.0]), np.array([45.0, 45.0])
+        self.random_reset_state = True
+        self.init_speed, self.init_theta = 0.0, math.pi / 4
+        self.goal_dis = 2.0
+        self.timestep_penalty, self.collision_penalty, self.goal_reward = -1.0, -50.0, 100.0
+        self.discount = 0.99
+        self.num_cores, self.num_obs, self.min_start_goal_dis = num_cores, num_obs, min_start_goal_dis
+        self.total_timesteps = 0          # env steps taken over ALL environments (curriculum key, marinenav_env.py:89-98)
+        self.set_boundary = False
+        # --- Robot / Sonar (robot.py:7-9,28-37) ---
+        self.dt, self.N = 0.1, 10
+        self.robot_r, self.max_speed = 0.8, 2.0
+        self.a = np.array([-0.4, 0.0, 0.4])
+        self.w = np.array([-np.pi / 6, 0.0, np.pi / 6])
+        self.sonar_range, self.sonar_angle, self.num_beams = 10.0, 2 * np.pi / 3, int(num_beams)
+
+        if schedule is not None:
+            max_cores = max_cores or max(schedule["num_cores"])
+            max_obstacles = max_obstacles or max(schedule["num_obstacles"])
+        self.max_cores = int(max_cores if max_cores is not None else num_cores)
+        self.max_obstacles = int(max_obstacles if max_obstacles is not None else num_obs)
+        E = self.num_envs
+        with torch.cuda.device(self.device):
+            self.buf = env_ops.alloc_env_buffers(E, self.max_cores, self.max_obstacles, self.num_beams, self.device)
+            self.buf["next_obs"] = torch.zeros_like(self.buf["obs"])
+            self.rng_key = torch.zeros(624, E, dtype=torch.int32, device=self.device)
+            self.rng_pos = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self._pinned = None
+        self.seed(seed)
+
+    # ---- gym-style surface -------------------------------------------------------------------------------------
+    @property
+    def obs_dim(self):
+        return 4 + 2 * self.num_beams
+
+    def get_state_space_dimension(self):
+        return self.obs_dim
+
+    def get_action_space_dimension(self):
+        return 9
+
+    def seed(self, seed):
+        """MarineNavEnv.seed per environment: stream e = RandomState(seed + e)."""
+        self.sd = seed
+        seeds = (np.arange(self.num_envs, dtype=np.int64) + int(seed)) % (1 << 32)
+        with torch.cuda.device(self.device):
+            env_ops.seed(self.rng_key, self.rng_pos,
+                         torch.from_numpy(seeds.astype(np.uint32).view(np.int32)).to(self.device))
+        return [seed]
+
+    def params(self):
+        p = _lib.default_params(self.num_beams)
+        p.dt, p.n_substeps = self.dt, self.N
+        for i in range(3):
+            p.accel[i], p.yaw_rate[i] = float(self.a[i]), float(self.w[i])
+        p.max_speed = self.max_speed
+        p.k_drag = float(np.max(self.a)) / self.max_speed                      # Robot.compute_k, robot.py:51-52
+        p.robot_r, p.core_r, p.goal_dis = self.robot_r, self.r, self.goal_dis
+        p.timestep_penalty, p.collision_penalty, p.goal_reward = self.timestep_penalty, self.collision_penalty, self.goal_reward
+        p.sonar_range, p.sonar_angle = self.sonar_range, self.sonar_angle
+        p.set_boundary, p.width, p.height = int(self.set_boundary), self.width, self.height
+        return p
+
+    def reset_params(self):
+        if self.schedule is not None:                                           # marinenav_env.py:89-98
+            steps = np.array(self.schedule["timesteps"])
+            idx = int((steps - self.total_timesteps <= 0).sum()) - 1
+            self.num_cores = self.schedule["num_cores"][idx]
+            self.num_obs = self.schedule["num_obstacles"][idx]
+            self.min_start_goal_dis = self.schedule["min_start_goal_dis"][idx]
+        r = _lib.default_reset_params()
+        r.width, r.height, r.core_r, r.v_rel_max, r.p = self.width, self.height, self.r, self.v_rel_max, self.p
+        r.v_range[0], r.v_range[1] = self.v_range
+        r.obs_r_range[0], r.obs_r_range[1] = self.obs_r_range
+        r.clear_r = self.clear_r
+        r.reset_start_and_goal = int(self.reset_start_and_goal)
+        r.start[0], r.start[1] = float(self.start[0]), float(self.start[1])
+        r.goal[0], r.goal[1] = float(self.goal[0]), float(self.goal[1])
+        r.random_reset_state, r.init_theta, r.init_speed = int(self.random_reset_state), self.init_theta, self.init_speed
+        r.max_speed = self.max_speed
+        r.num_cores, r.num_obs, r.min_start_goal_dis = int(self.num_cores), int(self.num_obs), float(self.min_start_goal_dis)
+        return r
+
+    def reset(self, mask=None):
+        """MarineNavEnv.reset for all (or the masked) environments; returns the observation tensor f32 [E, obs_dim]."""
+        with torch.cuda.device(self.device):
+            env_ops.reset(self.buf, self.rng_key, self.rng_pos, self.reset_params(), mask=mask)
+            env_ops.observe(self.buf, self.params(), mask=mask, velocity_from_state=True)
+        return self.buf["obs"]
+
+    def step(self, actions, auto_reset=True):
+        """actions: CUDA int32 [E].  Returns (obs, reward, done, info) device tensors.
+
+        With auto_reset (the VecEnv convention) environments that finished are reset and ``obs`` holds the first
+        observation of their next episode, while ``self.buf['next_obs']`` keeps the step's own (terminal) observation --
+        what IQNAgent.learn stores as next_state before it calls reset() (agent.py:122-124,170)."""
+        b = self.buf
+        with torch.cuda.device(self.device):
+            env_ops.step(b, self.params(), action=actions, obs=b["next_obs"])
+            self.total_timesteps += self.num_envs
+            b["obs"].copy_(b["next_obs"])
+            if auto_reset:
+                env_ops.reset(b, self.rng_key, self.rng_pos, self.reset_params(), mask=b["done"])
+                env_ops.observe(b, self.params(), mask=b["done"], velocity_from_state=True)
+        return b["obs"], b["reward"], b["done"], b["info"]
+
+    # ---- host-buffer surface (numpy in / numpy out, pinned staging) ------------------------------------------------
+    def _pin(self):
+        if self._pinned is None:
+            E, D = self.num_envs, self.obs_dim
+            self._pinned = dict(action=torch.zeros(E, dtype=torch.int32).pin_memory(),
+                                obs=torch.zeros(E, D, dtype=torch.float32).pin_memory(),
+                                reward=torch.zeros(E, dtype=torch.float32).pin_memory(),
+                                done=torch.zeros(E, dtype=torch.uint8).pin_memory(),
+                                info=torch.zeros(E, dtype=torch.uint8).pin_memory())
+        return self._pinned
+
+    def step_host(self, actions, auto_reset=True):
+        """numpy int actions [E] -> (obs f32 [E,D], reward f32 [E], done bool [E], info u8 [E]) numpy views of pinned buffers."""
+        pin = self._pin()
+        pin["action"].copy_(torch.as_tensor(actions, dtype=torch.int32))
+        with torch.cuda.device(self.device):
+            self.buf["action"].copy_(pin["action"], non_blocking=True)
+            obs, reward, done, info = self.step(self.buf["action"], auto_reset=auto_reset)
+            pin["obs"].copy_(obs, non_blocking=True); pin["reward"].copy_(reward, non_blocking=True)
+            pin["done"].copy_(done, non_blocking=True); pin["info"].copy_(info, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().astype(bool), pin["info"].numpy()
+
+    def reset_host(self):
+        pin = self._pin()
+        pin["obs"].copy_(self.reset())
+        return pin["obs"].numpy()
+
+    def h2d_bytes_per_step(self):
+        return self.num_envs * 4
+
+    def d2h_bytes_per_step(self):
+        return self.num_envs * (self.obs_dim * 4 + 4 + 1 + 1)
+
+    def close(self):
+        pass

@@ -1,0 +1,114 @@
+/*
+ * marinenav_b200.h -- C-ABI of libmarinenav_b200.so: the B200 (sm_100a) implementation of the hot path of
+ * RobustFieldAutonomyLab/Distributional_RL_Navigation (reference @ e77bbbf):
+ *     marinenav_env/envs/marinenav_env.py  MarineNavEnv.step / reset / get_observation
+ *     marinenav_env/envs/utils/robot.py    Robot.update_state / sonar_reflection
+ *     thirdparty/IQN/model.py, agent.py    ObsEncoder.forward / get_qvals, IQNAgent.act / train
+ *
+ * The reference has no FFI of its own (pure Python); these entry points are what a ctypes binding inside the
+ * reference's MarineNavEnv / IQNAgent would call (INTEGRATION.md shows that binding).  Conventions:
+ *   - extern "C", plain pointers + sizes, no C++/torch types.  Pointers named d_* are DEVICE pointers
+ *     (e.g. torch.Tensor.data_ptr()); the caller owns all memory, the library allocates nothing persistent.
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     no host synchronisation inside.
+ *   - return 0 = ok; > 0 = cudaError_t of the launch; < 0 = argument error (MNV_E_*).  mnv_last_error_string()
+ *     describes the last failure of the calling thread.
+ *
+ * Device data layout ("SoA by field", E = number of environments, every array 16-byte aligned):
+ *   d_state      f64 [4][E]        x, y, theta, speed                        (robot.py:41-45)
+ *   d_velocity   f64 [2][E]        robot.velocity wrt sea floor, world frame (robot.py:98-100)
+ *   d_goal       f64 [2][E]        goal position                             (marinenav_env.py:54)
+ *   d_cores      f64 [3*max_c][E]  rows x_0..x_{max_c-1}, y_0.., Gs_0..  Gs = +Gamma if clockwise else -Gamma,
+ *                                  Gs == 0 <=> empty slot                    (marinenav_env.py:8-15)
+ *   d_obstacles  f64 [3*max_o][E]  rows x_j, y_j, r_j ; r_j <= 0 <=> empty slot; LIST ORDER IS SEMANTIC (robot.py:149,192)
+ *   d_action     i32 [E]           0..8 = (a_idx*3 + w_idx)                  (robot.py:54-55)
+ *   d_episode_step i32 [E]         MarineNavEnv.episode_timesteps            (marinenav_env.py:69,259)
+ *   d_obs        f32 [E][4+2*n_beams] row-major: velocity_r(2), goal_r(2), per beam hit_r(2) or (0,0) (marinenav_env.py:273-326)
+ *   d_reward     f32 [E] ; d_done u8 [E] ; d_info u8 [E] (MNV_INFO_*)        (marinenav_env.py:240-257)
+ */
+#ifndef MARINENAV_B200_H
+#define MARINENAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNV_VERSION        100
+#define MNV_MAX_CORES      8      /* compiled capacity of the fused step kernel */
+#define MNV_MAX_OBSTACLES  32
+#define MNV_MAX_BEAMS      128
+
+/* info codes <-> info["state"] strings of marinenav_env.py:243,246,250,254,257 */
+enum { MNV_INFO_NORMAL = 0, MNV_INFO_TOO_LONG = 1, MNV_INFO_COLLISION = 2, MNV_INFO_REACH_GOAL = 3, MNV_INFO_OUT_OF_BOUNDARY = 4 };
+
+enum { MNV_E_NULL = -1, MNV_E_ALIGN = -2, MNV_E_SIZE = -3, MNV_E_CAPACITY = -4, MNV_E_PARAM = -5 };
+
+/* Robot / sonar / reward constants.  Defaults = robot.py:7-9,28-37 and marinenav_env.py:40-64,244. */
+typedef struct mnv_params {
+    double dt; int32_t n_substeps;                    /* Robot.dt, Robot.N */
+    double accel[3], yaw_rate[3];                     /* Robot.a, Robot.w ; action = 3*a_idx + w_idx */
+    double k_drag, max_speed;                         /* Robot.k = max(a)/max_speed, Robot.max_speed */
+    double robot_r, core_r, goal_dis;                 /* Robot.r, MarineNavEnv.r, MarineNavEnv.goal_dis */
+    double timestep_penalty, collision_penalty, goal_reward;
+    double sonar_range, sonar_angle; int32_t n_beams; /* Sonar.range, .angle, .num_beams */
+    int32_t max_episode_steps;                        /* 1000, marinenav_env.py:244 */
+    int32_t set_boundary; double width, height;       /* marinenav_env.py:73,40-41 */
+} mnv_params;
+
+/* Map-generation constants of MarineNavEnv.reset (marinenav_env.py:40-64,86-197). */
+typedef struct mnv_reset_params {
+    double width, height, core_r, v_rel_max, p;
+    double v_range[2], obs_r_range[2], clear_r;
+    int32_t reset_start_and_goal; double start[2], goal[2];
+    int32_t random_reset_state; double init_theta, init_speed, max_speed;
+    int32_t num_cores, num_obs; double min_start_goal_dis;
+} mnv_reset_params;
+
+int         mnv_version(void);
+const char* mnv_last_error_string(void);
+void        mnv_default_params(mnv_params* p);
+void        mnv_default_reset_params(mnv_reset_params* p);
+
+/* MarineNavEnv.step (marinenav_env.py:199-262) for E environments: N sub-steps of get_velocity (:422-455) +
+ * Robot.update_state (robot.py:102-123), then get_observation (:273-326, sonar robot.py:125-198), reward and the
+ * termination priority of :240-257.  In/out: d_state, d_episode_step (+1).  Out: d_velocity (last sub-step's, Q6),
+ * d_obs, d_reward, d_done, d_info.  ONE kernel launch. */
+int mnv_step(double* d_state, double* d_velocity, const double* d_goal, const double* d_cores, const double* d_obstacles,
+             const int32_t* d_action, int32_t* d_episode_step,
+             float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_info,
+             int64_t E, int32_t max_c, int32_t max_o, const mnv_params* p, void* stream);
+
+/* MarineNavEnv.get_observation (marinenav_env.py:273-326) of the current state, for every environment with
+ * d_mask[e] != 0 (d_mask == NULL: all); rows of masked-out environments are left untouched.  If velocity_from_state != 0
+ * the velocity is first set to steer + current(position) and written to d_velocity -- what reset_robot /
+ * Robot.reset_state leave behind (marinenav_env.py:196-197, robot.py:79-87). */
+int mnv_observe(const double* d_state, double* d_velocity, const double* d_goal, const double* d_cores,
+                const double* d_obstacles, const uint8_t* d_mask, float* d_obs, int64_t E, int32_t max_c, int32_t max_o,
+                const mnv_params* p, int32_t velocity_from_state, void* stream);
+
+/* numpy.random.RandomState(seed) per environment (MarineNavEnv.seed, marinenav_env.py:75-78): legacy MT19937.
+ *   d_rng_key u32 [624][E], d_rng_pos i32 [E].  d_seeds u32 [E]. */
+int mnv_seed(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint32_t* d_seeds, int64_t E, void* stream);
+
+/* MarineNavEnv.reset (marinenav_env.py:86-186) for every environment with d_mask[e] != 0 (d_mask == NULL: all):
+ * start/goal sampling, vortex-core and obstacle rejection sampling (check_core :344-383, check_obstacle :385-420),
+ * reset_robot's draws (:188-192), taken from each environment's own MT19937 stream in the reference's draw order, so
+ * that environment e reproduces MarineNavEnv(seed=seeds[e]).reset() bit-for-bit (tables, start, goal, theta0, speed0).
+ * Writes d_state (start x, y, theta0, speed0), d_goal, d_cores, d_obstacles, d_start_pose f64 [4][E] (optional: start x,
+ * y, init theta, init speed -- Robot.init_theta/init_speed, needed by reset_with_eval_config-style restarts),
+ * d_episode_step = 0 (optional), d_n_placed u8 [2][E] (optional: cores, obstacles actually placed, Q8).
+ * Does NOT write velocity / observation: follow with mnv_observe(mask, velocity_from_state = 1) -- reset_robot's
+ * robot.reset_state (marinenav_env.py:196-197) + get_observation (:186).
+ * rp->reset_start_and_goal == 0: start/goal = rp->start / rp->goal for all environments, unless rp->start[0] is NaN,
+ * which keeps each environment's own d_start_pose[0:2] / d_goal. */
+int mnv_reset(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint8_t* d_mask,
+              double* d_state, double* d_goal, double* d_cores, double* d_obstacles,
+              double* d_start_pose, int32_t* d_episode_step, uint8_t* d_n_placed,
+              int64_t E, int32_t max_c, int32_t max_o, const mnv_reset_params* rp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
