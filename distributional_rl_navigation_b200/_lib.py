@@ -50,6 +50,13 @@ _SIGNATURES = {
     "mnv_observe": (C.c_int, [_vp] * 7 + [_i64, _i32, _i32, C.POINTER(MnvParams), _i32, _vp]),
     "mnv_seed": (C.c_int, [_vp] * 3 + [_i64, _vp]),
     "mnv_reset": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, C.POINTER(MnvResetParams), _vp]),
+    "iqn_param_count": (C.c_int, []),
+    "iqn_packed_count": (C.c_int, []),
+    "iqn_pack": (C.c_int, [_vp, _vp, _vp]),
+    "iqn_forward": (C.c_int, [_vp] * 5 + [C.c_float] + [_vp] * 3 + [_i64, _i32, _vp]),
+    "iqn_train_scratch_floats": (C.c_int64, [_i64]),
+    "iqn_loss_grad": (C.c_int, [_vp] * 11 + [C.c_float] + [_vp] * 3 + [_i64, _vp]),
+    "iqn_clip_adam": (C.c_int, [_vp] * 5 + [C.c_float] * 6 + [_i64, _vp, _vp]),
 }
 
 _lib = None

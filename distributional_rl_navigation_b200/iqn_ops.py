@@ -1,0 +1,88 @@
+"""Tensor-level wrappers over the IQN entry points of libmarinenav_b200 (include/marinenav_b200.h)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+N_PARAMS = 35785
+N_PACKED = 30720
+N_ACTIONS = 9
+OBS_DIM = 26
+
+# ObsEncoder.state_dict() order and shapes (thirdparty/IQN/model.py:125-136)
+PARAM_SPECS = [
+    ("velocity_encoder.weight", (16, 2)), ("velocity_encoder.bias", (16,)),
+    ("goal_encoder.weight", (16, 2)), ("goal_encoder.bias", (16,)),
+    ("sensor_encoder.weight", (176, 22)), ("sensor_encoder.bias", (176,)),
+    ("cos_embedding.weight", (208, 64)), ("cos_embedding.bias", (208,)),
+    ("hidden_layer.weight", (64, 208)), ("hidden_layer.bias", (64,)),
+    ("hidden_layer_2.weight", (64, 64)), ("hidden_layer_2.bias", (64,)),
+    ("output_layer.weight", (9, 64)), ("output_layer.bias", (9,)),
+]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, n, name):
+    if t is None or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+        raise _lib.MarinenavError(f"{name}: expected contiguous CUDA float32 with {n} elements, got "
+                                  f"{None if t is None else (t.device, t.dtype, tuple(t.shape))}")
+
+
+def pack(params, packed):
+    _f32(params, N_PARAMS, "params"); _f32(packed, N_PACKED, "packed")
+    _lib.check(_lib.load().iqn_pack(_lib.ptr(params), _lib.ptr(packed), _stream()), "iqn_pack")
+
+
+def forward(params, packed, obs, taus, cvar=1.0, want_quantiles=True, want_qmean=False, want_greedy=False):
+    """ObsEncoder.forward / get_qvals.  obs f32 [B,26], taus f32 [B,n_tau] uniform samples; cvar float or f32 [B]."""
+    B, n_tau = taus.shape
+    _f32(params, N_PARAMS, "params"); _f32(packed, N_PACKED, "packed")
+    _f32(obs, B * OBS_DIM, "obs"); _f32(taus, B * n_tau, "taus")
+    dev = obs.device
+    cvar_t, cvar_s = (cvar, 1.0) if torch.is_tensor(cvar) else (None, float(cvar))
+    if cvar_t is not None:
+        _f32(cvar_t, B, "cvar")
+    q = torch.empty(B, n_tau, N_ACTIONS, dtype=torch.float32, device=dev) if want_quantiles else None
+    qm = torch.empty(B, N_ACTIONS, dtype=torch.float32, device=dev) if want_qmean else None
+    gr = torch.empty(B, dtype=torch.int32, device=dev) if want_greedy else None
+    rc = _lib.load().iqn_forward(_lib.ptr(params), _lib.ptr(packed), _lib.ptr(obs), _lib.ptr(taus), _lib.ptr(cvar_t),
+                                 C.c_float(cvar_s), _lib.ptr(q), _lib.ptr(qm), _lib.ptr(gr), B, n_tau, _stream())
+    _lib.check(rc, "iqn_forward")
+    return q, qm, gr
+
+
+def train_scratch_floats(B):
+    return int(_lib.load().iqn_train_scratch_floats(B))
+
+
+def loss_grad(params_l, packed_l, params_t, packed_t, states, actions, rewards, next_states, dones, taus_t, taus_l,
+              gamma_n, scratch, loss, grad):
+    B = states.shape[0]
+    _f32(params_l, N_PARAMS, "params_local"); _f32(params_t, N_PARAMS, "params_target")
+    _f32(packed_l, N_PACKED, "packed_local"); _f32(packed_t, N_PACKED, "packed_target")
+    _f32(states, B * OBS_DIM, "states"); _f32(next_states, B * OBS_DIM, "next_states")
+    _f32(rewards, B, "rewards"); _f32(dones, B, "dones"); _f32(taus_t, B * 8, "taus_target"); _f32(taus_l, B * 8, "taus_local")
+    if actions.dtype != torch.int64 or actions.numel() != B or not actions.is_cuda or not actions.is_contiguous():
+        raise _lib.MarinenavError("actions: expected contiguous CUDA int64 [B]")
+    _f32(grad, N_PARAMS, "grad"); _f32(loss, 1, "loss")
+    if scratch.numel() < train_scratch_floats(B):
+        raise _lib.MarinenavError("scratch too small")
+    rc = _lib.load().iqn_loss_grad(_lib.ptr(params_l), _lib.ptr(packed_l), _lib.ptr(params_t), _lib.ptr(packed_t),
+                                   _lib.ptr(states), _lib.ptr(actions), _lib.ptr(rewards), _lib.ptr(next_states),
+                                   _lib.ptr(dones), _lib.ptr(taus_t), _lib.ptr(taus_l), C.c_float(gamma_n),
+                                   _lib.ptr(scratch), _lib.ptr(loss), _lib.ptr(grad), B, _stream())
+    _lib.check(rc, "iqn_loss_grad")
+
+
+def clip_adam(params, grad, m, v, packed, step, lr=1e-4, max_norm=0.5, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-8,
+              grad_norm=None):
+    for t, n in ((params, "params"), (grad, "grad"), (m, "m"), (v, "v")):
+        _f32(t, N_PARAMS, n)
+    rc = _lib.load().iqn_clip_adam(_lib.ptr(params), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), _lib.ptr(packed),
+                                   C.c_float(grad_scale), C.c_float(max_norm), C.c_float(lr), C.c_float(beta1),
+                                   C.c_float(beta2), C.c_float(eps), int(step), _lib.ptr(grad_norm), _stream())
+    _lib.check(rc, "iqn_clip_adam")

@@ -108,6 +108,43 @@ int mnv_reset(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint8_t* d_mask,
               double* d_start_pose, int32_t* d_episode_step, uint8_t* d_n_placed,
               int64_t E, int32_t max_c, int32_t max_o, const mnv_reset_params* rp, void* stream);
 
+/* ======================================= IQN (thirdparty/IQN) ============================================
+ * Parameters: ONE flat fp32 vector of iqn_param_count() = 35 785 floats = the 14 tensors of ObsEncoder.state_dict() in
+ * order (velocity_encoder.weight [16,2], .bias, goal_encoder.*, sensor_encoder.* [176,22], cos_embedding.* [208,64],
+ * hidden_layer.* [64,208], hidden_layer_2.* [64,64], output_layer.* [9,64]; model.py:125-136), torch [out][in] layout.
+ * d_packed: iqn_packed_count() floats of kernel-side transposes; refresh with iqn_pack after ANY parameter change. */
+int     iqn_param_count(void);
+int     iqn_packed_count(void);
+int     iqn_pack(const float* d_params, float* d_packed, void* stream);
+
+/* ObsEncoder.forward / get_qvals (model.py:160-191) with caller-provided uniform samples:
+ *   d_obs f32 [B][26]; d_taus f32 [B][n_tau] in [0,1) (torch.rand of model.py:149); tau <- tau * cvar (model.py:153) with
+ *   cvar = d_cvar[b] if d_cvar != NULL (adaptive CVaR, agent.py:249-267) else cvar_scalar.  n_tau in {8,16,32,64}.
+ * Outputs (each optional): d_quantiles f32 [B][n_tau][9]; d_qmean f32 [B][9] = mean over taus; d_greedy i32 [B] =
+ * argmax_a qmean (first maximum, like np.argmax at agent.py:201). */
+int     iqn_forward(const float* d_params, const float* d_packed, const float* d_obs, const float* d_taus,
+                    const float* d_cvar, float cvar_scalar, float* d_quantiles, float* d_qmean, int32_t* d_greedy,
+                    int64_t B, int32_t n_tau, void* stream);
+
+/* IQNAgent.train up to loss.backward() (agent.py:276-298): target forward on next_states with d_taus_target (drawn
+ * first, Q9), local forward on states with d_taus_local (both f32 [B][8]), T = r + gamma_n (1-done) max_a Q', pairwise
+ * quantile Huber loss, full backward of the local network.  d_actions i64 [B]; rewards/dones f32 [B].
+ * d_scratch: iqn_train_scratch_floats(B) floats.  Writes d_loss (1 float) and d_grad (35 785 floats, unclipped). */
+int64_t iqn_train_scratch_floats(int64_t B);
+int     iqn_loss_grad(const float* d_params_local, const float* d_packed_local, const float* d_params_target,
+                      const float* d_packed_target, const float* d_states, const int64_t* d_actions,
+                      const float* d_rewards, const float* d_next_states, const float* d_dones,
+                      const float* d_taus_target, const float* d_taus_local, float gamma_n,
+                      float* d_scratch, float* d_loss, float* d_grad, int64_t B, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.Adam.step (agent.py:66,299-300) on the flat vectors;
+ * the gradient is first multiplied by grad_scale (1/world_size after a summing all-reduce).  step = number of optimizer
+ * steps including this one.  d_grad_norm (optional) receives the pre-clip total norm.  If d_packed != NULL it is
+ * refreshed from the updated parameters. */
+int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d_v, float* d_packed,
+                      float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
+                      float* d_grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

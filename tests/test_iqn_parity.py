@@ -1,0 +1,125 @@
+"""GPU parity: the IQN CUDA kernels (through the C-ABI) against fixtures recorded from the reference's PyTorch path and
+the numpy oracle.  north_star tolerance: loss within 1e-4 (relative); here 2e-5, gradients 5e-5 of the largest entry."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from distributional_rl_navigation_b200 import iqn_ops  # noqa: E402
+from oracle import iqn_oracle as io  # noqa: E402
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "iqn_kat.npz"))
+
+
+@pytest.fixture(scope="module")
+def weights(golden_dir):
+    w = np.load(os.path.join(golden_dir, "iqn_weights.npz"))
+    return {k: w[k] for k in w.files}
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV).to(dtype).contiguous()
+
+
+def packed_of(flat):
+    p = torch.empty(iqn_ops.N_PACKED, dtype=torch.float32, device=DEV)
+    iqn_ops.pack(flat, p)
+    return p
+
+
+@pytest.mark.parametrize("K", [8, 32])
+@pytest.mark.parametrize("cvar", [1.0, 0.37])
+def test_forward_matches_reference(kat, weights, K, cvar):
+    tag = f"K{K}_cvar{str(cvar).replace('.', 'p')}"
+    flat = dev(io.flatten(weights))
+    q, qm, gr = iqn_ops.forward(flat, packed_of(flat), dev(kat["fwd_x"]), dev(kat[f"fwd_taus_{tag}"]), cvar,
+                                want_qmean=True, want_greedy=True)
+    ref = kat[f"fwd_q_{tag}"]
+    assert np.abs(q.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    np.testing.assert_allclose(qm.cpu().numpy(), ref.mean(axis=1), rtol=1e-5, atol=1e-4)
+    ref_mean = ref.mean(axis=1)
+    top2 = np.sort(ref_mean, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-3            # argmax is only defined up to ties
+    assert np.array_equal(gr.cpu().numpy()[clear], ref_mean.argmax(axis=1)[clear])
+
+
+def test_forward_per_sample_cvar_and_ragged_batch(weights):
+    rs = np.random.RandomState(3)
+    B = 37                                              # not a multiple of the tile's sample count
+    x = (rs.randn(B, 26) * 3).astype(np.float32); taus = rs.rand(B, 32).astype(np.float32)
+    cvar = rs.uniform(0.05, 1.0, size=B).astype(np.float32)
+    flat = dev(io.flatten(weights))
+    q, _, _ = iqn_ops.forward(flat, packed_of(flat), dev(x), dev(taus), dev(cvar))
+    ref = np.stack([io.forward(weights, x[b:b + 1], taus[b:b + 1], cvar[b])[0] for b in range(B)])
+    assert np.abs(q.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("B", [32, 1024])
+def test_train_loss_grad_adam_vs_reference(kat, weights, B):
+    flat = dev(io.flatten(weights)); target = dev(kat[f"target_flat_B{B}"])
+    packed, packed_t = packed_of(flat), packed_of(target)
+    names = ("states", "actions", "rewards", "next_states", "dones")
+    st, ac, rw, ns, dn = [kat[f"{n}_B{B}"] for n in names]
+    st_d, ns_d = dev(st), dev(ns)
+    ac_d = dev(ac.reshape(B), torch.int64); rw_d = dev(rw.reshape(B)); dn_d = dev(dn.reshape(B))
+    taus = kat[f"taus_B{B}"]
+    scratch = torch.empty(iqn_ops.train_scratch_floats(B), dtype=torch.float32, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float32, device=DEV); grad = torch.zeros(iqn_ops.N_PARAMS, dtype=torch.float32, device=DEV)
+    m = torch.zeros_like(grad); v = torch.zeros_like(grad); gn = torch.zeros(1, dtype=torch.float32, device=DEV)
+    for k in range(3):
+        iqn_ops.loss_grad(flat, packed, target, packed_t, st_d, ac_d, rw_d, ns_d, dn_d, dev(taus[2 * k]), dev(taus[2 * k + 1]),
+                          0.99, scratch, loss, grad)
+        ref_loss = float(kat[f"losses_B{B}"][k])
+        assert abs(loss.item() - ref_loss) <= 2e-5 * abs(ref_loss), (loss.item(), ref_loss)
+        if k == 0:
+            ref_g = kat[f"grad_B{B}"]
+            err = np.abs(grad.cpu().numpy() - ref_g)
+            assert err.max() <= 5e-5 * np.abs(ref_g).max(), err.max() / np.abs(ref_g).max()
+        iqn_ops.clip_adam(flat, grad, m, v, packed, step=k + 1, grad_norm=gn)
+        if k == 0:
+            assert abs(gn.item() - float(kat[f"gradnorm_B{B}"])) <= 2e-5 * float(kat[f"gradnorm_B{B}"])
+            np.testing.assert_allclose(flat.cpu().numpy(), kat[f"params_after1_B{B}"], rtol=0, atol=5e-7)
+    np.testing.assert_allclose(flat.cpu().numpy(), kat[f"params_after3_B{B}"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(m.cpu().numpy(), kat[f"adam_m_after3_B{B}"], rtol=2e-3, atol=1e-8)
+    # packed transposes were refreshed by clip_adam
+    assert torch.equal(packed, packed_of(flat))
+
+
+def test_train_ragged_batch_vs_oracle(weights):
+    """B = 20 (not a multiple of the 8-sample tile): padded rows must not leak into loss or gradient."""
+    rs = np.random.RandomState(11)
+    B = 20
+    st = (rs.randn(B, 26) * 3).astype(np.float32); ns = (rs.randn(B, 26) * 3).astype(np.float32)
+    ac = rs.randint(0, 9, size=B); rw = rs.randn(B).astype(np.float32); dn = (rs.rand(B) < 0.3).astype(np.float32)
+    tt, tl = rs.rand(B, 8).astype(np.float32), rs.rand(B, 8).astype(np.float32)
+    P_t = {k: (v + 0.01 * rs.randn(*v.shape)).astype(np.float32) for k, v in weights.items()}
+    ref_loss, ref_grad = io.loss_and_grad(weights, P_t, st, ac, rw, ns, dn, tt, tl)
+    flat, target = dev(io.flatten(weights)), dev(io.flatten(P_t))
+    scratch = torch.empty(iqn_ops.train_scratch_floats(B), dtype=torch.float32, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float32, device=DEV); grad = torch.zeros(iqn_ops.N_PARAMS, dtype=torch.float32, device=DEV)
+    iqn_ops.loss_grad(flat, packed_of(flat), target, packed_of(target), dev(st), dev(ac, torch.int64), dev(rw), dev(ns), dev(dn),
+                      dev(tt), dev(tl), 0.99, scratch, loss, grad)
+    assert abs(loss.item() - ref_loss) <= 2e-5 * abs(ref_loss)
+    assert np.abs(grad.cpu().numpy() - ref_grad).max() <= 5e-5 * np.abs(ref_grad).max()
+
+
+def test_train_is_deterministic(kat, weights):
+    B = 1024
+    flat = dev(io.flatten(weights)); target = dev(kat[f"target_flat_B{B}"])
+    args = [dev(kat[f"states_B{B}"]), dev(kat[f"actions_B{B}"].reshape(B), torch.int64), dev(kat[f"rewards_B{B}"].reshape(B)),
+            dev(kat[f"next_states_B{B}"]), dev(kat[f"dones_B{B}"].reshape(B)), dev(kat[f"taus_B{B}"][0]), dev(kat[f"taus_B{B}"][1])]
+    scratch = torch.empty(iqn_ops.train_scratch_floats(B), dtype=torch.float32, device=DEV)
+    outs = []
+    for _ in range(2):
+        loss = torch.zeros(1, dtype=torch.float32, device=DEV); grad = torch.zeros(iqn_ops.N_PARAMS, dtype=torch.float32, device=DEV)
+        iqn_ops.loss_grad(flat, packed_of(flat), target, packed_of(target), *args, 0.99, scratch, loss, grad)
+        outs.append((loss.clone(), grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
