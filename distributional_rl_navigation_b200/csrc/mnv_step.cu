@@ -45,7 +45,7 @@ struct KParams {
 
 struct EnvPtrs {
     double* state; double* velocity; const double* goal; const double* cores; const double* obst;
-    const int32_t* action; int32_t* ep_step; const uint8_t* mask;
+    const int32_t* action; int32_t* ep_step; const uint8_t* mask; double* traj;
     float* obs; float* reward; uint8_t* done; uint8_t* info;
 };
 
@@ -123,6 +123,10 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
                 const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
                 c = c2; s = s2;
+                if (P.traj != nullptr) {                      // Robot.trajectory (marinenav_env.py:212), optional
+                    P.traj[(long long)(2 * it) * E + e] = x;
+                    P.traj[(long long)(2 * it + 1) * E + e] = y;
+                }
             }
             const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
             reward = K.pen_step + (dis_before - dis_after);   // marinenav_env.py:220,229
@@ -306,7 +310,7 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
 
 extern "C" int mnv_step(double* d_state, double* d_velocity, const double* d_goal, const double* d_cores,
                         const double* d_obstacles, const int32_t* d_action, int32_t* d_episode_step,
-                        float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_info,
+                        float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_info, double* d_trajectory,
                         int64_t E, int32_t max_c, int32_t max_o, const mnv_params* p, void* stream)
 {
     KParams K;
@@ -316,9 +320,10 @@ extern "C" int mnv_step(double* d_state, double* d_velocity, const double* d_goa
     if (max_c > 0) MNV_CHECK_PTR(d_cores);
     if (max_o > 0) MNV_CHECK_PTR(d_obstacles);
     MNV_CHECK_PTR(d_action); MNV_CHECK_PTR(d_episode_step); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_reward);
+    MNV_CHECK_PTR_OPT(d_trajectory);
     if (d_done == nullptr || d_info == nullptr) { mnv_set_error("mnv_step: null done/info"); return MNV_E_NULL; }
     if ((E & 1) != 0 && E != 1) { /* fp64 rows stay 8-byte aligned for any E; nothing to do */ }
-    EnvPtrs P{d_state, d_velocity, d_goal, d_cores, d_obstacles, d_action, d_episode_step, nullptr, d_obs, d_reward, d_done, d_info};
+    EnvPtrs P{d_state, d_velocity, d_goal, d_cores, d_obstacles, d_action, d_episode_step, nullptr, d_trajectory, d_obs, d_reward, d_done, d_info};
     return launch_env<true>(P, K, (cudaStream_t)stream);
 }
 
@@ -334,6 +339,6 @@ extern "C" int mnv_observe(const double* d_state, double* d_velocity, const doub
     if (max_c > 0) MNV_CHECK_PTR(d_cores);
     if (max_o > 0) MNV_CHECK_PTR(d_obstacles);
     MNV_CHECK_PTR(d_obs);
-    EnvPtrs P{const_cast<double*>(d_state), d_velocity, d_goal, d_cores, d_obstacles, nullptr, nullptr, d_mask, d_obs, nullptr, nullptr, nullptr};
+    EnvPtrs P{const_cast<double*>(d_state), d_velocity, d_goal, d_cores, d_obstacles, nullptr, nullptr, d_mask, nullptr, d_obs, nullptr, nullptr, nullptr};
     return launch_env<false>(P, K, (cudaStream_t)stream);
 }

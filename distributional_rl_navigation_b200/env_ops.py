@@ -37,7 +37,7 @@ def alloc_env_buffers(E, max_c, max_o, n_beams, device):
     )
 
 
-def step(buf, params, action=None, obs=None):
+def step(buf, params, action=None, obs=None, trajectory=None):
     """MarineNavEnv.step for the whole batch (one kernel). Results land in buf['obs'|'reward'|'done'|'info']."""
     E = buf["state"].shape[1]
     max_c, max_o = buf["cores"].shape[0] // 3, buf["obstacles"].shape[0] // 3
@@ -47,10 +47,13 @@ def step(buf, params, action=None, obs=None):
     _chk(buf["goal"], torch.float64, (2, E), "goal"); _chk(action, torch.int32, (E,), "action")
     _chk(buf["episode_step"], torch.int32, (E,), "episode_step")
     _chk(obs, torch.float32, (E, 4 + 2 * params.n_beams), "obs")
+    if trajectory is not None:
+        _chk(trajectory, torch.float64, (params.n_substeps, 2, E), "trajectory")
     rc = _lib.load().mnv_step(_lib.ptr(buf["state"]), _lib.ptr(buf["velocity"]), _lib.ptr(buf["goal"]),
                               _lib.ptr(buf["cores"]), _lib.ptr(buf["obstacles"]), _lib.ptr(action),
                               _lib.ptr(buf["episode_step"]), _lib.ptr(obs), _lib.ptr(buf["reward"]),
-                              _lib.ptr(buf["done"]), _lib.ptr(buf["info"]), E, max_c, max_o, C.byref(params), _stream())
+                              _lib.ptr(buf["done"]), _lib.ptr(buf["info"]), _lib.ptr(trajectory), E, max_c, max_o,
+                              C.byref(params), _stream())
     _lib.check(rc, "mnv_step")
 
 

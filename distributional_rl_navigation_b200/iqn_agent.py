@@ -1,0 +1,399 @@
+"""IQNAgent: host-side mirror of thirdparty/IQN/agent.py whose act / train run in the CUDA kernels.
+
+Drop-in surface (same names, argument meaning and defaults as agent.py:12-29,86-398): IQNAgent(...), learn, act,
+act_adaptive, act_eval, act_adaptive_eval, adjust_cvar, train, soft_update, evaluation, load_model, linear_eps and the
+attributes qnetwork_local / qnetwork_target / memory / current_timestep / learning_timestep / eval_*.  The single-env
+loop follows the reference's random choices (python `random` for epsilon-greedy and replay sampling, torch CPU generator
+for the taus, target taus drawn before local taus).  On top of it: act_batch / learn_vec drive a VecMarineNavEnv with
+everything (observations, replay, taus, epsilon-greedy) resident on the GPU, and train() all-reduces the flat gradient
+when torch.distributed is initialised (one NCCL all-reduce of 35 785 floats per update).
+"""
+import os
+import random
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib, distributed as mdist, iqn_ops
+from .iqn_model import ObsEncoder
+from .replay_buffer import DeviceReplayBuffer, ReplayBuffer
+
+
+def _resolve_device(device):
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        # the reference's default is device="cpu" (train_IQN_model.py -D); this implementation only computes on the GPU
+        warnings.warn("IQNAgent(device='cpu'): this implementation has no CPU path, using cuda:%d" % torch.cuda.current_device()
+                      if torch.cuda.is_available() else "IQNAgent needs a CUDA device")
+        if not torch.cuda.is_available():
+            raise _lib.MarinenavError("IQNAgent needs a CUDA device (there is no CPU fallback)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class _AdamState:
+    """Stand-in for torch.optim.Adam(qnetwork_local.parameters(), lr) (agent.py:66): moments as flat device vectors."""
+
+    def __init__(self, n, lr, device):
+        self.lr, self.betas, self.eps = lr, (0.9, 0.999), 1e-8
+        self.m = torch.zeros(n, dtype=torch.float32, device=device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=device)
+        self.step_count = 0
+
+    def zero_grad(self):
+        pass
+
+    def state_dict(self):
+        return dict(lr=self.lr, betas=self.betas, eps=self.eps, step=self.step_count, exp_avg=self.m.clone(), exp_avg_sq=self.v.clone())
+
+    def load_state_dict(self, sd):
+        self.lr, self.betas, self.eps, self.step_count = sd["lr"], tuple(sd["betas"]), sd["eps"], int(sd["step"])
+        self.m.copy_(sd["exp_avg"]); self.v.copy_(sd["exp_avg_sq"])
+
+
+class IQNAgent:
+    def __init__(self, state_size, action_size, layer_size=64, n_step=1, BATCH_SIZE=32, BUFFER_SIZE=1_000_000, LR=1e-4,
+                 TAU=1.0, GAMMA=0.99, UPDATE_EVERY=4, learning_starts=10000, target_update_interval=10000,
+                 exploration_fraction=0.1, initial_eps=1.0, final_eps=0.05, device="cpu", seed=0):
+        self.state_size, self.action_size = state_size, action_size
+        self.device = _resolve_device(device)
+        self.LR, self.TAU, self.GAMMA = LR, TAU, GAMMA
+        self.UPDATE_EVERY, self.BATCH_SIZE, self.BUFFER_SIZE, self.n_step = UPDATE_EVERY, BATCH_SIZE, BUFFER_SIZE, n_step
+        self.learning_starts, self.target_update_interval = learning_starts, target_update_interval
+        self.exploration_fraction, self.initial_eps, self.final_eps = exploration_fraction, initial_eps, final_eps
+        self.seed = seed
+
+        self.qnetwork_local = ObsEncoder(state_size, action_size, seed, self.device)       # agent.py:63-64: same seed twice
+        self.qnetwork_target = ObsEncoder(state_size, action_size, seed, self.device)
+        self.optimizer = _AdamState(iqn_ops.N_PARAMS, LR, self.device)
+        self.memory = ReplayBuffer(BUFFER_SIZE, BATCH_SIZE, self.device, seed, GAMMA, n_step, state_size)   # agent.py:70
+        self.current_timestep = 0
+        self.learning_timestep = 0
+
+        self.eval_timesteps = dict(greedy=[], adaptive=[])
+        self.eval_actions = dict(greedy=[], adaptive=[])
+        self.eval_rewards = dict(greedy=[], adaptive=[])
+        self.eval_successes = dict(greedy=[], adaptive=[])
+        self.eval_times = dict(greedy=[], adaptive=[])
+        self.eval_energies = dict(greedy=[], adaptive=[])
+
+        n = iqn_ops.N_PARAMS
+        self._grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._scratch = None
+        self.device_memory = None              # DeviceReplayBuffer of the vectorised trainer
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed) + 12345)
+
+    # ---- persistence ---------------------------------------------------------------------------------------------------
+    def load_model(self, path, device=None):
+        """agent.py:86-92: both networks from network_params.pth, fresh Adam."""
+        dev = self.device if device is None else _resolve_device(device)
+        self.qnetwork_local = ObsEncoder.load(path, dev)
+        self.qnetwork_target = ObsEncoder.load(path, dev)
+        self.optimizer = _AdamState(iqn_ops.N_PARAMS, self.LR, dev)
+
+    # ---- schedules -------------------------------------------------------------------------------------------------------
+    def linear_eps(self, total_timesteps):
+        """agent.py:176-183"""
+        progress = self.current_timestep / total_timesteps
+        if progress < self.exploration_fraction:
+            r = progress / self.exploration_fraction
+            return self.initial_eps + r * (self.final_eps - self.initial_eps)
+        return self.final_eps
+
+    # ---- acting: single observation (the reference's interface) ---------------------------------------------------------
+    def _qvals(self, state, cvar):
+        x = torch.from_numpy(np.asarray(state)).float().unsqueeze(0)
+        self.qnetwork_local.eval()
+        with torch.no_grad():
+            action_values = self.qnetwork_local.get_qvals(x, cvar)
+        self.qnetwork_local.train()
+        return action_values
+
+    def act(self, state, eps, cvar=1.0):
+        """agent.py:186-205: K = 32 quantile samples, epsilon-greedy with python `random`."""
+        action_values = self._qvals(state, cvar)
+        if random.random() > eps:
+            action = np.argmax(action_values.cpu().data.numpy())
+        else:
+            action = random.choice(np.arange(self.action_size))
+        return action
+
+    def act_adaptive(self, state, eps):
+        """agent.py:207-215"""
+        cvar = self.adjust_cvar(state)
+        return self.act(state, eps, cvar), cvar
+
+    def act_eval(self, state, eps=0.0, cvar=1.0):
+        """agent.py:217-237: also returns the quantiles [1,32,9] and taus [1,32,1]."""
+        x = torch.from_numpy(np.asarray(state)).float().unsqueeze(0)
+        self.qnetwork_local.eval()
+        with torch.no_grad():
+            quantiles, taus = self.qnetwork_local.forward(x, self.qnetwork_local.K, cvar)
+            action_values = quantiles.mean(dim=1)
+        self.qnetwork_local.train()
+        if random.random() > eps:
+            action = np.argmax(action_values.cpu().data.numpy())
+        else:
+            action = random.choice(np.arange(self.action_size))
+        return action, quantiles.cpu().data.numpy(), taus.cpu().data.numpy()
+
+    def act_adaptive_eval(self, state, eps=0.0):
+        """agent.py:239-247"""
+        cvar = self.adjust_cvar(state)
+        return self.act_eval(state, eps, cvar), cvar
+
+    def adjust_cvar(self, state):
+        """agent.py:249-267: CVaR = min(1, closest sonar return / 10); a beam with |x|,|y| < 1e-3 is 'no return'."""
+        pts = np.asarray(state)[4:].reshape(-1, 2)
+        seen = ~((np.abs(pts[:, 0]) < 1e-3) & (np.abs(pts[:, 1]) < 1e-3))
+        closest = np.inf
+        for p in pts[seen]:
+            closest = min(closest, np.linalg.norm(p))
+        return closest / 10.0 if closest < 10.0 else 1.0
+
+    # ---- acting: whole env batch on the device -----------------------------------------------------------------------------
+    def adjust_cvar_batch(self, obs):
+        """adjust_cvar for obs f32 [E, 26] on the device -> f32 [E]."""
+        pts = obs[:, 4:].reshape(obs.shape[0], -1, 2)
+        seen = ~((pts[..., 0].abs() < 1e-3) & (pts[..., 1].abs() < 1e-3))
+        d = torch.linalg.vector_norm(pts, dim=-1)
+        closest = torch.where(seen, d, torch.full_like(d, float("inf"))).min(dim=1).values
+        return torch.where(closest < 10.0, closest / 10.0, torch.ones_like(closest)).contiguous()
+
+    def act_batch(self, obs, eps, cvar=1.0, adaptive=False):
+        """Epsilon-greedy actions (int32 [E]) for a device batch of observations; K = 32 taus per env drawn on the device."""
+        net = self.qnetwork_local
+        E = obs.shape[0]
+        with torch.cuda.device(self.device):
+            taus = torch.rand(E, net.K, device=self.device, generator=self.gen)
+            cv = self.adjust_cvar_batch(obs) if adaptive else cvar
+            _, _, greedy = iqn_ops.forward(net.flat, net.packed, obs, taus, cv, want_quantiles=False, want_greedy=True)
+            if eps <= 0.0:
+                return greedy
+            explore = torch.rand(E, device=self.device, generator=self.gen) <= eps           # agent.py:200: greedy iff random() > eps
+            rand_a = torch.randint(0, self.action_size, (E,), device=self.device, generator=self.gen, dtype=torch.int32)
+            return torch.where(explore, rand_a, greedy)
+
+    # ---- learning --------------------------------------------------------------------------------------------------------
+    def train(self, experiences, taus=None):
+        """agent.py:269-304.  experiences = (states [B,26], actions [B,1] int64, rewards [B,1], next_states, dones [B,1]).
+        taus (optional) = (taus_target, taus_local) f32 [B,8]; by default they are drawn like the reference does (target
+        first).  Returns the loss as a numpy scalar.  With torch.distributed initialised the flat gradient is summed over
+        ranks and divided by the world size before the clip + Adam step (identical on every rank)."""
+        states, actions, rewards, next_states, dones = experiences
+        dev = self.device
+        B = states.shape[0]
+        f = lambda t: t.to(dev, torch.float32).reshape(B, -1).contiguous()
+        states, next_states = f(states), f(next_states)
+        rewards, dones = f(rewards).reshape(B), f(dones).reshape(B)
+        actions = actions.to(dev, torch.int64).reshape(B).contiguous()
+        self.optimizer.zero_grad()
+        if taus is None:
+            taus_t = self.qnetwork_target.draw_taus(B, 8)          # Q9: the target forward draws first (agent.py:279)
+            taus_l = self.qnetwork_local.draw_taus(B, 8)
+        else:
+            taus_t, taus_l = (t.to(dev, torch.float32).contiguous() for t in taus)
+        need = iqn_ops.train_scratch_floats(B)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float32, device=dev)
+        L, T, opt = self.qnetwork_local, self.qnetwork_target, self.optimizer
+        with torch.cuda.device(dev):
+            iqn_ops.loss_grad(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus_t, taus_l,
+                              float(self.GAMMA ** self.n_step), self._scratch, self._loss, self._grad)
+            world = mdist.all_reduce_sum_(self._grad)             # no-op (returns 1) unless torch.distributed is initialised
+            opt.step_count += 1
+            iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
+                              grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm)
+        return self._loss.detach().cpu().numpy()[0]
+
+    def train_async(self, experiences, taus):
+        """train() without the device->host read of the loss (for CUDA-graph / benchmark loops). Returns the loss tensor."""
+        states, actions, rewards, next_states, dones = experiences
+        B = states.shape[0]
+        need = iqn_ops.train_scratch_floats(B)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float32, device=self.device)
+        L, T, opt = self.qnetwork_local, self.qnetwork_target, self.optimizer
+        iqn_ops.loss_grad(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus[0], taus[1],
+                          float(self.GAMMA ** self.n_step), self._scratch, self._loss, self._grad)
+        world = mdist.all_reduce_sum_(self._grad)
+        opt.step_count += 1
+        iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
+                          grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm)
+        return self._loss
+
+    def soft_update(self, local_model, target_model):
+        """agent.py:307-317: theta_target = TAU * theta_local + (1 - TAU) * theta_target (TAU = 1: hard copy)."""
+        target_model.flat.copy_(self.TAU * local_model.flat + (1.0 - self.TAU) * target_model.flat)
+        target_model.repack()
+
+    # ---- the reference's single-env training loop (agent.py:94-173) -------------------------------------------------------
+    def learn(self, total_timesteps, train_env, eval_env, eval_config, eval_freq, eval_log_path, verbose=True):
+        state = train_env.reset()
+        ep_reward, ep_length, ep_num = 0.0, 0, 0
+        while self.current_timestep <= total_timesteps:
+            eps = self.linear_eps(total_timesteps)
+            action = self.act(state, eps)
+            next_state, reward, done, info = train_env.step(action)
+            ep_reward += train_env.discount ** ep_length * reward
+            ep_length += 1
+            self.memory.add(state, action, reward, next_state, done)
+            state = next_state
+            if self.current_timestep >= self.learning_starts:
+                if self.learning_timestep % self.UPDATE_EVERY == 0 and len(self.memory) > self.BATCH_SIZE:
+                    self.train(self.memory.sample())
+                if self.learning_timestep % self.target_update_interval == 0:
+                    self.soft_update(self.qnetwork_local, self.qnetwork_target)
+                if self.learning_timestep % eval_freq == 0:
+                    self.evaluation(eval_env, eval_config=eval_config, eval_log_path=eval_log_path)
+                    self.evaluation(eval_env, eval_config=eval_config, greedy=False, eval_log_path=eval_log_path)
+                    if eval_log_path is not None:
+                        self.qnetwork_local.save(eval_log_path)
+                self.learning_timestep += 1
+            if done:
+                ep_num += 1
+                if verbose:
+                    print("======== training info ========")
+                    print("current ep_length: ", ep_length)
+                    print("current ep_reward: ", ep_reward)
+                    print("current ep_result: ", info["state"])
+                    print("episodes_num: ", ep_num)
+                    print("exploration_rate: ", eps)
+                    print("current_timesteps: ", self.current_timestep)
+                    print("total_timesteps: ", total_timesteps)
+                    print("======== training info ========\n")
+                ep_reward, ep_length = 0.0, 0
+                state = train_env.reset()
+            self.current_timestep += 1
+
+    def evaluation(self, eval_env, eval_config, greedy=True, eval_log_path=None, verbose=True):
+        """agent.py:319-398: one episode per evaluation map (<= 1000 steps), .npz log with the reference's schema."""
+        action_data, reward_data, success_data, time_data, energy_data = [], [], [], [], []
+        for idx, config in enumerate(eval_config.values()):
+            if verbose:
+                print(f"Evaluating episode {idx}")
+            observation = eval_env.reset_with_eval_config(config)
+            actions, cumulative_reward, length, energy, done = [], 0.0, 0, 0.0, False
+            info = {"state": "normal"}
+            while not done and length < 1000:
+                if greedy:
+                    action = self.act(observation, eps=0.0)
+                else:
+                    action, _ = self.act_adaptive(observation, eps=0.0)
+                observation, reward, done, info = eval_env.step(action)
+                cumulative_reward += eval_env.discount ** length * reward
+                length += 1
+                energy += eval_env.robot.compute_action_energy_cost(int(action))
+                actions.append(int(action))
+            action_data.append(actions); reward_data.append(cumulative_reward)
+            success_data.append(info["state"] == "reach goal")
+            time_data.append(eval_env.robot.dt * eval_env.robot.N * length); energy_data.append(energy)
+        self._log_evaluation(greedy, action_data, reward_data, success_data, time_data, energy_data, eval_log_path, verbose)
+
+    def _log_evaluation(self, greedy, action_data, reward_data, success_data, time_data, energy_data, eval_log_path, verbose=True):
+        avg_r = np.mean(reward_data)
+        success_rate = np.sum(success_data) / len(success_data)
+        idx = np.where(np.array(success_data) == 1)[0]
+        avg_t = np.mean(np.array(time_data)[idx]) if len(idx) else float("nan")
+        avg_e = np.mean(np.array(energy_data)[idx]) if len(idx) else float("nan")
+        policy = "greedy" if greedy else "adaptive"
+        if verbose:
+            print(f"++++++++ Evaluation info ({policy} IQN) ++++++++")
+            print(f"Avg cumulative reward: {avg_r:.2f}")
+            print(f"Success rate: {success_rate:.2f}")
+            print(f"Avg time: {avg_t:.2f}")
+            print(f"Avg energy: {avg_e:.2f}")
+            print(f"++++++++ Evaluation info ({policy} IQN) ++++++++\n")
+        self.eval_timesteps[policy].append(self.current_timestep)
+        self.eval_actions[policy].append(action_data)
+        self.eval_rewards[policy].append(reward_data)
+        self.eval_successes[policy].append(success_data)
+        self.eval_times[policy].append(time_data)
+        self.eval_energies[policy].append(energy_data)
+        if eval_log_path is not None:
+            filename = "greedy_evaluations.npz" if greedy else "adaptive_evaluations.npz"
+            np.savez(os.path.join(eval_log_path, filename),
+                     timesteps=np.array(self.eval_timesteps[policy]),
+                     actions=np.array(self.eval_actions[policy], dtype=object),
+                     rewards=np.array(self.eval_rewards[policy]), successes=np.array(self.eval_successes[policy]),
+                     times=np.array(self.eval_times[policy]), energies=np.array(self.eval_energies[policy]))
+
+    # ---- vectorised training: everything stays on the device ----------------------------------------------------------------
+    def evaluation_vec(self, eval_config, greedy=True, eval_log_path=None, verbose=False, params=None):
+        """evaluation() with all maps of eval_config stepped as ONE env batch (same episode definitions)."""
+        from .vec_env import VecMarineNavEnv
+        cfgs = list(eval_config.values())
+        env = VecMarineNavEnv.from_eval_configs(cfgs, device=self.device)
+        obs = env.observe_all()
+        n = len(cfgs)
+        ret = torch.zeros(n, dtype=torch.float64, device=self.device)
+        alive = torch.ones(n, dtype=torch.bool, device=self.device)
+        last_info = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        length = torch.zeros(n, dtype=torch.int64, device=self.device)
+        acts = []
+        for t in range(1000):
+            a = self.act_batch(obs, 0.0, adaptive=not greedy)
+            obs, reward, done, info = env.step(a, auto_reset=False)
+            ret += torch.where(alive, (env.discount ** t) * reward.double(), torch.zeros_like(ret))
+            last_info = torch.where(alive, info, last_info)
+            length += alive.long()
+            acts.append(torch.where(alive, a, torch.full_like(a, -1)))
+            alive = alive & (done == 0)
+            if t % 50 == 49 and not bool(alive.any()):
+                break
+        acts = torch.stack(acts).cpu().numpy()
+        length_h = length.cpu().numpy()
+        action_data = [[int(x) for x in acts[:length_h[i], i]] for i in range(n)]
+        energy = [float(sum(env.compute_action_energy_cost(a) for a in action_data[i])) for i in range(n)]
+        self._log_evaluation(greedy, action_data, list(ret.cpu().numpy()), list((last_info == 3).cpu().numpy()),
+                             list(env.dt * env.N * length_h.astype(np.float64)), energy, eval_log_path, verbose)
+
+    def learn_vec(self, total_timesteps, train_env, eval_config=None, eval_freq=None, eval_log_path=None, batch_size=None,
+                  updates_per_step=1, learning_starts=None, target_update_interval=None, buffer_size=None, verbose=False,
+                  on_step=None):
+        """Vectorised counterpart of learn(): E transitions per env.step, device replay buffer, `updates_per_step` IQN
+        updates of `batch_size` per vector step once `learning_starts` transitions were collected.  Schedules (epsilon,
+        target update, evaluation) are keyed on transitions / learning steps like the reference's."""
+        E = train_env.num_envs
+        B = batch_size or self.BATCH_SIZE
+        learning_starts = self.learning_starts if learning_starts is None else learning_starts
+        target_update_interval = self.target_update_interval if target_update_interval is None else target_update_interval
+        if self.device_memory is None:
+            self.device_memory = DeviceReplayBuffer(buffer_size or self.BUFFER_SIZE, B, self.device, seed=self.seed)
+        mem = self.device_memory
+        obs = train_env.reset().clone()
+        losses = []
+        next_eval = 0
+        while self.current_timestep <= total_timesteps:
+            eps = self.linear_eps(total_timesteps)
+            action = self.act_batch(obs, eps)
+            _, reward, done, _ = train_env.step(action, auto_reset=True)
+            # buf['next_obs'] keeps the step's own (terminal) observation; buf['obs'] the post-auto-reset one (agent.py:122-124,170)
+            mem.add_batch(obs, action, reward, train_env.buf["next_obs"], done)
+            obs.copy_(train_env.buf["obs"])
+            self.current_timestep += E
+            if self.current_timestep >= learning_starts and len(mem) > B:
+                for _ in range(updates_per_step):
+                    s, a, r, s2, d = mem.sample(B)
+                    taus_t = torch.rand(B, 8, device=self.device, generator=self.gen)
+                    taus_l = torch.rand(B, 8, device=self.device, generator=self.gen)
+                    if self.learning_timestep % target_update_interval == 0:
+                        self.soft_update(self.qnetwork_local, self.qnetwork_target)
+                    loss = self.train_async((s.contiguous(), a.contiguous(), r.contiguous(), s2.contiguous(), d.contiguous()),
+                                            (taus_t, taus_l))
+                    self.learning_timestep += 1
+                if verbose and self.learning_timestep % 100 == 0:
+                    losses.append(float(loss.item()))
+                if eval_config is not None and eval_freq and self.learning_timestep >= next_eval:
+                    self.evaluation_vec(eval_config, greedy=True, eval_log_path=eval_log_path)
+                    self.evaluation_vec(eval_config, greedy=False, eval_log_path=eval_log_path)
+                    if eval_log_path is not None:
+                        self.qnetwork_local.save(eval_log_path)
+                    next_eval += eval_freq
+            if on_step is not None:
+                on_step(self)
+        return losses

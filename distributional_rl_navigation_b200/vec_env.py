@@ -120,7 +120,7 @@ class VecMarineNavEnv:
             env_ops.observe(self.buf, self.params(), mask=mask, velocity_from_state=True)
         return self.buf["obs"]
 
-    def step(self, actions, auto_reset=True):
+    def step(self, actions, auto_reset=True, trajectory=None):
         """actions: CUDA int32 [E].  Returns (obs, reward, done, info) device tensors.
 
         With auto_reset (the VecEnv convention) environments that finished are reset and ``obs`` holds the first
@@ -128,7 +128,7 @@ class VecMarineNavEnv:
         what IQNAgent.learn stores as next_state before it calls reset() (agent.py:122-124,170)."""
         b = self.buf
         with torch.cuda.device(self.device):
-            env_ops.step(b, self.params(), action=actions, obs=b["next_obs"])
+            env_ops.step(b, self.params(), action=actions, obs=b["next_obs"], trajectory=trajectory)
             self.total_timesteps += self.num_envs
             b["obs"].copy_(b["next_obs"])
             if auto_reset:
@@ -172,3 +172,99 @@ class VecMarineNavEnv:
 
     def close(self):
         pass
+
+    # ---- Robot helpers the callers reach through env.robot.* ---------------------------------------------------------
+    def compute_action_energy_cost(self, action):
+        """Robot.compute_action_energy_cost (robot.py:72-77): |a| / max(a) + |w| / max(w)."""
+        a, w = self.a[int(action) // 3], self.w[int(action) % 3]
+        return float(abs(a / np.max(self.a)) + abs(w / np.max(self.w)))
+
+    # ---- evaluation maps (reset_with_eval_config, marinenav_env.py:467-555) ------------------------------------------
+    @classmethod
+    def from_eval_configs(cls, cfgs, device="cuda:0", seed=0):
+        """One environment per eval-config dict (schema of eval_config.json), restarted at its recorded start pose."""
+        num_beams = cfgs[0]["robot"]["sonar"]["num_beams"]
+        max_c = max(1, max(len(c["env"]["cores"]["positions"]) for c in cfgs))
+        max_o = max(1, max(len(c["env"]["obstacles"]["positions"]) for c in cfgs))
+        env = cls(len(cfgs), seed=seed, device=device, num_cores=max_c, num_obs=max_o, num_beams=num_beams,
+                  max_cores=max_c, max_obstacles=max_o)
+        env.load_eval_configs(cfgs)
+        return env
+
+    def load_eval_configs(self, cfgs):
+        """Per-env maps / start poses from eval-config dicts; the scalar env / robot / sonar constants come from cfgs[0]
+        (they are identical across the reference's evaluation maps)."""
+        assert len(cfgs) == self.num_envs
+        c0, E = cfgs[0], self.num_envs
+        e, r = c0["env"], c0["robot"]
+        self.width, self.height, self.r = e["width"], e["height"], e["r"]
+        self.v_rel_max, self.p = e["v_rel_max"], e["p"]
+        self.v_range, self.obs_r_range, self.clear_r = list(e["v_range"]), list(e["obs_r_range"]), e["clear_r"]
+        self.goal_dis = e["goal_dis"]
+        self.timestep_penalty, self.collision_penalty, self.goal_reward = e["timestep_penalty"], e["collision_penalty"], e["goal_reward"]
+        self.discount = e["discount"]
+        self.dt, self.N, self.robot_r, self.max_speed = r["dt"], r["N"], r["r"], r["max_speed"]
+        self.a, self.w = np.array(r["a"]), np.array(r["w"])
+        self.sonar_range, self.sonar_angle = r["sonar"]["range"], r["sonar"]["angle"]
+        assert r["sonar"]["num_beams"] == self.num_beams, "allocate the env with the config's num_beams"
+        mc, mo = self.max_cores, self.max_obstacles
+        state = np.zeros((4, E)); goal = np.zeros((2, E)); cores = np.zeros((3 * mc, E)); obst = np.zeros((3 * mo, E))
+        for i, cfg in enumerate(cfgs):
+            ce, cr = cfg["env"], cfg["robot"]
+            state[:, i] = [ce["start"][0], ce["start"][1], cr["init_theta"], cr["init_speed"]]
+            goal[:, i] = ce["goal"]
+            pos, cw, G = ce["cores"]["positions"], ce["cores"]["clockwise"], ce["cores"]["Gamma"]
+            assert len(pos) <= mc and len(ce["obstacles"]["positions"]) <= mo
+            for k in range(len(pos)):
+                cores[k, i], cores[mc + k, i], cores[2 * mc + k, i] = pos[k][0], pos[k][1], (G[k] if cw[k] else -G[k])
+            for k, (pp, rr) in enumerate(zip(ce["obstacles"]["positions"], ce["obstacles"]["r"])):
+                obst[k, i], obst[mo + k, i], obst[2 * mo + k, i] = pp[0], pp[1], rr
+        b = self.buf
+        for name, arr in (("state", state), ("goal", goal), ("cores", cores), ("obstacles", obst), ("start_pose", state)):
+            b[name].copy_(torch.from_numpy(arr))
+        b["episode_step"].zero_()
+        b["n_placed"][0].copy_(torch.tensor([len(c["env"]["cores"]["positions"]) for c in cfgs], dtype=torch.uint8))
+        b["n_placed"][1].copy_(torch.tensor([len(c["env"]["obstacles"]["positions"]) for c in cfgs], dtype=torch.uint8))
+
+    def observe_all(self):
+        """robot.reset_state + get_observation after load_eval_configs (marinenav_env.py:551-555)."""
+        with torch.cuda.device(self.device):
+            env_ops.observe(self.buf, self.params(), velocity_from_state=True)
+        return self.buf["obs"]
+
+    def restart_episodes(self, mask=None):
+        """Put (masked) environments back on their recorded start pose without drawing a new map."""
+        b = self.buf
+        if mask is None:
+            b["state"].copy_(b["start_pose"]); b["episode_step"].zero_()
+        else:
+            m = mask.bool()
+            b["state"][:, m] = b["start_pose"][:, m]; b["episode_step"][m] = 0
+        with torch.cuda.device(self.device):
+            env_ops.observe(b, self.params(), mask=mask, velocity_from_state=True)
+        return b["obs"]
+
+    def episode_data(self, i=0, action_history=(), trajectory=()):
+        """MarineNavEnv.episode_data (marinenav_env.py:557-622) of environment i, the eval_config.json schema."""
+        b = self.buf
+        nc, no = int(b["n_placed"][0, i]), int(b["n_placed"][1, i])
+        cores = b["cores"][:, i].cpu().numpy(); obst = b["obstacles"][:, i].cpu().numpy()
+        sp = b["start_pose"][:, i].cpu().numpy(); goal = b["goal"][:, i].cpu().numpy()
+        mc, mo = self.max_cores, self.max_obstacles
+        ep = {"env": {"seed": self.sd, "width": self.width, "height": self.height, "r": self.r, "v_rel_max": self.v_rel_max,
+                      "p": self.p, "v_range": list(self.v_range), "obs_r_range": list(self.obs_r_range), "clear_r": self.clear_r,
+                      "start": [float(sp[0]), float(sp[1])], "goal": [float(goal[0]), float(goal[1])], "goal_dis": self.goal_dis,
+                      "timestep_penalty": self.timestep_penalty, "collision_penalty": self.collision_penalty,
+                      "goal_reward": self.goal_reward, "discount": self.discount,
+                      "cores": {"positions": [[float(cores[k]), float(cores[mc + k])] for k in range(nc)],
+                                "clockwise": [int(cores[2 * mc + k] > 0) for k in range(nc)],
+                                "Gamma": [float(abs(cores[2 * mc + k])) for k in range(nc)]},
+                      "obstacles": {"positions": [[float(obst[k]), float(obst[mo + k])] for k in range(no)],
+                                    "r": [float(obst[2 * mo + k]) for k in range(no)]}},
+              "robot": {"dt": self.dt, "N": self.N, "length": 1.0, "width": 0.5, "r": self.robot_r, "max_speed": self.max_speed,
+                        "a": [float(x) for x in self.a], "w": [float(x) for x in self.w],
+                        "init_theta": float(sp[2]), "init_speed": float(sp[3]),
+                        "sonar": {"range": self.sonar_range, "angle": self.sonar_angle, "num_beams": self.num_beams},
+                        "action_history": [int(a) for a in action_history],
+                        "trajectory": [[float(p[0]), float(p[1])] for p in trajectory]}}
+        return ep

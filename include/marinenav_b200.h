@@ -74,10 +74,11 @@ void        mnv_default_reset_params(mnv_reset_params* p);
 /* MarineNavEnv.step (marinenav_env.py:199-262) for E environments: N sub-steps of get_velocity (:422-455) +
  * Robot.update_state (robot.py:102-123), then get_observation (:273-326, sonar robot.py:125-198), reward and the
  * termination priority of :240-257.  In/out: d_state, d_episode_step (+1).  Out: d_velocity (last sub-step's, Q6),
- * d_obs, d_reward, d_done, d_info.  ONE kernel launch. */
+ * d_obs, d_reward, d_done, d_info; d_trajectory (optional, may be NULL) f64 [n_substeps][2][E] = the position after every
+ * sub-step (Robot.trajectory, marinenav_env.py:212).  ONE kernel launch. */
 int mnv_step(double* d_state, double* d_velocity, const double* d_goal, const double* d_cores, const double* d_obstacles,
              const int32_t* d_action, int32_t* d_episode_step,
-             float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_info,
+             float* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_info, double* d_trajectory,
              int64_t E, int32_t max_c, int32_t max_o, const mnv_params* p, void* stream);
 
 /* MarineNavEnv.get_observation (marinenav_env.py:273-326) of the current state, for every environment with

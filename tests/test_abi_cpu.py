@@ -44,7 +44,7 @@ def test_struct_layouts_match_defaults(lib):
 def test_argument_errors_before_any_launch(lib):
     p = _lib.default_params()
     ok = C.c_void_p(4096)
-    args = [ok] * 11
+    args = [ok] * 12
     assert lib.mnv_step(*args, 0, 4, 8, C.byref(p), None) == -3                      # E == 0
     assert lib.mnv_step(*args, 16, 9, 8, C.byref(p), None) == -4                     # cores over capacity
     assert lib.mnv_step(*args, 16, 4, 33, C.byref(p), None) == -4                    # obstacles over capacity

@@ -1,0 +1,169 @@
+"""GPU: the drop-in Python surfaces (marinenav_env.MarineNavEnv facade, thirdparty.IQNAgent) against the oracle, the
+reference's KATs and its recorded evaluation results."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import marinenav_oracle as mo  # noqa: E402
+
+SCHED = dict(timesteps=[0, 1000000, 2000000], num_cores=[4, 6, 8], num_obstacles=[6, 8, 10], min_start_goal_dis=[30.0, 35.0, 40.0])
+
+
+def close(a, b, tol=1e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max() <= tol
+
+
+def make_env(seed, schedule=None):
+    import marinenav_env  # noqa: F401  (registers the id)
+    from distributional_rl_navigation_b200 import marinenav_env as impl
+    env = impl._gym.make('marinenav_env:marinenav_env-v0', seed=seed, schedule=schedule)
+    env.verbose_schedule = False
+    return env
+
+
+@pytest.fixture(scope="module")
+def pretrained_dir(golden_dir, tmp_path_factory):
+    d = tmp_path_factory.mktemp("pretrained")
+    w = np.load(os.path.join(golden_dir, "iqn_weights.npz"))
+    torch.save({k: torch.from_numpy(w[k]) for k in w.files}, os.path.join(d, "network_params.pth"))
+    with open(os.path.join(d, "constructor_params.json"), "w") as f:
+        json.dump({"state_size": 26, "action_size": 9, "seed": 103}, f)
+    return str(d)
+
+
+def test_facade_follows_oracle_env_free_running():
+    """gym.make(...) facade vs the oracle's stateful env with the same seed + curriculum: same maps, same returns of
+    reset()/step() for 400 random-policy steps including the resets in between."""
+    for seed in (0, 5):
+        env, orc = make_env(seed, SCHED), mo.OracleEnv(seed=seed, schedule=SCHED)
+        assert env.get_state_space_dimension() == 26 and env.get_action_space_dimension() == 9
+        close(env.reset(), orc.reset())
+        rng = np.random.RandomState(seed)
+        n_done = 0
+        for t in range(400):
+            a = int(rng.randint(9)) if t % 3 else 8
+            o1, r1, d1, i1 = env.step(a)
+            o2, r2, d2, i2 = orc.step(a)
+            assert isinstance(r1, float) and isinstance(d1, bool) and o1.dtype == np.float64 and o1.shape == (26,)
+            close(o1, o2); close(r1, r2)
+            assert d1 == d2 and i1 == i2
+            if d1:
+                n_done += 1
+                close(env.reset(), orc.reset())
+        assert env.total_timesteps == 400 and len(env.robot.trajectory) > 0
+        with pytest.raises(IndexError):
+            env.step(9)
+
+
+def test_facade_eval_config_roundtrip_and_replay(golden_dir):
+    cfg = json.load(open(os.path.join(golden_dir, "eval_config.json")))
+    d = np.load(os.path.join(golden_dir, "episodes_greedy.npz"))
+    offs = np.concatenate([[0], np.cumsum(d["lengths"].ravel())])
+    env = make_env(0)
+    for m in (0, 13, 29):
+        env.reset_with_eval_config(cfg[f"env_{m}"])
+        got = env.episode_data()
+        want = cfg[f"env_{m}"]
+        assert got["env"]["cores"] == want["env"]["cores"] and got["env"]["obstacles"] == want["env"]["obstacles"]
+        assert got["robot"]["init_theta"] == want["robot"]["init_theta"] and got["env"]["start"] == want["env"]["start"]
+        ev = 299
+        k = ev * 30 + m
+        acts = d["actions_flat"][offs[k]:offs[k + 1]]
+        ret, info = 0.0, None
+        for t, a in enumerate(acts):
+            _, r, done, info = env.step(int(a))
+            ret += env.discount ** t * r
+        assert (info["state"] == "reach goal") == bool(d["successes"][ev, m])
+        assert abs(ret - d["rewards"][ev, m]) < 1e-2
+        assert abs(env.robot.dt * env.robot.N * len(acts) - d["times"][ev, m]) < 1e-9
+        assert len(env.robot.trajectory) == 10 * len(acts) and env.episode_data()["robot"]["action_history"] == [int(a) for a in acts]
+    cur = env.get_velocity(20.0, 20.0)
+    orc = mo.OracleEnv(seed=0); orc.reset_with_eval_config(cfg["env_29"])
+    close(cur, orc.get_velocity(20.0, 20.0), 1e-10)
+
+
+def test_agent_train_kat_follows_reference_rng(golden_dir, pretrained_dir):
+    """SURVEY 8(c) KAT: IQNAgent(..., BATCH_SIZE=B, seed=0).load_model(pretrained); torch.manual_seed(1234); train(batch)
+    -> 266.52407837 (B=32) / 307.13052368 (B=1024): same tau stream (CPU generator, target first) and same loss."""
+    from thirdparty import IQNAgent
+    kat = np.load(os.path.join(golden_dir, "iqn_kat.npz"))
+    for B, want in ((32, 266.52407837), (1024, 307.13052368)):
+        agent = IQNAgent(26, 9, BATCH_SIZE=B, seed=0, device="cuda:0")
+        agent.load_model(pretrained_dir)
+        batch = tuple(torch.from_numpy(kat[f"{n}_B{B}"]) for n in ("states", "actions", "rewards", "next_states", "dones"))
+        torch.manual_seed(1234)
+        loss = agent.train(batch)
+        assert abs(float(loss) - want) <= 1e-4 * want, (loss, want)
+        assert abs(float(agent._grad_norm.item())) > 0.5          # clipping was active, as in the reference KAT
+
+
+def test_agent_initial_weights_and_act_surface(pretrained_dir):
+    from thirdparty import IQNAgent
+    import torch.nn as nn
+    agent = IQNAgent(26, 9, seed=7, device="cuda:0")
+    torch.manual_seed(7)
+    ref_first = nn.Linear(2, 16)                                   # model.py:117,125: first layer created after manual_seed(seed)
+    assert torch.equal(agent.qnetwork_local.state_dict()["velocity_encoder.weight"].cpu(), ref_first.weight.detach())
+    assert torch.equal(agent.qnetwork_local.flat, agent.qnetwork_target.flat)
+    agent.load_model(pretrained_dir)
+    obs = np.zeros(26); obs[2:4] = [30.0, 5.0]; obs[10:12] = [3.0, 0.5]
+    random.seed(0)
+    a = agent.act(obs, eps=0.0)
+    assert 0 <= int(a) < 9
+    a2, cvar = agent.act_adaptive(obs, eps=0.0)
+    assert abs(cvar - np.hypot(3.0, 0.5) / 10.0) < 1e-12
+    a3, quantiles, taus = agent.act_eval(obs)
+    assert quantiles.shape == (1, 32, 9) and taus.shape == (1, 32, 1)
+    (a4, q4, t4), cvar4 = agent.act_adaptive_eval(obs)
+    assert t4.max() <= cvar4 + 1e-6
+    batch_obs = torch.from_numpy(np.tile(obs, (64, 1))).float().cuda()
+    acts = agent.act_batch(batch_obs, 0.0)
+    assert acts.dtype == torch.int32 and acts.shape == (64,)
+    assert (acts == int(a)).float().mean() > 0.9                  # same observation -> (almost surely) the same greedy action
+    assert torch.allclose(agent.adjust_cvar_batch(batch_obs), torch.full((64,), float(cvar), device="cuda"), atol=1e-6)
+
+
+def test_pretrained_agent_reaches_goals_vectorised_eval(golden_dir, pretrained_dir, tmp_path):
+    """evaluation_vec: the reference's pretrained weights, greedy policy, its 30 evaluation maps as ONE env batch.
+    The reference logged 0.867 success at this checkpoint; taus are random so allow a band."""
+    from thirdparty import IQNAgent
+    cfg = json.load(open(os.path.join(golden_dir, "eval_config.json")))
+    agent = IQNAgent(26, 9, seed=0, device="cuda:0")
+    agent.load_model(pretrained_dir)
+    agent.evaluation_vec(cfg, greedy=True, eval_log_path=str(tmp_path))
+    agent.evaluation_vec(cfg, greedy=False, eval_log_path=str(tmp_path))
+    g = np.load(os.path.join(tmp_path, "greedy_evaluations.npz"), allow_pickle=True)
+    assert set(g.files) == {"timesteps", "actions", "rewards", "successes", "times", "energies"}
+    assert g["successes"].shape == (1, 30) and len(g["actions"][0, 0]) > 10
+    assert g["successes"].mean() >= 0.7, g["successes"].mean()
+    ad = np.load(os.path.join(tmp_path, "adaptive_evaluations.npz"), allow_pickle=True)
+    assert ad["successes"].mean() >= 0.6
+
+
+def test_learn_single_env_and_vectorised_smoke(tmp_path, golden_dir):
+    from thirdparty import IQNAgent
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+    cfg = json.load(open(os.path.join(golden_dir, "eval_config.json")))
+    small_cfg = {k: cfg[k] for k in ("env_0", "env_1")}
+    env, eval_env = make_env(3, SCHED), make_env(348)
+    agent = IQNAgent(26, 9, seed=103, device="cuda:0", learning_starts=40, target_update_interval=20)
+    before = agent.qnetwork_local.flat.clone()
+    agent.learn(total_timesteps=120, train_env=env, eval_env=eval_env, eval_config=small_cfg, eval_freq=1000,
+                eval_log_path=str(tmp_path), verbose=False)
+    assert agent.current_timestep == 121 and agent.learning_timestep == 81 and len(agent.memory) == 121
+    assert not torch.equal(before, agent.qnetwork_local.flat) and torch.isfinite(agent.qnetwork_local.flat).all()
+    assert os.path.isfile(os.path.join(tmp_path, "network_params.pth")) and os.path.isfile(os.path.join(tmp_path, "greedy_evaluations.npz"))
+    # vectorised
+    venv = VecMarineNavEnv(2048, seed=0, schedule=SCHED, device="cuda:0")
+    agent2 = IQNAgent(26, 9, seed=1, device="cuda:0", BATCH_SIZE=256, BUFFER_SIZE=50000)
+    agent2.learn_vec(total_timesteps=2048 * 12, train_env=venv, batch_size=256, learning_starts=4096, target_update_interval=4,
+                     updates_per_step=2)
+    assert agent2.learning_timestep == 2 * 11 and len(agent2.device_memory) == min(50000, 2048 * 13)
+    assert torch.isfinite(agent2.qnetwork_local.flat).all() and agent2.optimizer.step_count == agent2.learning_timestep
