@@ -165,5 +165,5 @@ def test_learn_single_env_and_vectorised_smoke(tmp_path, golden_dir):
     agent2 = IQNAgent(26, 9, seed=1, device="cuda:0", BATCH_SIZE=256, BUFFER_SIZE=50000)
     agent2.learn_vec(total_timesteps=2048 * 12, train_env=venv, batch_size=256, learning_starts=4096, target_update_interval=4,
                      updates_per_step=2)
-    assert agent2.learning_timestep == 2 * 11 and len(agent2.device_memory) == min(50000, 2048 * 13)
+    assert agent2.learning_timestep == 2 * 12 and len(agent2.device_memory) == min(50000, 2048 * 13)
     assert torch.isfinite(agent2.qnetwork_local.flat).all() and agent2.optimizer.step_count == agent2.learning_timestep
