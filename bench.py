@@ -238,6 +238,11 @@ def run_b200(args):
     e2e_value = world * E * K / float(te.item())
     checksum = float(np.asarray(rew, np.float64).sum())
 
+    for env in batches[1:]:
+        env.buf = None
+    batches = batches[:1]
+    torch.cuda.empty_cache()
+    iqn = None if args.no_iqn else iqn_bench(args, dev, world)       # every rank takes part (all-reduce inside)
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         abytes = algorithmic_bytes_per_env_step()
@@ -271,13 +276,119 @@ def run_b200(args):
                                     "sample": f"{E} envs x 40 steps of the same workload, oracle/marinenav_oracle.c "
                                               f"({cpu_dt:.1f} s on {cpu_cores} threads; the Python reference itself: "
                                               "330-385 steps/s/core, SURVEY.md section 6)"}
-        extra = getattr(sys.modules[__name__], "iqn_bench", None)
-        if extra is not None:
-            line["iqn"] = extra(args, dev, world)
+        if iqn is not None:
+            line["iqn"] = iqn
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# IQN legs (second half of the BASELINE metric: IQN updates/s; plus act and rollout+learn at BASELINE configs[2])
+# ---------------------------------------------------------------------------------------------------------------
+IQN_FLOP_PER_SAMPLE = 1813568          # fwd target + fwd local + bwd local, N = N' = 8
+IQN_ACT_FLOP_PER_ENV = 2010816         # K = 32 forward
+
+
+def iqn_bench(args, dev, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from distributional_rl_navigation_b200.iqn_agent import IQNAgent
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+    from distributional_rl_navigation_b200 import iqn_ops
+
+    out = {}
+    B, E = 1024, args.envs
+    agent = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    n_sets = 64                                                            # 64 different batches (26 MB) rotated
+    st = torch.randn(n_sets, B, 26, device=dev, generator=g) * 3; ns = torch.randn(n_sets, B, 26, device=dev, generator=g) * 3
+    ac = torch.randint(0, 9, (n_sets, B), device=dev, generator=g); rw = torch.randn(n_sets, B, device=dev, generator=g)
+    dn = (torch.rand(n_sets, B, device=dev, generator=g) < 0.05).float()
+    tt = torch.rand(n_sets, B, 8, device=dev, generator=g); tl = torch.rand(n_sets, B, 8, device=dev, generator=g)
+
+    def update(i):
+        k = i % n_sets
+        return agent.train_async((st[k], ac[k], rw[k], ns[k], dn[k]), (tt[k], tl[k]))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_upd = max(50, min(args.steps, 400))
+    for i in range(10):
+        update(i)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_upd):
+        update(i)
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1) / n_upd], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    out["updates_per_s"] = 1e3 / ms
+    out["update_ms"] = ms
+    out["update_config"] = f"batch {B} per GPU, N=N'=8, fp32 FFMA, loss_grad + " + ("NCCL all-reduce(35785 f32) + " if world > 1 else "") + "clip_adam + pack"
+    out["update_tflops_fp32"] = IQN_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
+    out["samples_per_s_all_gpus"] = world * B * 1e3 / ms
+    out["loss_finite"] = bool(torch.isfinite(agent._loss).all().item())
+
+    # act: K = 32 forward + argmax for a whole env batch (fp32 path)
+    obs = torch.randn(E, 26, device=dev, generator=g) * 3
+    for _ in range(2):
+        agent.act_batch(obs, 0.05)
+    sync()
+    n_act = 5
+    e0.record()
+    for _ in range(n_act):
+        agent.act_batch(obs, 0.05)
+    e1.record()
+    sync()
+    act_ms = e0.elapsed_time(e1) / n_act
+    out["act_ms_per_env_batch"] = act_ms
+    out["acts_per_s"] = world * E * 1e3 / act_ms
+    out["act_tflops_fp32"] = IQN_ACT_FLOP_PER_ENV * E / (act_ms * 1e-3) / 1e12
+
+    # rollout + learn (BASELINE configs[2]): act -> env step (+auto-reset) -> replay append -> 1 update of 1024 per vector step
+    env = VecMarineNavEnv(E, seed=12345 + E * (int(os.environ.get("RANK", 0))), device=dev, num_cores=N_CORES, num_obs=N_OBS,
+                          min_start_goal_dis=30.0, num_beams=N_BEAMS)
+    agent2 = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B, BUFFER_SIZE=4 * E)
+    n_roll = 6
+    agent2.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
+    sync()
+    t0 = time.perf_counter()
+    start_ts = agent2.current_timestep
+    agent2.learn_vec(total_timesteps=start_ts + E * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
+    sync()
+    dt = time.perf_counter() - t0
+    steps_done = agent2.current_timestep - start_ts
+    out["rollout_learn_env_steps_per_s"] = world * steps_done / dt
+    out["rollout_learn_config"] = f"{E} envs/GPU, eps-greedy IQN act K=32 (fp32), fused env step + auto-reset, device replay, 1 update of {B} per vector step"
+
+    if int(os.environ.get("RANK", 0)) == 0 and world == 1:
+        # CPU baseline for the update: the numpy oracle (port of IQNAgent.train) on the host
+        from oracle import iqn_oracle as io
+        rs = np.random.RandomState(0)
+        P = io.unflatten(agent.qnetwork_local.flat.cpu().numpy())
+        b = 1024
+        xs, x2 = rs.randn(b, 26).astype(np.float32), rs.randn(b, 26).astype(np.float32)
+        a_, r_, d_ = rs.randint(0, 9, b), rs.randn(b).astype(np.float32), (rs.rand(b) < 0.05).astype(np.float32)
+        t1, t2 = rs.rand(b, 8).astype(np.float32), rs.rand(b, 8).astype(np.float32)
+        io.loss_and_grad(P, P, xs, a_, r_, x2, d_, t1, t2)
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < 5.0:
+            io.loss_and_grad(P, P, xs, a_, r_, x2, d_, t1, t2); n += 1
+        out["cpu_baseline_updates_per_s"] = {"value": n / (time.perf_counter() - t0), "kind": "port", "cores": os.cpu_count(),
+                                             "sample": f"{n} updates of batch 1024, oracle/iqn_oracle.py (numpy/BLAS); the PyTorch "
+                                                       "reference: 242 updates/s at batch 32 on 1 thread (SURVEY.md section 6)"}
+    return out
 
 
 def main():
@@ -287,6 +398,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-iqn", action="store_true", help="skip the IQN legs")
     ap.add_argument("--preload", type=float, default=1.0, help="seconds of untimed identical load before the timed region (clock sampling)")
     args = ap.parse_args()
     if args.impl == "reference":
