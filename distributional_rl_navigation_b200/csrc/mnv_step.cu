@@ -59,6 +59,15 @@ __device__ __forceinline__ double fast_rcp(double a)
     return r;
 }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Dynamic shared memory: [kBlock * obs_dim floats, padded to 16 B][3 * max_o rows x kBlock doubles]
 template <int MAXC, int MAXO, bool STEP>
 __global__ void __launch_bounds__(kBlock, 8)
 mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
@@ -66,10 +75,13 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     extern __shared__ __align__(16) float s_obs[];           // [kBlock][obs_dim]
     const long long E = K.E;
     const long long e0 = (long long)blockIdx.x * kBlock;
-    const long long e = e0 + threadIdx.x;
+    const int tid = threadIdx.x;
+    const long long e = e0 + tid;
     const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
     const int D = K.obs_dim;
-    float* my_obs = s_obs + threadIdx.x * D;
+    float* my_obs = s_obs + tid * D;
+    double* s_ob = reinterpret_cast<double*>(s_obs + ((kBlock * D + 3) & ~3));   // obstacle rows of this CTA
+    const int max_o = K.max_o;
 
     if (live) {
         double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
@@ -81,13 +93,25 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 
         // ---- vortex cores -> registers; k = Gs/(2pi) carries the spin in its sign ----
         double cx[MAXC], cy[MAXC], ck[MAXC];
+        {
+            const double* pc = P.cores + e;
+            const long long rowstride = (long long)K.max_c * E;
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-            if (i < K.max_c) {
-                cx[i] = __ldg(P.cores + (long long)i * E + e);
-                cy[i] = __ldg(P.cores + (long long)(K.max_c + i) * E + e);
-                ck[i] = __ldg(P.cores + (long long)(2 * K.max_c + i) * E + e) * (1.0 / (2.0 * MNV_PI));
-            } else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+            for (int i = 0; i < MAXC; ++i) {
+                if (i < K.max_c) {
+                    cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride);
+                    ck[i] = __ldg(pc + 2 * rowstride) * (1.0 / (2.0 * MNV_PI));
+                } else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+                pc += E;
+            }
+        }
+        // ---- obstacle rows -> shared memory, asynchronously (after the loads the integration is waiting for): they are
+        //      first needed after the sub-step loop, so this DRAM round trip overlaps the integration; each thread
+        //      copies, and later reads, only its own column ----
+        {
+            const double* po = P.obst + e;
+            for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
+            cp_async_commit();
         }
         auto current = [&](double px, double py, double& ux, double& uy) {
             ux = 0.0; uy = 0.0;
@@ -109,6 +133,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
             const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
             vx = 0.0; vy = 0.0;
+            double* ptraj = P.traj != nullptr ? P.traj + e : nullptr;
             for (int it = 0; it < K.n_substeps; ++it) {
                 double ux, uy;
                 current(x, y, ux, uy);
@@ -117,15 +142,19 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 x = fma(vx, K.dt, x);                         // robot.py:105-107
                 y = fma(vy, K.dt, y);
                 sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
-                sp = fmin(fmax(sp, 0.0), K.max_speed);        // robot.py:114
+                sp = sp < 0.0 ? 0.0 : sp;                     // robot.py:114 (np.clip)
+                sp = sp > K.max_speed ? K.max_speed : sp;
                 th = __dadd_rn(th, wdt);                      // robot.py:117
-                while (th < 0.0) th += 2.0 * MNV_PI;          // robot.py:120-123
-                while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                if (th < 0.0 || th >= 2.0 * MNV_PI) {         // robot.py:120-123
+#pragma unroll 1
+                    while (th < 0.0) th += 2.0 * MNV_PI;
+#pragma unroll 1
+                    while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                }
                 const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
                 c = c2; s = s2;
-                if (P.traj != nullptr) {                      // Robot.trajectory (marinenav_env.py:212), optional
-                    P.traj[(long long)(2 * it) * E + e] = x;
-                    P.traj[(long long)(2 * it + 1) * E + e] = y;
+                if (ptraj != nullptr) {                       // Robot.trajectory (marinenav_env.py:212), optional
+                    ptraj[0] = x; ptraj[E] = y; ptraj += 2 * E;
                 }
             }
             const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
@@ -145,28 +174,29 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         my_obs[2] = (float)fma(c, gx - x, s * (gy - y));
         my_obs[3] = (float)fma(c, gy - y, -s * (gx - x));
 
-        // ---- obstacles -> robot frame, registers ----
-        double qx[MAXO], qy[MAXO], r2[MAXO], lim[MAXO];
-        unsigned may_out = 0u, may_in = 0u;
+        // ---- obstacles -> robot frame, registers.  q is pre-multiplied by sigma = +1 (robot outside the circle) or -1
+        //      (inside) so that "the nearer root can be in front" reads tc >= 0 in both cases; obstacles that cannot be
+        //      reached within the sonar range get r2 = -1 (discriminant always negative). ----
+        cp_async_wait_all();
+        const double* ob = s_ob + tid;
+        float qx[MAXO], qy[MAXO], r2[MAXO];                     // fp32: only the conservative candidate filter uses them
+        bool force_slow = false;                                // robot within 1e-9 of a circle: decide everything exactly
         double best_d2 = INFINITY, best_r = 0.0;               // Q4: nearest CENTRE only (marinenav_env.py:329-336)
 #pragma unroll
         for (int j = 0; j < MAXO; ++j) {
             double r = -1.0, ox = 0.0, oy = 0.0;
-            if (j < K.max_o) {
-                ox = __ldg(P.obst + (long long)j * E + e);
-                oy = __ldg(P.obst + (long long)(K.max_o + j) * E + e);
-                r = __ldg(P.obst + (long long)(2 * K.max_o + j) * E + e);
-            }
+            if (j < max_o) { ox = ob[j * kBlock]; oy = ob[(max_o + j) * kBlock]; r = ob[(2 * max_o + j) * kBlock]; }
             const double dx = ox - x, dy = oy - y;
             const bool on = r > 0.0;
-            qx[j] = fma(c, dx, s * dy);
-            qy[j] = fma(c, dy, -s * dx);
-            r2[j] = on ? r * r : -1.0;                         // empty slot: discriminant always negative
-            lim[j] = K.range_slack + r;
             const double d2 = fma(dx, dx, dy * dy);
+            const double rr = r * r, lim = K.range_slack + r;
             if (on && d2 < best_d2) { best_d2 = d2; best_r = r; }
-            if (on && d2 >= r2[j] * (1.0 - 1e-9)) may_out |= 1u << j;   // robot (almost) outside this circle
-            if (on && d2 <= r2[j] * (1.0 + 1e-9)) may_in |= 1u << j;    // robot (almost) inside
+            const bool inside = d2 < rr;
+            force_slow |= on && (fabs(d2 - rr) <= 1e-9 * rr);
+            const double sg = inside ? -1.0 : 1.0;
+            qx[j] = (float)(sg * fma(c, dx, s * dy));
+            qy[j] = (float)(sg * fma(c, dy, -s * dx));
+            r2[j] = (on && d2 <= lim * lim) ? (float)rr : -1.0f;
         }
 
         // ---- sonar (robot.py:125-198) ----
@@ -175,31 +205,39 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             double bx = K.beam_cos[b], by = K.beam_sin[b];      // beam direction in the robot frame
             if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }            // Q10: exactly (0,+1) in the world frame
             else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }     // Q10: exactly (0,-1)
-            int cnt = 0;
-            double tc_s = 0.0, disc_s = 0.0;
+            int cnt = 0, jsel = 0;
+            const float bxf = (float)bx, byf = (float)by;
 #pragma unroll
             for (int j = 0; j < MAXO; ++j) {
-                const double tc = fma(qx[j], bx, qy[j] * by);
-                const double cr = fma(qx[j], by, -qy[j] * bx);
-                const double disc = fma(-cr, cr, r2[j]);
-                // conservative candidate filter (no sqrt): real roots, the nearer root can be >= 0 and <= range
-                const bool side = (tc > 0.0) ? ((may_out >> j) & 1u) : ((may_in >> j) & 1u);
-                if (disc >= 0.0 && side && tc <= lim[j]) { ++cnt; tc_s = tc; disc_s = disc; }
+                // conservative candidate filter in fp32 (no sqrt): "real roots and the nearer root not behind the robot"
+                // with a 1e-3 margin, ~100x the fp32 rounding error of these expressions (|q| <= range + r); every
+                // candidate is then decided exactly in fp64 below, so the filter can only cost time, never a result
+                const float tc = fmaf(qx[j], bxf, qy[j] * byf);
+                const float cr = fmaf(qx[j], byf, -qy[j] * bxf);
+                const float disc = fmaf(-cr, cr, r2[j]);
+                if (fminf(disc, tc) >= -1e-3f) { ++cnt; jsel = j; }
             }
             bool hit = false;
             double t = 0.0;
-            if (cnt == 1) {
-                const double h = sqrt(disc_s);
-                t = tc_s > 0.0 ? tc_s - h : tc_s + h;           // nearer root first (robot.py:184)
-                hit = (t <= K.range) && (t >= 0.0);             // robot.py:185-190
-            } else if (cnt > 1) {
+            if (cnt == 1 && !force_slow) {
+                const double r = ob[(2 * max_o + jsel) * kBlock];
+                const double dx = ob[jsel * kBlock] - x, dy = ob[(max_o + jsel) * kBlock] - y;
+                const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
+                const double tc = fma(ax, bx, ay * by);
+                const double cr = fma(ax, by, -ay * bx);
+                const double disc = fma(-cr, cr, r * r);
+                if (disc >= 0.0) {                               // robot.py:172-174
+                    const double h = sqrt(disc);
+                    t = tc > 0.0 ? tc - h : tc + h;              // nearer root first (robot.py:184)
+                    hit = (t <= K.range) && (t >= 0.0);          // robot.py:185-190
+                }
+            } else if (cnt > 1 || force_slow) {
                 // several obstacles on this beam: replay the reference's ordered scan (Q3) exactly
                 double best = INFINITY;
-                for (int j = 0; j < K.max_o; ++j) {
-                    const double r = __ldg(P.obst + (long long)(2 * K.max_o + j) * E + e);
+                for (int j = 0; j < max_o; ++j) {
+                    const double r = ob[(2 * max_o + j) * kBlock];
                     if (!(r > 0.0)) continue;
-                    const double dx = __ldg(P.obst + (long long)j * E + e) - x;
-                    const double dy = __ldg(P.obst + (long long)(K.max_o + j) * E + e) - y;
+                    const double dx = ob[j * kBlock] - x, dy = ob[(max_o + j) * kBlock] - y;
                     const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
                     const double tc = fma(ax, bx, ay * by);
                     const double cr = fma(ax, by, -ay * bx);
@@ -235,27 +273,32 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         }
     }
 
-    // ---- observation rows of this CTA: one contiguous block, float4 stores ----
-    __syncthreads();
-    const long long rows = (E - e0 < kBlock) ? (E - e0) : kBlock;
-    const long long n = rows * D;
-    float* dst = P.obs + e0 * D;                                  // e0*D*4 bytes: 16-byte aligned (kBlock*4 % 16 == 0)
+    // ---- observation rows: every warp streams out its own 32 rows (one contiguous 32*D*4-byte block, float4 stores);
+    //      only a warp-level sync is needed because a thread's row was written by that thread ----
+    __syncwarp();
+    const int lane = tid & 31, w0 = tid & ~31;                   // first row of this warp inside the CTA
+    const long long left = E - (e0 + w0);
+    const int rows = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
+    const int n = rows * D;
+    const float* src = s_obs + w0 * D;                            // w0*D*4 bytes: 16-byte aligned (32*4 % 16 == 0)
+    float* dst = P.obs + (e0 + w0) * D;
     if (!STEP && P.mask != nullptr) {                             // masked observe: only the selected rows
-        for (long long i = threadIdx.x; i < n; i += kBlock)
-            if (P.mask[e0 + i / D] != 0) dst[i] = s_obs[i];
+        for (int i = lane; i < n; i += 32)
+            if (P.mask[e0 + w0 + i / D] != 0) dst[i] = src[i];
         return;
     }
-    const long long n4 = n >> 2;
-    for (long long i = threadIdx.x; i < n4; i += kBlock)
-        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_obs)[i];
-    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += kBlock) dst[i] = s_obs[i];
+    const int n4 = n >> 2;
+#pragma unroll 2
+    for (int i = lane; i < n4; i += 32)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    for (int i = (n4 << 2) + lane; i < n; i += 32) dst[i] = src[i];
 }
 
 template <bool STEP>
 int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
-    const size_t smem = (size_t)kBlock * K.obs_dim * sizeof(float);
+    const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double);
 #define MNV_LAUNCH(MC, MO)                                                                                   \
     do {                                                                                                     \
         auto kern = mnv_env_kernel<MC, MO, STEP>;                                                            \
