@@ -74,7 +74,7 @@ def observe(buf, params, mask=None, velocity_from_state=False, obs=None):
 def seed(rng_key, rng_pos, seeds):
     """RandomState(seed) per environment (MarineNavEnv.seed)."""
     E = seeds.shape[0]
-    _chk(rng_key, torch.int32, (624, E), "rng_key"); _chk(rng_pos, torch.int32, (E,), "rng_pos")
+    _chk(rng_key, torch.int32, (E, 624), "rng_key"); _chk(rng_pos, torch.int32, (E,), "rng_pos")
     _chk(seeds, torch.int32, (E,), "seeds")   # bit pattern of u32 seeds
     rc = _lib.load().mnv_seed(_lib.ptr(rng_key), _lib.ptr(rng_pos), _lib.ptr(seeds), E, _stream())
     _lib.check(rc, "mnv_seed")

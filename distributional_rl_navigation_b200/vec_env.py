@@ -55,7 +55,7 @@ class VecMarineNavEnv:
         with torch.cuda.device(self.device):
             self.buf = env_ops.alloc_env_buffers(E, self.max_cores, self.max_obstacles, self.num_beams, self.device)
             self.buf["next_obs"] = torch.zeros_like(self.buf["obs"])
-            self.rng_key = torch.zeros(624, E, dtype=torch.int32, device=self.device)
+            self.rng_key = torch.zeros(E, 624, dtype=torch.int32, device=self.device)
             self.rng_pos = torch.zeros(E, dtype=torch.int32, device=self.device)
         self._pinned = None
         self.seed(seed)

@@ -90,7 +90,7 @@ int mnv_observe(const double* d_state, double* d_velocity, const double* d_goal,
                 const mnv_params* p, int32_t velocity_from_state, void* stream);
 
 /* numpy.random.RandomState(seed) per environment (MarineNavEnv.seed, marinenav_env.py:75-78): legacy MT19937.
- *   d_rng_key u32 [624][E], d_rng_pos i32 [E].  d_seeds u32 [E]. */
+ *   d_rng_key u32 [E][624] (one contiguous MT19937 state per environment), d_rng_pos i32 [E].  d_seeds u32 [E]. */
 int mnv_seed(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint32_t* d_seeds, int64_t E, void* stream);
 
 /* MarineNavEnv.reset (marinenav_env.py:86-186) for every environment with d_mask[e] != 0 (d_mask == NULL: all):

@@ -175,7 +175,7 @@ def test_reset_bit_exact_vs_reference_vectors(golden_dir):
     d = np.load(os.path.join(golden_dir, "reset_vectors.npz"))
     E = d["seed"].shape[0]
     buf = env_ops.alloc_env_buffers(E, 8, 10, 11, DEV)
-    key = torch.zeros(624, E, dtype=torch.int32, device=DEV); pos = torch.zeros(E, dtype=torch.int32, device=DEV)
+    key = torch.zeros(E, 624, dtype=torch.int32, device=DEV); pos = torch.zeros(E, dtype=torch.int32, device=DEV)
     env_ops.seed(key, pos, torch.from_numpy(d["seed"].astype(np.uint32).view(np.int32)).to(DEV))
     rp = _lib.default_reset_params()
     rp.num_cores, rp.num_obs, rp.min_start_goal_dis = 4, 8, 30.0
@@ -198,7 +198,7 @@ def test_reset_eval_config_kat(golden_dir):
     regenerate the reference's eval_config.json bit-for-bit on the device."""
     cfg = json.load(open(os.path.join(golden_dir, "eval_config.json")))
     buf = env_ops.alloc_env_buffers(1, 8, 10, 11, DEV)
-    key = torch.zeros(624, 1, dtype=torch.int32, device=DEV); pos = torch.zeros(1, dtype=torch.int32, device=DEV)
+    key = torch.zeros(1, 624, dtype=torch.int32, device=DEV); pos = torch.zeros(1, dtype=torch.int32, device=DEV)
     env_ops.seed(key, pos, torch.tensor([348], dtype=torch.int32, device=DEV))
     rp = _lib.default_reset_params()
     rp.reset_start_and_goal = 0
@@ -226,7 +226,7 @@ def test_reset_masked_and_stream_continuation():
     E = 512
     op = mo.default_params(11)
     buf = env_ops.alloc_env_buffers(E, 4, 8, 11, DEV)
-    key = torch.zeros(624, E, dtype=torch.int32, device=DEV); pos = torch.zeros(E, dtype=torch.int32, device=DEV)
+    key = torch.zeros(E, 624, dtype=torch.int32, device=DEV); pos = torch.zeros(E, dtype=torch.int32, device=DEV)
     seeds = np.arange(E, dtype=np.uint32) + 77
     env_ops.seed(key, pos, torch.from_numpy(seeds.view(np.int32)).to(DEV))
     rp = _lib.default_reset_params()
