@@ -164,14 +164,18 @@ class IQNAgent:
         closest = torch.where(seen, d, torch.full_like(d, float("inf"))).min(dim=1).values
         return torch.where(closest < 10.0, closest / 10.0, torch.ones_like(closest)).contiguous()
 
-    def act_batch(self, obs, eps, cvar=1.0, adaptive=False):
-        """Epsilon-greedy actions (int32 [E]) for a device batch of observations; K = 32 taus per env drawn on the device."""
+    def act_batch(self, obs, eps, cvar=1.0, adaptive=False, tensor_cores=True):
+        """Epsilon-greedy actions (int32 [E]) for a device batch of observations; K = 32 taus per env drawn on the device.
+        tensor_cores=True: tcgen05 kernel (bf16 operands, only the argmax is consumed); False: the fp32 parity kernel."""
         net = self.qnetwork_local
         E = obs.shape[0]
         with torch.cuda.device(self.device):
             taus = torch.rand(E, net.K, device=self.device, generator=self.gen)
             cv = self.adjust_cvar_batch(obs) if adaptive else cvar
-            _, _, greedy = iqn_ops.forward(net.flat, net.packed, obs, taus, cv, want_quantiles=False, want_greedy=True)
+            if tensor_cores:
+                _, greedy = iqn_ops.act_tc(net.flat, net.packed_tc, obs, taus, cv)
+            else:
+                _, _, greedy = iqn_ops.forward(net.flat, net.packed, obs, taus, cv, want_quantiles=False, want_greedy=True)
             if eps <= 0.0:
                 return greedy
             explore = torch.rand(E, device=self.device, generator=self.gen) <= eps           # agent.py:200: greedy iff random() > eps
@@ -208,6 +212,7 @@ class IQNAgent:
             opt.step_count += 1
             iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
                               grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm)
+            iqn_ops.pack_tc(L.flat, L.packed_tc)
         return self._loss.detach().cpu().numpy()[0]
 
     def train_async(self, experiences, taus):
@@ -224,6 +229,7 @@ class IQNAgent:
         opt.step_count += 1
         iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
                           grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm)
+        iqn_ops.pack_tc(L.flat, L.packed_tc)
         return self._loss
 
     def soft_update(self, local_model, target_model):

@@ -33,6 +33,7 @@ class ObsEncoder:
         assert flat.numel() == iqn_ops.N_PARAMS
         self.flat = flat.to(dev).contiguous()
         self.packed = torch.empty(iqn_ops.N_PACKED, dtype=torch.float32, device=dev)
+        self.packed_tc = torch.empty(iqn_ops.packed_tc_bytes(), dtype=torch.uint8, device=dev)   # bf16 tiles for act_tc
         self.training = True
         self.tau_generator = None                                 # None: CPU default generator, like model.py:149
         self.repack()
@@ -41,6 +42,7 @@ class ObsEncoder:
     def repack(self):
         with torch.cuda.device(self.device):
             iqn_ops.pack(self.flat, self.packed)
+            iqn_ops.pack_tc(self.flat, self.packed_tc)
 
     def named_views(self):
         out, o = OrderedDict(), 0
@@ -71,6 +73,7 @@ class ObsEncoder:
         if torch.device(device) != self.device:
             self.device = torch.device(device)
             self.flat = self.flat.to(self.device); self.packed = self.packed.to(self.device)
+            self.packed_tc = self.packed_tc.to(self.device)
         return self
 
     def eval(self):

@@ -86,3 +86,31 @@ def clip_adam(params, grad, m, v, packed, step, lr=1e-4, max_norm=0.5, grad_scal
                                    C.c_float(grad_scale), C.c_float(max_norm), C.c_float(lr), C.c_float(beta1),
                                    C.c_float(beta2), C.c_float(eps), int(step), _lib.ptr(grad_norm), _stream())
     _lib.check(rc, "iqn_clip_adam")
+
+
+def packed_tc_bytes():
+    return int(_lib.load().iqn_packed_tc_bytes())
+
+
+def pack_tc(params, packed_tc):
+    """fp32 parameters -> bf16 UMMA weight tiles for act_tc (call after any parameter change)."""
+    _f32(params, N_PARAMS, "params")
+    if packed_tc.dtype != torch.uint8 or packed_tc.numel() != packed_tc_bytes() or not packed_tc.is_cuda:
+        raise _lib.MarinenavError("packed_tc: expected CUDA uint8 buffer of iqn_packed_tc_bytes() bytes")
+    _lib.check(_lib.load().iqn_pack_tc(_lib.ptr(params), _lib.ptr(packed_tc), _stream()), "iqn_pack_tc")
+
+
+def act_tc(params, packed_tc, obs, taus, cvar=1.0, want_qmean=False, want_greedy=True, debug=None):
+    """get_qvals + argmax on the tensor cores (bf16 operands): obs f32 [B,26], taus f32 [B,32]."""
+    B, n_tau = taus.shape
+    _f32(params, N_PARAMS, "params"); _f32(obs, B * OBS_DIM, "obs"); _f32(taus, B * n_tau, "taus")
+    dev = obs.device
+    cvar_t, cvar_s = (cvar, 1.0) if torch.is_tensor(cvar) else (None, float(cvar))
+    if cvar_t is not None:
+        _f32(cvar_t, B, "cvar")
+    qm = torch.empty(B, N_ACTIONS, dtype=torch.float32, device=dev) if want_qmean else None
+    gr = torch.empty(B, dtype=torch.int32, device=dev) if want_greedy else None
+    rc = _lib.load().iqn_act_tc(_lib.ptr(params), _lib.ptr(packed_tc), _lib.ptr(obs), _lib.ptr(taus), _lib.ptr(cvar_t),
+                                C.c_float(cvar_s), _lib.ptr(qm), _lib.ptr(gr), _lib.ptr(debug), B, n_tau, _stream())
+    _lib.check(rc, "iqn_act_tc")
+    return qm, gr

@@ -146,6 +146,18 @@ int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d
                       float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                       float* d_grad_norm, void* stream);
 
+/* Acting forward on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in TMEM): get_qvals + argmax for a
+ * whole env batch, K = n_tau = 32 (ObsEncoder.K, model.py:118).  Same inputs as iqn_forward; outputs d_qmean f32 [B][9]
+ * and/or d_greedy i32 [B].  d_packed_tc: iqn_packed_tc_bytes() bytes of bf16 weight tiles, refresh with iqn_pack_tc after
+ * any parameter change.  d_debug (optional, NULL in production): 45 056 floats = the four raw accumulators of tile 0
+ * (128x208, 128x64, 128x64, 128x16) for diagnostics.  Q-values differ from the fp32 path by bf16 rounding (~1e-2
+ * relative): use where only the argmax is consumed (agent.py:200-203); iqn_forward stays the parity path. */
+int     iqn_packed_tc_bytes(void);
+int     iqn_pack_tc(const float* d_params, void* d_packed_tc, void* stream);
+int     iqn_act_tc(const float* d_params, const void* d_packed_tc, const float* d_obs, const float* d_taus,
+                   const float* d_cvar, float cvar_scalar, float* d_qmean, int32_t* d_greedy, float* d_debug,
+                   int64_t B, int32_t n_tau, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

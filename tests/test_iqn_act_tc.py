@@ -1,0 +1,91 @@
+"""GPU: the tcgen05 acting kernel (iqn_act_tc) against a bf16-emulating reference (stage by stage) and the fp32 kernel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from distributional_rl_navigation_b200 import iqn_ops  # noqa: E402
+from oracle import iqn_oracle as io  # noqa: E402
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def weights(golden_dir):
+    w = np.load(os.path.join(golden_dir, "iqn_weights.npz"))
+    return {k: w[k] for k in w.files}
+
+
+def bf(a):
+    """round-to-nearest-even bf16 rounding of a float32 array (emulation of the kernel's operand precision)."""
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def emulate(P, x, taus, cvar=1.0):
+    """The kernel's arithmetic: fp32 encoders, bf16 operands for the four GEMMs, fp32 accumulation."""
+    B, K = taus.shape
+    t = (taus * np.float32(cvar)).astype(np.float32)
+    feat = np.concatenate([x[:, 0:2] @ P["velocity_encoder.weight"].T + P["velocity_encoder.bias"],
+                           x[:, 2:4] @ P["goal_encoder.weight"].T + P["goal_encoder.bias"],
+                           x[:, 4:26] @ P["sensor_encoder.weight"].T + P["sensor_encoder.bias"]], axis=1).astype(np.float32)
+    cos = np.cos(np.pi * np.arange(64)[None, None, :] * t[:, :, None].astype(np.float64)).astype(np.float32).reshape(B * K, 64)
+    d1 = bf(cos) @ bf(P["cos_embedding.weight"]).T
+    h0 = np.maximum(d1 + P["cos_embedding.bias"], 0) * np.repeat(feat, K, axis=0)
+    d2 = bf(h0) @ bf(P["hidden_layer.weight"]).T
+    d3 = bf(np.maximum(d2 + P["hidden_layer.bias"], 0)) @ bf(P["hidden_layer_2.weight"]).T
+    d4 = bf(np.maximum(d3 + P["hidden_layer_2.bias"], 0)) @ bf(P["output_layer.weight"]).T
+    q = d4.reshape(B, K, 9).mean(axis=1) + P["output_layer.bias"]
+    return d1, d2, d3, d4, q
+
+
+def setup(weights):
+    flat = torch.from_numpy(io.flatten(weights)).to(DEV)
+    ptc = torch.empty(iqn_ops.packed_tc_bytes(), dtype=torch.uint8, device=DEV)
+    iqn_ops.pack_tc(flat, ptc)
+    return flat, ptc
+
+
+def test_stage_accumulators_match_bf16_emulation(weights):
+    rs = np.random.RandomState(0)
+    B = 8
+    x = (rs.randn(B, 26) * 3).astype(np.float32); x[:, 4:] *= (rs.rand(B, 22) > 0.5)
+    taus = rs.rand(B, 32).astype(np.float32)
+    flat, ptc = setup(weights)
+    debug = torch.zeros(128 * (208 + 64 + 64 + 16), dtype=torch.float32, device=DEV)
+    qm, gr = iqn_ops.act_tc(flat, ptc, torch.from_numpy(x).to(DEV), torch.from_numpy(taus).to(DEV), 1.0, want_qmean=True, debug=debug)
+    d = debug.cpu().numpy()
+    g1 = d[:128 * 208].reshape(128, 208); g2 = d[128 * 208:128 * 272].reshape(128, 64)
+    g3 = d[128 * 272:128 * 336].reshape(128, 64); g4 = d[128 * 336:].reshape(128, 16)
+    d1, d2, d3, d4, q = emulate(weights, x, taus)
+    for name, got, want in (("D1", g1, d1[:128]), ("D2", g2, d2[:128]), ("D3", g3, d3[:128]), ("D4", g4[:, :9], d4[:128])):
+        scale = max(1.0, np.abs(want).max())
+        err = np.abs(got - want).max() / scale
+        assert err < 2e-2, (name, err)          # each stage re-rounds its inputs to bf16: small drift accumulates
+    assert np.abs(g4[:, 9:]).max() == 0.0        # padded output columns
+    assert np.abs(qm.cpu().numpy() - q).max() < 2e-2 * max(1.0, np.abs(q).max())
+
+
+@pytest.mark.parametrize("B", [1, 37, 4096])
+def test_qmean_and_argmax_vs_fp32_kernel(weights, B):
+    rs = np.random.RandomState(B)
+    x = (rs.randn(B, 26) * 3).astype(np.float32); x[:, 4:] *= (rs.rand(B, 22) > 0.5)
+    x[:, 2:4] = rs.uniform(-40, 40, size=(B, 2))
+    taus = rs.rand(B, 32).astype(np.float32)
+    cvar = rs.uniform(0.1, 1.0, size=B).astype(np.float32)
+    flat, ptc = setup(weights)
+    packed = torch.empty(iqn_ops.N_PACKED, dtype=torch.float32, device=DEV)
+    iqn_ops.pack(flat, packed)
+    xd, td, cd = torch.from_numpy(x).to(DEV), torch.from_numpy(taus).to(DEV), torch.from_numpy(cvar).to(DEV)
+    for cv in (1.0, cd):
+        qm, gr = iqn_ops.act_tc(flat, ptc, xd, td, cv, want_qmean=True)
+        _, q32, g32 = iqn_ops.forward(flat, packed, xd, td, cv, want_quantiles=False, want_qmean=True, want_greedy=True)
+        q32 = q32.cpu().numpy(); qm = qm.cpu().numpy()
+        assert np.abs(qm - q32).max() < 3e-2 * max(1.0, np.abs(q32).max())
+        top2 = np.sort(q32, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 5e-2 * np.maximum(1.0, np.abs(top2[:, 1]))
+        assert np.array_equal(gr.cpu().numpy()[clear], g32.cpu().numpy()[clear])
+        assert (gr.cpu().numpy() == g32.cpu().numpy()).mean() > 0.9
+        assert np.array_equal(gr.cpu().numpy(), qm.argmax(axis=1))
