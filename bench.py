@@ -340,21 +340,22 @@ def iqn_bench(args, dev, world):
     out["samples_per_s_all_gpus"] = world * B * 1e3 / ms
     out["loss_finite"] = bool(torch.isfinite(agent._loss).all().item())
 
-    # act: K = 32 forward + argmax for a whole env batch (fp32 path)
+    # act: K = 32 forward + argmax for a whole env batch: tcgen05 kernel (bf16 operands) and the fp32 parity kernel
     obs = torch.randn(E, 26, device=dev, generator=g) * 3
-    for _ in range(2):
-        agent.act_batch(obs, 0.05)
-    sync()
-    n_act = 5
-    e0.record()
-    for _ in range(n_act):
-        agent.act_batch(obs, 0.05)
-    e1.record()
-    sync()
-    act_ms = e0.elapsed_time(e1) / n_act
-    out["act_ms_per_env_batch"] = act_ms
-    out["acts_per_s"] = world * E * 1e3 / act_ms
-    out["act_tflops_fp32"] = IQN_ACT_FLOP_PER_ENV * E / (act_ms * 1e-3) / 1e12
+    for name, tc, n_act in (("tc", True, 20), ("fp32", False, 3)):
+        for _ in range(2):
+            agent.act_batch(obs, 0.05, tensor_cores=tc)
+        sync()
+        e0.record()
+        for _ in range(n_act):
+            agent.act_batch(obs, 0.05, tensor_cores=tc)
+        e1.record()
+        sync()
+        act_ms = e0.elapsed_time(e1) / n_act
+        out[f"act_{name}_ms_per_env_batch"] = act_ms
+        out[f"act_{name}_acts_per_s"] = world * E * 1e3 / act_ms
+        out[f"act_{name}_tflops"] = IQN_ACT_FLOP_PER_ENV * E / (act_ms * 1e-3) / 1e12
+    out["act_config"] = f"{E} envs x K=32 taus: torch.rand taus + iqn_act_tc (tcgen05, bf16 operands) / iqn_forward (fp32) + eps-greedy"
 
     # rollout + learn (BASELINE configs[2]): act -> env step (+auto-reset) -> replay append -> 1 update of 1024 per vector step
     env = VecMarineNavEnv(E, seed=12345 + E * (int(os.environ.get("RANK", 0))), device=dev, num_cores=N_CORES, num_obs=N_OBS,
@@ -370,7 +371,7 @@ def iqn_bench(args, dev, world):
     dt = time.perf_counter() - t0
     steps_done = agent2.current_timestep - start_ts
     out["rollout_learn_env_steps_per_s"] = world * steps_done / dt
-    out["rollout_learn_config"] = f"{E} envs/GPU, eps-greedy IQN act K=32 (fp32), fused env step + auto-reset, device replay, 1 update of {B} per vector step"
+    out["rollout_learn_config"] = f"{E} envs/GPU, eps-greedy IQN act K=32 (tcgen05), fused env step + auto-reset, device replay, 1 update of {B} per vector step"
 
     if int(os.environ.get("RANK", 0)) == 0 and world == 1:
         # CPU baseline for the update: the numpy oracle (port of IQNAgent.train) on the host
