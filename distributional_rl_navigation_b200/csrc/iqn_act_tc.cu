@@ -7,7 +7,8 @@
 // (132 GFLOP per vector step).  Only the argmax of the mean is consumed, so operands are bf16 with fp32 accumulation
 // (the fp32 FFMA kernel in iqn.cu stays the parity path for training and for act_eval's quantile outputs).
 //
-// One persistent CTA per SM, 256 threads, a tile = 128 rows = 4 environments x 32 taus:
+// One persistent CTA per SM, 512 threads = two groups of 256, each group owns one tile (128 rows = 4 environments x 32 taus)
+// at a time, so that one group's epilogue overlaps the other group's MMAs:
 //   * all four weight matrices live in shared memory for the whole kernel as bf16 K-major core-matrix tiles
 //     (pre-packed by iqn_pack_tc, 63.5 KB);
 //   * A operands are produced in-kernel and written straight into the same UMMA canonical layout (no swizzle):
@@ -27,7 +28,8 @@ namespace {
 
 using namespace iqn;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;            // two tile groups x 256 threads (8 warps: 4 TMEM lane quadrants x 2 column halves)
+constexpr int kGroupThreads = 256;
 constexpr int kRows = 128;              // rows per tile (UMMA M)
 constexpr int kTaus = 32;               // quantile samples per environment (ObsEncoder.K)
 constexpr int kEnvsPerTile = kRows / kTaus;
@@ -39,7 +41,8 @@ constexpr int kWcEl = kFeat * kCos, kW1El = kHid * kFeat, kW2El = kHid * kHid, k
 constexpr int kPackedTcEl = kWcEl + kW1El + kW2El + kW3El;       // 31 744 bf16 = 63 488 bytes
 
 // TMEM column bases of the four accumulators
-constexpr uint32_t kD1 = 0, kD2 = 208, kD3 = 272, kD4 = 336;
+// (per tile group: 256 columns; D2 / D3 / D4 reuse D1's columns, which the first epilogue has drained by then)
+constexpr uint32_t kD1 = 0, kD2 = 0, kD3 = 64, kD4 = 128;
 
 // UMMA canonical K-major layout without swizzle: 8 x 8 (bf16) core matrices of 128 contiguous bytes; the core matrices of
 // one 8-row group are contiguous along K (LBO = 128 B) and row groups follow each other (SBO = (K/8) * 128 B).
@@ -48,14 +51,20 @@ __host__ __device__ constexpr int tile_offset(int r, int k, int K)       // in e
     return (r >> 3) * (K * 8) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
 }
 
-struct __align__(128) Smem {
-    __nv_bfloat16 wc[kWcEl], w1[kW1El], w2[kW2El], w3[kW3El];
-    __nv_bfloat16 a0[kRows * kCos], a1[kRows * kFeat], a2[kRows * kHid], a3[kRows * kHid];
+// per tile-group buffers (two groups of 256 threads keep two tiles in flight per CTA)
+struct __align__(128) GroupSmem {
+    __nv_bfloat16 x0[kRows * kCos];        // A0 (cos features), later A2, later A3: each is dead before the next is written
+    __nv_bfloat16 a1[kRows * kFeat];
     float feat[kEnvsPerTile * kFeat];
-    float bc[kFeat], b1[kHid], b2[kHid], b3[kN4];
     float x[kEnvsPerTile * 28];
     float tau[kRows];
     unsigned long long bar;
+};
+
+struct __align__(128) Smem {
+    __nv_bfloat16 wc[kWcEl], w1[kW1El], w2[kW2El], w3[kW3El];
+    GroupSmem g[2];
+    float bc[kFeat], b1[kHid], b2[kHid], b3[kN4];
     uint32_t tmem_base;
 };
 
@@ -102,6 +111,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kGroupThreads) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 {
@@ -112,6 +122,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 consecutive columns of this thread's row with ONE round trip to TMEM
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ void store_chunk(__nv_bfloat16* base, int r, int kc, int K, const float (&v)[8])
@@ -135,6 +162,8 @@ __device__ __forceinline__ void issue_layer(const __nv_bfloat16* A, const __nv_b
     umma_commit(bar);
 }
 
+// Two groups of 256 threads per CTA, each owning one 128-row tile at a time (its own A buffers, TMEM columns and
+// mbarrier): while one group runs an epilogue on the CUDA cores the other group's MMAs occupy the tensor core.
 __global__ void __launch_bounds__(kThreads, 1)
 iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ obs,
                   const float* __restrict__ taus, const float* __restrict__ cvar, float cvar_scalar,
@@ -143,8 +172,11 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int g = t >> 8, tg = t & 255;                      // tile group, thread index inside the group
+    const int half = (warp >> 2) & 1;                        // column half handled by this warp (warps q and q+4 share a lane quadrant)
+    GroupSmem& gs = s.g[g];
 
-    // ---- one-time setup: weights + biases to shared memory, TMEM allocation, mbarrier ----
+    // ---- one-time setup: weights + biases to shared memory, TMEM allocation, mbarriers ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(Wp);
         uint4* dst = reinterpret_cast<uint4*>(s.wc);        // wc, w1, w2, w3 are contiguous in Smem and in the packed buffer
@@ -157,59 +189,65 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (t == 32) mbar_init(&s.bar, 1);
+    if (tg == 32) mbar_init(&gs.bar, 1);
     fence_async_smem();
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = s.tmem_base;
+    const uint32_t tmem = s.tmem_base + (uint32_t)g * 256u;           // this group's 256 TMEM columns
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;     // this warp's TMEM lane quadrant
-    const int half = warp >> 2;                                       // column half handled by this warpgroup
     const int row = (warp & 3) * 32 + lane;                           // TMEM lane == tile row of this thread
     uint32_t phase = 0;
 
     const long long n_tiles = (B + kEnvsPerTile - 1) / kEnvsPerTile;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tile_step = (long long)gridDim.x * 2;
+    long long tile = (long long)blockIdx.x * 2 + g;
+
+    // inputs of a tile, one element per thread: threads 0..127 carry tau of row tg, threads 128..239 one element of the
+    // tile's 4 x 26 observation block
+    auto load_in = [&](long long tl) -> float {
+        if (tl >= n_tiles) return 0.f;
+        if (tg < kRows) {
+            const long long b = tl * kEnvsPerTile + tg / kTaus;
+            return b < B ? taus[b * kTaus + (tg % kTaus)] * (cvar != nullptr ? cvar[b] : cvar_scalar) : 0.f;   // model.py:153
+        }
+        const int i = tg - kRows, e = i / 28, k = i % 28;
+        const long long b = tl * kEnvsPerTile + e;
+        return (e < kEnvsPerTile && b < B && k < kObs) ? obs[b * kObs + k] : 0.f;
+    };
+    float n_in = load_in(tile);
+
+    for (; tile < n_tiles; tile += tile_step) {
         const long long env0 = tile * kEnvsPerTile;
-        // ---- inputs ----
-        for (int idx = t; idx < kEnvsPerTile * 28; idx += kThreads) {
-            const int e = idx / 28, k = idx % 28;
-            const long long b = env0 + e;
-            s.x[idx] = (b < B && k < kObs) ? obs[b * kObs + k] : 0.f;
-        }
-        if (t < kRows) {
-            const long long b = env0 + t / kTaus;
-            float v = 0.f;
-            if (b < B) v = taus[b * kTaus + (t % kTaus)] * (cvar != nullptr ? cvar[b] : cvar_scalar);    // model.py:153
-            s.tau[t] = v;
-        }
-        __syncthreads();
+        if (tg < kRows) gs.tau[tg] = n_in;
+        else if (tg < kRows + kEnvsPerTile * 28) gs.x[tg - kRows] = n_in;
+        n_in = load_in(tile + tile_step);                    // prefetch the next tile's inputs: consumed one iteration later
+        group_sync(g);
         // ---- observation encoders (fp32, model.py:169-172) ----
-        for (int idx = t; idx < kEnvsPerTile * kFeat; idx += kThreads) {
+        for (int idx = tg; idx < kEnvsPerTile * kFeat; idx += kGroupThreads) {
             const int e = idx / kFeat, f = idx % kFeat;
-            const float* x = s.x + e * 28;
+            const float* x = gs.x + e * 28;
             float v;
             if (f < 16) v = fmaf(__ldg(P + oVW + f * 2 + 1), x[1], fmaf(__ldg(P + oVW + f * 2), x[0], __ldg(P + oVB + f)));
             else if (f < 32) {
-                const int g = f - 16;
-                v = fmaf(__ldg(P + oGW + g * 2 + 1), x[3], fmaf(__ldg(P + oGW + g * 2), x[2], __ldg(P + oGB + g)));
+                const int q = f - 16;
+                v = fmaf(__ldg(P + oGW + q * 2 + 1), x[3], fmaf(__ldg(P + oGW + q * 2), x[2], __ldg(P + oGB + q)));
             } else {
-                const int g = f - 32;
-                v = __ldg(P + oSB + g);
+                const int q = f - 32;
+                v = __ldg(P + oSB + q);
 #pragma unroll
-                for (int k = 0; k < 22; ++k) v = fmaf(__ldg(P + oSW + g * 22 + k), x[4 + k], v);
+                for (int k = 0; k < 22; ++k) v = fmaf(__ldg(P + oSW + q * 22 + k), x[4 + k], v);
             }
-            s.feat[idx] = v;
+            gs.feat[idx] = v;
         }
         // ---- A0 = cos(pi * i * tau), i = 0..63: thread (row, half) fills i in [32 half, 32 half + 32) by rotating
-        //      (cos, sin)(i0 * pi * tau) with (cos, sin)(pi * tau) ----
+        //      (cos, sin)(i pi tau) with (cos, sin)(pi tau), starting from an exact sincospif at i = 32 half ----
         {
-            const int r = t & 127, h = t >> 7;
-            const float tau = s.tau[r];
+            const float tau = gs.tau[row];
             float c1, s1, c, sn;
             sincospif(tau, &s1, &c1);
-            sincospif(32.f * (float)h * tau, &sn, &c);
+            sincospif(32.f * (float)half * tau, &sn, &c);
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
                 float v[8];
@@ -219,70 +257,98 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                     const float c2 = fmaf(c, c1, -sn * s1), s2 = fmaf(sn, c1, c * s1);
                     c = c2; sn = s2;
                 }
-                store_chunk(s.a0, r, h * 4 + kc, kCos, v);
+                store_chunk(gs.x0, row, half * 4 + kc, kCos, v);
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
 
         // ---- layer 1: D1[128 x 208] = A0 . Wc^T ----
-        if (t == 0) { tc_fence_after(); issue_layer(s.a0, s.wc, kCos, kFeat, tmem + kD1, &s.bar); }
-        mbar_wait(&s.bar, phase); phase ^= 1;
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.x0, s.wc, kCos, kFeat, tmem + kD1, &gs.bar); }
+        mbar_wait(&gs.bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            const float* feat = s.feat + (row / kTaus) * kFeat;
-            for (int ch = half * 13; ch < half * 13 + 13; ++ch) {           // 26 chunks of 8 columns, 13 per warpgroup
-                float v[8];
-                tmem_ld8(tmem + lane_base + kD1 + ch * 8, v);
+            // this warp's 104 columns [104 half, 104 half + 104) = 3 x 32 + 8
+            const float* feat = gs.feat + (row / kTaus) * kFeat;
+            const int c0 = half * 104;
+#pragma unroll 1
+            for (int blk = 0; blk < 3; ++blk) {
+                float v[32];
+                const int col = c0 + blk * 32;
+                tmem_ld32(tmem + lane_base + kD1 + col, v);
                 if (debug != nullptr && tile == 0)
-                    for (int j = 0; j < 8; ++j) debug[row * kFeat + ch * 8 + j] = v[j];
+                    for (int j = 0; j < 32; ++j) debug[row * kFeat + col + j] = v[j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + s.bc[ch * 8 + j], 0.f) * feat[ch * 8 + j];   // model.py:177-180
-                store_chunk(s.a1, row, ch, kFeat, v);
+                for (int q = 0; q < 4; ++q) {
+                    float u[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j] + s.bc[col + q * 8 + j], 0.f) * feat[col + q * 8 + j];   // model.py:177-180
+                    store_chunk(gs.a1, row, (col >> 3) + q, kFeat, u);
+                }
+            }
+            {
+                float v[8];
+                const int col = c0 + 96;
+                tmem_ld8(tmem + lane_base + kD1 + col, v);
+                if (debug != nullptr && tile == 0)
+                    for (int j = 0; j < 8; ++j) debug[row * kFeat + col + j] = v[j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + s.bc[col + j], 0.f) * feat[col + j];
+                store_chunk(gs.a1, row, col >> 3, kFeat, v);
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
 
         // ---- layer 2: D2[128 x 64] = A1 . W1^T ----
-        if (t == 0) { tc_fence_after(); issue_layer(s.a1, s.w1, kFeat, kHid, tmem + kD2, &s.bar); }
-        mbar_wait(&s.bar, phase); phase ^= 1;
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kFeat, kHid, tmem + kD2, &gs.bar); }
+        mbar_wait(&gs.bar, phase); phase ^= 1;
         tc_fence_after();
-        for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
-            float v[8];
-            tmem_ld8(tmem + lane_base + kD2 + ch * 8, v);
+        {
+            float v[32];
+            const int col = half * 32;
+            tmem_ld32(tmem + lane_base + kD2 + col, v);
             if (debug != nullptr && tile == 0)
-                for (int j = 0; j < 8; ++j) debug[kRows * kFeat + row * kHid + ch * 8 + j] = v[j];
+                for (int j = 0; j < 32; ++j) debug[kRows * kFeat + row * kHid + col + j] = v[j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + s.b1[ch * 8 + j], 0.f);
-            store_chunk(s.a2, row, ch, kHid, v);
+            for (int q = 0; q < 4; ++q) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j] + s.b1[col + q * 8 + j], 0.f);
+                store_chunk(gs.x0, row, (col >> 3) + q, kHid, u);          // A2 over the (consumed) A0
+            }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
 
         // ---- layer 3: D3[128 x 64] = A2 . W2^T ----
-        if (t == 0) { tc_fence_after(); issue_layer(s.a2, s.w2, kHid, kHid, tmem + kD3, &s.bar); }
-        mbar_wait(&s.bar, phase); phase ^= 1;
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.x0, s.w2, kHid, kHid, tmem + kD3, &gs.bar); }
+        mbar_wait(&gs.bar, phase); phase ^= 1;
         tc_fence_after();
-        for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
-            float v[8];
-            tmem_ld8(tmem + lane_base + kD3 + ch * 8, v);
+        {
+            float v[32];
+            const int col = half * 32;
+            tmem_ld32(tmem + lane_base + kD3 + col, v);
             if (debug != nullptr && tile == 0)
-                for (int j = 0; j < 8; ++j) debug[kRows * (kFeat + kHid) + row * kHid + ch * 8 + j] = v[j];
+                for (int j = 0; j < 32; ++j) debug[kRows * (kFeat + kHid) + row * kHid + col + j] = v[j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + s.b2[ch * 8 + j], 0.f);
-            store_chunk(s.a3, row, ch, kHid, v);
+            for (int q = 0; q < 4; ++q) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j] + s.b2[col + q * 8 + j], 0.f);
+                store_chunk(gs.x0, row, (col >> 3) + q, kHid, u);          // A3 over the (consumed) A2
+            }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
 
         // ---- output layer: D4[128 x 16] = A3 . W3^T, then mean over the 32 taus of each env (one warp) + argmax ----
-        if (t == 0) { tc_fence_after(); issue_layer(s.a3, s.w3, kHid, kN4, tmem + kD4, &s.bar); }
-        mbar_wait(&s.bar, phase); phase ^= 1;
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.x0, s.w3, kHid, kN4, tmem + kD4, &gs.bar); }
+        mbar_wait(&gs.bar, phase); phase ^= 1;
         tc_fence_after();
         if (half == 0) {
             float q[kN4];
@@ -316,7 +382,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
             }
         }
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
     }
 
     // ---- teardown ----
@@ -324,7 +390,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -370,7 +436,8 @@ extern "C" int iqn_act_tc(const float* d_params, const void* d_packed_tc, const 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (B + kEnvsPerTile - 1) / kEnvsPerTile;
-    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    const long long pairs = (n_tiles + 1) / 2;                     // two tile groups per CTA
+    const int grid = (int)(pairs < sms ? pairs : sms);
     iqn_act_tc_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(
         d_params, (const __nv_bfloat16*)d_packed_tc, d_obs, d_taus, d_cvar, cvar_scalar, d_qmean, d_greedy, d_debug, B);
     return mnv_launch_status("iqn_act_tc");
