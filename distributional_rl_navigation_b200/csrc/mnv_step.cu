@@ -20,6 +20,7 @@
 //     intersected along exactly (0,+-1)).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mnv_common.cuh"
@@ -36,7 +37,7 @@ struct KParams {
     double range, range_slack;
     double width, height;
     int n_substeps, n_beams, max_ep_steps, set_boundary;
-    int max_c, max_o, obs_dim, velocity_from_state;
+    int max_c, max_o, obs_dim, velocity_from_state, allow_tma;
     long long E;
     double beam_angle[MNV_MAX_BEAMS];
     double beam_cos[MNV_MAX_BEAMS];
@@ -64,6 +65,31 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// TMA (bulk async copy engine): one thread moves a whole 16-byte-aligned row slice global -> shared and signals an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -81,8 +107,28 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     const int D = K.obs_dim;
     float* my_obs = s_obs + tid * D;
     double* s_ob = reinterpret_cast<double*>(s_obs + ((kBlock * D + 3) & ~3));   // obstacle rows of this CTA
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ob + 3 * K.max_o * kBlock);
     const int max_o = K.max_o;
 
+    // ---- (optional, MNV_TMA=1) obstacle table slice of every warp -> shared memory with the TMA bulk-copy engine: 3*max_o rows of 32 consecutive
+    //      environments (256 contiguous bytes each), issued by the warp's lane 0 and tracked by the warp's own mbarrier.  The rows are first
+    //      needed after the sub-step loop, so this DRAM round trip overlaps the integration.  Ragged / masked / odd-E
+    //      launches (rows not 16-byte aligned or not full) use per-thread cp.async instead. ----
+    const bool use_tma = K.allow_tma && (e0 + kBlock <= E) && ((E & 1) == 0) && (STEP || P.mask == nullptr) && max_o > 0;
+    const int warp_in_cta = tid >> 5;
+    unsigned long long* my_bar = s_bar + warp_in_cta;             // one mbarrier per warp: no CTA-wide sync needed
+    if (use_tma) {
+        if ((tid & 31) == 0) {
+            mbar_init(my_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(my_bar, (unsigned)(3 * max_o * 32 * sizeof(double)));
+            const double* po = P.obst + e0 + warp_in_cta * 32;
+            double* ps = s_ob + warp_in_cta * 32;
+            for (int row = 0; row < 3 * max_o; ++row, po += E, ps += kBlock)
+                tma_bulk_g2s(ps, po, (unsigned)(32 * sizeof(double)), my_bar);
+        }
+        __syncwarp();                                              // the warp's barrier is initialised before its lanes poll it
+    }
     if (live) {
         double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
         const double gx = P.goal[e], gy = P.goal[E + e];
@@ -105,10 +151,10 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 pc += E;
             }
         }
-        // ---- obstacle rows -> shared memory, asynchronously (after the loads the integration is waiting for): they are
-        //      first needed after the sub-step loop, so this DRAM round trip overlaps the integration; each thread
-        //      copies, and later reads, only its own column ----
-        {
+        // ---- staging of the obstacle rows with per-thread cp.async (each thread copies, and later reads, only its own column):
+        //      issued after the loads the integration is waiting for; first needed after the sub-step loop, so this DRAM
+        //      round trip overlaps the integration ----
+        if (!use_tma) {
             const double* po = P.obst + e;
             for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
             cp_async_commit();
@@ -177,7 +223,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         // ---- obstacles -> robot frame, registers.  q is pre-multiplied by sigma = +1 (robot outside the circle) or -1
         //      (inside) so that "the nearer root can be in front" reads tc >= 0 in both cases; obstacles that cannot be
         //      reached within the sonar range get r2 = -1 (discriminant always negative). ----
-        cp_async_wait_all();
+        if (use_tma) mbar_wait(my_bar, 0); else cp_async_wait_all();
         const double* ob = s_ob + tid;
         float qx[MAXO], qy[MAXO], r2[MAXO];                     // fp32: only the conservative candidate filter uses them
         bool force_slow = false;                                // robot within 1e-9 of a circle: decide everything exactly
@@ -298,7 +344,7 @@ template <bool STEP>
 int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
-    const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double);
+    const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + 8 * (kBlock / 32);
 #define MNV_LAUNCH(MC, MO)                                                                                   \
     do {                                                                                                     \
         auto kern = mnv_env_kernel<MC, MO, STEP>;                                                            \
@@ -340,6 +386,9 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
     K.width = p->width; K.height = p->height;
     K.n_beams = p->n_beams; K.max_ep_steps = p->max_episode_steps; K.set_boundary = p->set_boundary;
     K.max_c = max_c; K.max_o = max_o; K.obs_dim = 4 + 2 * p->n_beams; K.E = E;
+    { static int tma = -1; if (tma < 0) { const char* e = getenv("MNV_TMA"); tma = (e != nullptr && e[0] == '1') ? 1 : 0; } K.allow_tma = tma; }
+    // MNV_TMA=1 stages the obstacle rows with the TMA bulk-copy engine (UBLKCP) instead of per-thread cp.async (LDGSTS).
+    // Measured A/B in one process (profiles/README.md): 25.03 us vs 24.18 us per step -> cp.async is the default.
     // Sonar.compute_phi / compute_beam_angles (robot.py:14-21)
     const double phi = p->sonar_angle / (p->n_beams - 1), a0 = -p->sonar_angle / 2;
     for (int i = 0; i < p->n_beams; ++i) {
