@@ -25,6 +25,7 @@ UNIT = "env_steps/s"
 N_CORES, N_OBS, N_BEAMS = 4, 8, 11
 ENVS_PER_GPU = 65536
 N_BATCHES = 8
+NCU_DRAM_BYTES_PER_LAUNCH = 22.575e6     # measured, profiles/r1_step_kernel_v3_ncu_full.csv (algorithmic read volume: 22.5 MB)
 
 
 def algorithmic_bytes_per_env_step(n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS, s=8):
@@ -262,7 +263,10 @@ def run_b200(args):
                        "launch": f"CUDA graph of {chunk} mnv_step launches x {n_rep} replays + {rem} eager",
                        "timed_region_ms": round(times[0], 4)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E == ENVS_PER_GPU else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                           "(profiles/r1_step_kernel_v3_ncu_full.csv); the 9.6 MB of writes were still in L2 "
+                                           "when the profiled launch ended", "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": "mnv_env_kernel<4,8,true>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env0.h2d_bytes_per_step() * world,
                     "d2h_bytes_per_step": env0.d2h_bytes_per_step() * world, "checksum": checksum,
