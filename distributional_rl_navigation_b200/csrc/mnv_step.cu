@@ -340,9 +340,204 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     for (int i = (n4 << 2) + lane; i < n; i += 32) dst[i] = src[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Dense maps (BASELINE configs[4]: 32 obstacles x 64 beams, few thousand envs per GPU): ONE WARP PER ENVIRONMENT.
+// A thread-per-env mapping leaves a 16 384-env batch with 3.5 warps per SM and 2 048 serial ray/circle tests per thread;
+// here lane j owns obstacle j (and, in the sub-steps, vortex core j), every beam is one warp-wide test, and the
+// reference's ordered first-hit scan (robot.py:192-195, Q3) is rebuilt from warp ballots:
+//   V  = ballot(valid hit on my obstacle)                      valid = real root, 0 <= t <= range (robot.py:172-190)
+//   p(j) = highest set bit of V below lane j                   the previously recorded hit when the scan reaches j
+//   Bk = ballot(valid_j && p(j) exists && t_j >= t_p(j))       the scan breaks at the first such j
+//   result = Bk ? p(ffs(Bk)) : highest set bit of V            (the recorded hits form a strictly decreasing run)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDenseWarps = 4;
+
+template <bool STEP>
+__global__ void __launch_bounds__(kDenseWarps * 32)
+mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
+{
+    extern __shared__ __align__(16) float s_obs[];                 // [kDenseWarps][obs_dim]
+    const long long E = K.E;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long e = (long long)blockIdx.x * kDenseWarps + w;
+    const int D = K.obs_dim;
+    float* my_obs = s_obs + w * D;
+    if (e >= E) return;                                            // warp-uniform
+    if (!STEP && P.mask != nullptr && P.mask[e] == 0) return;
+
+    double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
+    const double gx = P.goal[e], gy = P.goal[E + e];
+    double c, s;
+    sincos(th, &s, &c);
+    double vx, vy, reward = 0.0;
+    int ep = 0;
+
+    // lane i < max_c owns vortex core i (k = Gs / 2pi carries the spin in its sign)
+    double cx = 0.0, cy = 0.0, ck = 0.0;
+    if (lane < K.max_c) {
+        cx = __ldg(P.cores + (long long)lane * E + e);
+        cy = __ldg(P.cores + (long long)(K.max_c + lane) * E + e);
+        ck = __ldg(P.cores + (long long)(2 * K.max_c + lane) * E + e) * (1.0 / (2.0 * MNV_PI));
+    }
+    // lane j < max_o owns obstacle j
+    double ox = 0.0, oy = 0.0, orad = -1.0;
+    if (lane < K.max_o) {
+        ox = __ldg(P.obst + (long long)lane * E + e);
+        oy = __ldg(P.obst + (long long)(K.max_o + lane) * E + e);
+        orad = __ldg(P.obst + (long long)(2 * K.max_o + lane) * E + e);
+    }
+    auto current = [&](double px, double py, double& ux, double& uy) {
+        const double dx = cx - px, dy = cy - py;
+        const double d2 = fma(dx, dx, dy * dy);
+        const double f = ck * (d2 <= K.core_r2 ? K.inv_core_r2 : fast_rcp(d2 > 0.0 ? d2 : 1.0));   // empty lanes: ck = 0
+        ux = -dy * f; uy = dx * f;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {                    // sum over the (<= 8) core lanes, every lane gets the total
+            ux += __shfl_xor_sync(0xffffffffu, ux, off);
+            uy += __shfl_xor_sync(0xffffffffu, uy, off);
+        }
+        ux = __shfl_sync(0xffffffffu, ux, 0); uy = __shfl_sync(0xffffffffu, uy, 0);   // lanes 8..31 hold zeros: take group 0
+    };
+
+    if (STEP) {
+        const int action = P.action[e];
+        ep = P.ep_step[e];
+        const int ai = action / 3, wi = action - 3 * ai;
+        const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
+        const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+        vx = 0.0; vy = 0.0;
+        for (int it = 0; it < K.n_substeps; ++it) {
+            double ux, uy;
+            current(x, y, ux, uy);
+            vx = fma(sp, c, ux); vy = fma(sp, s, uy);              // robot.py:98-100 (Q6)
+            x = fma(vx, K.dt, x); y = fma(vy, K.dt, y);            // robot.py:105-107
+            sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
+            sp = sp < 0.0 ? 0.0 : sp;                              // robot.py:114
+            sp = sp > K.max_speed ? K.max_speed : sp;
+            th = __dadd_rn(th, wdt);                               // robot.py:117
+            if (th < 0.0 || th >= 2.0 * MNV_PI) {                  // robot.py:120-123
+#pragma unroll 1
+                while (th < 0.0) th += 2.0 * MNV_PI;
+#pragma unroll 1
+                while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+            }
+            const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
+            c = c2; s = s2;
+            if (P.traj != nullptr && lane == 0) {
+                P.traj[(long long)(2 * it) * E + e] = x; P.traj[(long long)(2 * it + 1) * E + e] = y;
+            }
+        }
+        const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+        reward = K.pen_step + (dis_before - dis_after);            // marinenav_env.py:220,229
+    } else {
+        if (K.velocity_from_state) {
+            double ux, uy;
+            current(x, y, ux, uy);
+            vx = fma(sp, c, ux); vy = fma(sp, s, uy);
+            if (lane == 0) { P.velocity[e] = vx; P.velocity[E + e] = vy; }
+        } else { vx = P.velocity[e]; vy = P.velocity[E + e]; }
+    }
+
+    if (lane == 0) {                                               // observation head (marinenav_env.py:278-293)
+        my_obs[0] = (float)fma(c, vx, s * vy);
+        my_obs[1] = (float)fma(c, vy, -s * vx);
+        my_obs[2] = (float)fma(c, gx - x, s * (gy - y));
+        my_obs[3] = (float)fma(c, gy - y, -s * (gx - x));
+    }
+
+    // ---- my obstacle in the robot frame ----
+    const bool on = orad > 0.0;
+    const double dxo = ox - x, dyo = oy - y;
+    const double d2o = fma(dxo, dxo, dyo * dyo);
+    const double qx = fma(c, dxo, s * dyo), qy = fma(c, dyo, -s * dxo), rr = orad * orad;
+    const double lim = K.range_slack + orad;
+    const bool relevant = on && d2o <= lim * lim;                  // reachable within the sonar range at all
+    const bool borderline = on && fabs(d2o - rr) <= 1e-9 * rr;     // robot on the circle: never filter
+    const float sg = d2o < rr ? -1.f : 1.f;                        // inside the circle the nearer root is in front iff tc <= 0
+    const float qxf = sg * (float)qx, qyf = sg * (float)qy, r2f = (float)rr;
+
+    // ---- Q4: collision against the nearest CENTRE only (marinenav_env.py:329-336): warp arg-min ----
+    double best_d2 = on ? d2o : INFINITY, best_r = orad;
+    int best_i = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best_d2, off), orr = __shfl_xor_sync(0xffffffffu, best_r, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        // ties: the lowest obstacle index wins, like the first minimum of a sequential scan
+        if (od < best_d2 || (od == best_d2 && oi < best_i)) { best_d2 = od; best_r = orr; best_i = oi; }
+    }
+
+    // ---- sonar: one warp-wide ray/circle test per beam ----
+    for (int b = 0; b < K.n_beams; ++b) {
+        const double ang = th + K.beam_angle[b];                   // robot.py:131 (not wrapped)
+        double bx = K.beam_cos[b], by = K.beam_sin[b];
+        if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }             // Q10
+        else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }
+        const float bxf = (float)bx, byf = (float)by;
+        // conservative fp32 filter (see mnv_env_kernel): real roots and the nearer root not behind the robot, 1e-3 margin
+        const float tcf = fmaf(qxf, bxf, qyf * byf), crf = fmaf(qxf, byf, -qyf * bxf);
+        const bool cand = relevant && (borderline || fminf(fmaf(-crf, crf, r2f), tcf) >= -1e-3f);
+        float hx = 0.f, hy = 0.f;
+        if (__any_sync(0xffffffffu, cand)) {
+            bool valid = false;
+            double t = 0.0;
+            if (cand) {                                            // exact fp64 decision (robot.py:164-190)
+                const double tc = fma(qx, bx, qy * by), cr = fma(qx, by, -qy * bx);
+                const double disc = fma(-cr, cr, rr);
+                if (disc >= 0.0) {
+                    const double h = sqrt(disc);
+                    t = tc > 0.0 ? tc - h : tc + h;                // nearer root first (robot.py:184)
+                    valid = (t <= K.range) && (t >= 0.0);
+                }
+            }
+            const unsigned V = __ballot_sync(0xffffffffu, valid);
+            if (V != 0u) {
+                const unsigned below = V & ((1u << lane) - 1u);
+                const int pj = below ? 31 - __clz(below) : -1;     // previous valid hit in list order
+                const double tp = __shfl_sync(0xffffffffu, t, pj < 0 ? 0 : pj);
+                const unsigned Bk = __ballot_sync(0xffffffffu, valid && pj >= 0 && t >= tp);
+                int res;
+                if (Bk == 0u) res = 31 - __clz(V);
+                else {
+                    const int f = __ffs(Bk) - 1;
+                    const unsigned bf = V & ((1u << f) - 1u);
+                    res = 31 - __clz(bf);                          // bf != 0: a breaking lane has a predecessor
+                }
+                const double tr = __shfl_sync(0xffffffffu, t, res);
+                hx = (float)(tr * bx); hy = (float)(tr * by);      // marinenav_env.py:314-320
+            }
+        }
+        if (lane == 0) { my_obs[4 + 2 * b] = hx; my_obs[5 + 2 * b] = hy; }
+    }
+
+    if (STEP && lane == 0) {
+        int done = 0, info = MNV_INFO_NORMAL;                      // marinenav_env.py:240-257 (Q5)
+        const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
+        if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
+        else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
+        else if (best_d2 < INFINITY && sqrt(best_d2) <= best_r + K.robot_r) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
+        else if (sqrt(fma(x - gx, x - gx, (y - gy) * (y - gy))) <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
+        P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
+        P.velocity[e] = vx; P.velocity[E + e] = vy;
+        P.ep_step[e] = ep + 1;
+        P.reward[e] = (float)reward;
+        P.done[e] = (uint8_t)done;
+        P.info[e] = (uint8_t)info;
+    }
+    __syncwarp();
+    float* dst = P.obs + e * D;                                    // 8-byte aligned rows (D even): float2 stores
+    for (int i = lane; i < (D >> 1); i += 32)
+        reinterpret_cast<float2*>(dst)[i] = reinterpret_cast<const float2*>(my_obs)[i];
+}
+
 template <bool STEP>
 int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
 {
+    if (K.max_o > 16) {                                            // dense maps: one warp per environment
+        const unsigned dgrid = (unsigned)((K.E + kDenseWarps - 1) / kDenseWarps);
+        mnv_env_dense_kernel<STEP><<<dgrid, kDenseWarps * 32, (size_t)kDenseWarps * K.obs_dim * sizeof(float), st>>>(P, K);
+        return mnv_launch_status(STEP ? "mnv_step(dense)" : "mnv_observe(dense)");
+    }
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
     const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + 8 * (kBlock / 32);
 #define MNV_LAUNCH(MC, MO)                                                                                   \
@@ -356,8 +551,7 @@ int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
     } while (0)
     if (K.max_c <= 4 && K.max_o <= 8) MNV_LAUNCH(4, 8);
     else if (K.max_c <= 8 && K.max_o <= 10) MNV_LAUNCH(8, 10);
-    else if (K.max_c <= 8 && K.max_o <= 16) MNV_LAUNCH(8, 16);
-    else MNV_LAUNCH(8, 32);
+    else MNV_LAUNCH(8, 16);
 #undef MNV_LAUNCH
     return mnv_launch_status(STEP ? "mnv_step" : "mnv_observe");
 }
