@@ -28,7 +28,8 @@ struct Smem {
     float c[R * LD208];            // relu(cos_embedding(cos)); the backward pass overwrites it with dzc
     float h1[R * LD64];            // ... overwritten with dz1
     float h2[R * LD64];            // ... overwritten with dz2
-    float w[13312];                // weight stage (largest matrix: 208 x 64)
+    float w[13312];                // weight stage: two halves (reduction rows [0,RED/2) and [RED/2,RED)), filled by cp.async
+    float w3[kAct * kHid + 12];    // output layer weights + bias of the network being evaluated
     float dfp[16 * kFeat];         // per row-group partial sums of d(feat)
     float feat[8 * kFeat];
     float dfeat[8 * kFeat];
@@ -41,34 +42,53 @@ struct Smem {
 };
 
 // out(m, n) = sum_{r < RED} xf(r, m) * Y(r, n)     m in [0, M), n in [0, N)
-// thread tile MT x NT with (M/MT)*(N/NT) == 256 threads.  Y is either a shared-memory matrix [RED][ldy] read with
-// float4 (NT % 4 == 0) / scalar loads, or, if yf is given (YF != nullptr_t), a functor.
-template <int RED, int M, int N, int MT, int NT, class XF, class YF, class Epi>
-__device__ __forceinline__ void tile_mm(XF xf, YF yf, Epi epi)
-{
+// thread tile MT x NT with (M/MT)*(N/NT) == 256 threads.  yf(r, n0, yv) loads NT values of row r starting at column n0.
+template <int M, int N, int MT, int NT>
+struct TileAcc {
     static_assert((M / MT) * (N / NT) == kThreads && M % MT == 0 && N % NT == 0, "tile shape");
-    const int tn = threadIdx.x % (N / NT), tm = threadIdx.x / (N / NT);
-    const int m0 = tm * MT, n0 = tn * NT;
     float acc[MT][NT];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-    for (int r = 0; r < RED; ++r) {
-        float xv[MT], yv[NT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) xv[i] = xf(r, m0 + i);
-        yf(r, n0, yv);
+    int m0, n0;
+    __device__ __forceinline__ TileAcc()
+    {
+        const int tn = threadIdx.x % (N / NT), tm = threadIdx.x / (N / NT);
+        m0 = tm * MT; n0 = tn * NT;
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+            for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
     }
+    // accumulate reduction rows [r0, r1); yf sees the row index relative to yrow0
+    template <class XF, class YF>
+    __device__ __forceinline__ void run(int r0, int r1, int yrow0, XF xf, YF yf)
+    {
+#pragma unroll 2
+        for (int r = r0; r < r1; ++r) {
+            float xv[MT], yv[NT];
 #pragma unroll
-    for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < MT; ++i) xv[i] = xf(r, m0 + i);
+            yf(r - yrow0, n0, yv);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) epi(m0 + i, n0 + j, acc[i][j]);
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+        }
+    }
+    template <class Epi>
+    __device__ __forceinline__ void finish(Epi epi)
+    {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) epi(m0 + i, n0 + j, acc[i][j]);
+    }
+};
+
+template <int RED, int M, int N, int MT, int NT, class XF, class YF, class Epi>
+__device__ __forceinline__ void tile_mm(XF xf, YF yf, Epi epi)
+{
+    TileAcc<M, N, MT, NT> t;
+    t.run(0, RED, 0, xf, yf);
+    t.finish(epi);
 }
 
 // Y loaders for a shared-memory matrix [RED][ld]
@@ -90,16 +110,54 @@ struct YMat {
     }
 };
 
-__device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int n)
+// ---- weight staging: global [RED][N] fp32 -> shared memory with cp.async, in two halves of the reduction dimension.
+// While a GEMM consumes half 0 its half 1 is in flight, and while it consumes half 1 the NEXT GEMM's half 0 is in flight,
+// so only the very first half of a kernel is an exposed L2 round trip.
+constexpr int kHalfStage = 13312 / 2;                              // floats per half buffer (largest matrix / 2)
+
+__device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int n)
 {
-    for (int i = threadIdx.x * 4; i < n; i += kThreads * 4)      // n % 4 == 0, both 16-byte aligned
-        *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+    for (int i = threadIdx.x * 4; i < n; i += kThreads * 4) {       // n % 4 == 0, both 16-byte aligned
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// request half 0 of a [RED][N] matrix into buffer A (= s.w)
+__device__ __forceinline__ void request_first_half(Smem& s, const float* __restrict__ W, int red, int n)
+{
+    stage_async(s.w, W, (red / 2) * n);
+}
+
+// out = xf x W with W [RED][N] in global memory whose half 0 has already been requested into s.w; after half 1 landed the
+// first half of `next` ([next_red][next_n], may be null) is requested.  Ends with the epilogue, no trailing barrier.
+template <int RED, int M, int N, int MT, int NT, class XF, class Epi>
+__device__ __forceinline__ void tile_mm_staged(Smem& s, const float* __restrict__ W, const float* __restrict__ next, int next_red,
+                                               int next_n, XF xf, Epi epi)
+{
+    static_assert(RED % 2 == 0 && ((RED / 2) * N) % 4 == 0 && (RED / 2) * N <= kHalfStage, "stage halves");
+    float* A = s.w;
+    float* B = s.w + kHalfStage;
+    TileAcc<M, N, MT, NT> t;
+    stage_wait();
+    __syncthreads();                                               // half 0 visible; nobody still reads buffer B
+    stage_async(B, W + (RED / 2) * N, (RED / 2) * N);
+    t.run(0, RED / 2, 0, xf, YMat<NT>{A, N});
+    stage_wait();
+    __syncthreads();                                               // half 1 visible; nobody still reads buffer A
+    if (next != nullptr) stage_async(A, next, (next_red / 2) * next_n);
+    t.run(RED / 2, RED, RED / 2, xf, YMat<NT>{B, N});
+    t.finish(epi);
 }
 
 // ObsEncoder.forward (model.py:160-186) for one 64-row tile; row r belongs to sample r / n_tau of the tile.
-// In: s.x (8 x 28, zero padded), s.tau (already multiplied by cvar).  Out: s.feat, s.cos, s.c, s.h1, s.h2, s.q.
-// P: flat parameters (torch layout); PT: packed transposes (iqn_pack).
-__device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* __restrict__ PT, int n_tau)
+// In: s.x (8 x 28, zero padded), s.tau (already multiplied by cvar); half 0 of PT's WcT ALREADY requested into s.w.
+// Out: s.feat, s.cos, s.c, s.h1, s.h2, s.q.  P: flat parameters (torch layout); PT: packed transposes (iqn_pack).
+// After the last staged GEMM the first half of `next` ([next_red][next_n]) is requested (the following pass's first matrix).
+__device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* __restrict__ PT, int n_tau,
+                             const float* __restrict__ next, int next_red, int next_n)
 {
     const int t = threadIdx.x;
     __syncthreads();
@@ -126,31 +184,27 @@ __device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* 
         const float pis = (float)(MNV_PI_D * (double)i);
         s.cos[r * LD64 + i] = cosf(s.tau[r] * pis);
     }
-    stage(s.w, PT + ptWc, kFeat * kCos);
-    __syncthreads();
-    // c = relu(cos_embedding(cos))  (model.py:177)
-    tile_mm<kCos, R, kFeat, 4, 13>([&](int k, int row) { return s.cos[row * LD64 + k]; }, YMat<13>{s.w, kFeat},
-                                   [&](int row, int f, float a) { s.c[row * LD208 + f] = fmaxf(a + __ldg(P + oCB + f), 0.f); });
-    __syncthreads();
-    stage(s.w, PT + ptW1, kFeat * kHid);
-    __syncthreads();
+    for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads)     // output layer of this network -> shared memory
+        s.w3[idx] = __ldg(P + oOW + idx);                          // (output_layer.weight and .bias are contiguous)
+    // c = relu(cos_embedding(cos))  (model.py:177)      [the staged GEMM starts with a barrier: cos / feat are visible]
+    tile_mm_staged<kCos, R, kFeat, 4, 13>(s, PT + ptWc, PT + ptW1, kFeat, kHid,
+                                          [&](int k, int row) { return s.cos[row * LD64 + k]; },
+                                          [&](int row, int f, float a) { s.c[row * LD208 + f] = fmaxf(a + __ldg(P + oCB + f), 0.f); });
     // h1 = relu(hidden_layer(feat * c))  (model.py:180-182)
-    tile_mm<kFeat, R, kHid, 4, 4>([&](int k, int row) { return s.c[row * LD208 + k] * s.feat[(row / n_tau) * kFeat + k]; },
-                                  YMat<4>{s.w, kHid},
-                                  [&](int row, int o, float a) { s.h1[row * LD64 + o] = fmaxf(a + __ldg(P + oH1B + o), 0.f); });
-    __syncthreads();
-    stage(s.w, PT + ptW2, kHid * kHid);
-    __syncthreads();
+    tile_mm_staged<kFeat, R, kHid, 4, 4>(s, PT + ptW1, PT + ptW2, kHid, kHid,
+                                         [&](int k, int row) { return s.c[row * LD208 + k] * s.feat[(row / n_tau) * kFeat + k]; },
+                                         [&](int row, int o, float a) { s.h1[row * LD64 + o] = fmaxf(a + __ldg(P + oH1B + o), 0.f); });
     // h2 = relu(hidden_layer_2(h1))  (model.py:183)
-    tile_mm<kHid, R, kHid, 4, 4>([&](int k, int row) { return s.h1[row * LD64 + k]; }, YMat<4>{s.w, kHid},
-                                 [&](int row, int o, float a) { s.h2[row * LD64 + o] = fmaxf(a + __ldg(P + oH2B + o), 0.f); });
+    tile_mm_staged<kHid, R, kHid, 4, 4>(s, PT + ptW2, next, next_red, next_n,
+                                        [&](int k, int row) { return s.h1[row * LD64 + k]; },
+                                        [&](int row, int o, float a) { s.h2[row * LD64 + o] = fmaxf(a + __ldg(P + oH2B + o), 0.f); });
     __syncthreads();
     // q = output_layer(h2)  (model.py:184)
     for (int idx = t; idx < R * kAct; idx += kThreads) {
         const int row = idx / kAct, a = idx % kAct;
-        float v = __ldg(P + oOB + a);
+        float v = s.w3[kAct * kHid + a];
 #pragma unroll 8
-        for (int k = 0; k < kHid; ++k) v = fmaf(s.h2[row * LD64 + k], __ldg(P + oOW + a * kHid + k), v);
+        for (int k = 0; k < kHid; ++k) v = fmaf(s.h2[row * LD64 + k], s.w3[a * kHid + k], v);
         s.q[row * 12 + a] = v;
     }
     __syncthreads();
@@ -193,8 +247,9 @@ iqn_forward_kernel(const float* __restrict__ P, const float* __restrict__ PT, co
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const long long tile = blockIdx.x;
     const int S = R / n_tau, t = threadIdx.x;
+    request_first_half(s, PT + ptWc, kCos, kFeat);
     load_inputs(s, obs, taus, cvar, cvar_scalar, B, n_tau, tile);
-    forward_tile(s, P, PT, n_tau);
+    forward_tile(s, P, PT, n_tau, nullptr, 0, 0);
     const long long s0 = tile * S;
     if (quantiles != nullptr) {
         for (int idx = t; idx < R * kAct; idx += kThreads) {
@@ -245,8 +300,9 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     constexpr int NT8 = kTrainTaus;
 
     // ---- target network on next_states (taus drawn first: Q9) -> T_j = r + gamma^n (1 - done) max_a Q'(s', tau_j) ----
+    request_first_half(s, PTTG + ptWc, kCos, kFeat);
     load_inputs(s, next_states, taus_t, nullptr, 1.f, B, NT8, tile);
-    forward_tile(s, PTG, PTTG, NT8);
+    forward_tile(s, PTG, PTTG, NT8, PTL + ptWc, kCos, kFeat);          // ... then prefetch the local network's first matrix
     if (t < R) {
         const long long b = s0 + t / NT8;
         float tv = 0.f;
@@ -262,7 +318,7 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
 
     // ---- local network on states ----
     load_inputs(s, states, taus_l, nullptr, 1.f, B, NT8, tile);
-    forward_tile(s, PL, PTL, NT8);
+    forward_tile(s, PL, PTL, NT8, PL + oH2W, kHid, kHid);              // ... then prefetch W2 (torch layout) for the backward pass
 
     // ---- pairwise quantile Huber loss (agent.py:289-295) and dL/dE ----
     float li = 0.f;
@@ -316,7 +372,6 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
         const float h = s.h2[r * LD64 + o];
         s.h2[r * LD64 + o] = h > 0.f ? s.dE[r] * __ldg(PL + oOW + s.act[r / NT8] * kHid + o) : 0.f;
     }
-    stage(s.w, PL + oH2W, kHid * kHid);                                              // W2 in torch layout [o][k]
     __syncthreads();
     // dW2[o][k] = sum_r dz2[r][o] h1[r][k] ; db2
     tile_mm<R, kHid, kHid, 4, 4>([&](int r, int o) { return s.h2[r * LD64 + o]; }, YMat<4>{s.h1, LD64},
@@ -327,9 +382,11 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
         g[oH2B + t] = acc;
     }
     __syncthreads();
-    // dz1 = (dz2 W2) * (h1 > 0), in place over h1
-    tile_mm<kHid, R, kHid, 4, 4>([&](int o, int r) { return s.h2[r * LD64 + o]; }, YMat<4>{s.w, kHid},
-                                 [&](int r, int k, float a) { float& h = s.h1[r * LD64 + k]; h = h > 0.f ? a : 0.f; });
+    // dz1 = (dz2 W2) * (h1 > 0), in place over h1  (W2 in torch layout [o][k], prefetched during the forward pass;
+    // W1 in torch layout is prefetched for dh0 meanwhile)
+    tile_mm_staged<kHid, R, kHid, 4, 4>(s, PL + oH2W, PL + oH1W, kHid, kFeat,
+                                        [&](int o, int r) { return s.h2[r * LD64 + o]; },
+                                        [&](int r, int k, float a) { float& h = s.h1[r * LD64 + k]; h = h > 0.f ? a : 0.f; });
     __syncthreads();
     // dW1[o][k] = sum_r dz1[r][o] h0[r][k], h0 = feat * c ; db1
     tile_mm<R, kHid, kFeat, 4, 13>([&](int r, int o) { return s.h1[r * LD64 + o]; },
@@ -344,12 +401,11 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
         for (int r = 0; r < R; ++r) acc += s.h1[r * LD64 + t];
         g[oH1B + t] = acc;
     }
-    stage(s.w, PL + oH1W, kHid * kFeat);                                             // W1 in torch layout [o][k]
     __syncthreads();
     // dh0 = dz1 W1 ; dzc = dh0 * feat * (c > 0) in place over c ; d(feat) += dh0 * c
     {
         const int tm = threadIdx.x / 16;                                             // row group of 4 rows (one sample = 2 groups)
-        tile_mm<kHid, R, kFeat, 4, 13>([&](int o, int r) { return s.h1[r * LD64 + o]; }, YMat<13>{s.w, kFeat},
+        tile_mm_staged<kHid, R, kFeat, 4, 13>(s, PL + oH1W, nullptr, 0, 0, [&](int o, int r) { return s.h1[r * LD64 + o]; },
                                        [&](int r, int k, float a) {
                                            float& cv = s.c[r * LD208 + k];
                                            const float c0 = cv;
