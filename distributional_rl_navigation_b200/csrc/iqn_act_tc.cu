@@ -9,8 +9,8 @@
 //
 // One persistent CTA per SM, 512 threads = two groups of 256, each group owns one tile (128 rows = 4 environments x 32 taus)
 // at a time, so that one group's epilogue overlaps the other group's MMAs:
-//   * all four weight matrices live in shared memory for the whole kernel as bf16 K-major core-matrix tiles
-//     (pre-packed by iqn_pack_tc, 63.5 KB);
+//   * all four weight matrices (with their bias as one extra reduction column) live in shared memory for the whole kernel
+//     as bf16 K-major core-matrix tiles (pre-packed by iqn_pack_tc, 73 KB);
 //   * A operands are produced in-kernel and written straight into the same UMMA canonical layout (no swizzle):
 //       A0 = cos(pi i tau)            (rotation recurrence from one sincospif per row)
 //       A1 = relu(D1 + b_c) * feat    A2 = relu(D2 + b_1)    A3 = relu(D3 + b_2)
@@ -36,9 +36,13 @@ constexpr int kEnvsPerTile = kRows / kTaus;
 constexpr int kN4 = 16;                 // output layer padded 9 -> 16 (UMMA N granularity at M = 128)
 constexpr int kTmemCols = 512;
 
+// The biases ride inside the GEMMs: every A operand carries one extra K-step whose first column is 1.0 (rest 0) and the
+// weight tiles carry the bias in that column, so the accumulators already hold W x + b and the epilogues are relu (and the
+// feature product) only.  Reduction lengths including that step:
+constexpr int kK0 = kCos + 16, kK1 = kFeat + 16, kK2 = kHid + 16, kK3 = kHid + 16;      // 80, 224, 80, 80
 // bf16 element counts of the packed weight tiles (core-matrix layout, see tile_offset)
-constexpr int kWcEl = kFeat * kCos, kW1El = kHid * kFeat, kW2El = kHid * kHid, kW3El = kN4 * kHid;
-constexpr int kPackedTcEl = kWcEl + kW1El + kW2El + kW3El;       // 31 744 bf16 = 63 488 bytes
+constexpr int kWcEl = kFeat * kK0, kW1El = kHid * kK1, kW2El = kHid * kK2, kW3El = kN4 * kK3;
+constexpr int kPackedTcEl = kWcEl + kW1El + kW2El + kW3El;       // 37 376 bf16 = 74 752 bytes
 
 // TMEM column bases of the four accumulators
 // (per tile group: 256 columns; D2 / D3 / D4 reuse D1's columns, which the first epilogue has drained by then)
@@ -53,8 +57,9 @@ __host__ __device__ constexpr int tile_offset(int r, int k, int K)       // in e
 
 // per tile-group buffers (two groups of 256 threads keep two tiles in flight per CTA)
 struct __align__(128) GroupSmem {
-    __nv_bfloat16 x0[kRows * kCos];        // A0 (cos features), later A2, later A3: each is dead before the next is written
-    __nv_bfloat16 a1[kRows * kFeat];
+    // ONE operand region per group: A0 (cos features, 16 KB) is consumed by layer 1 before the first epilogue overwrites
+    // the region with A1 (52 KB); A2 / A3 (16 KB each) are written after layers 2 / 3 have consumed A1 / A2.
+    __nv_bfloat16 a1[kRows * kK1];
     float feat[kEnvsPerTile * kFeat];
     float x[kEnvsPerTile * 28];
     float tau[kRows];
@@ -64,7 +69,7 @@ struct __align__(128) GroupSmem {
 struct __align__(128) Smem {
     __nv_bfloat16 wc[kWcEl], w1[kW1El], w2[kW2El], w3[kW3El];
     GroupSmem g[2];
-    float bc[kFeat], b1[kHid], b2[kHid], b3[kN4];
+    float enc[oCW];                        // the three observation encoders (weights + biases, fp32, state_dict order)
     uint32_t tmem_base;
 };
 
@@ -151,6 +156,13 @@ __device__ __forceinline__ void store_chunk(__nv_bfloat16* base, int r, int kc, 
     *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8, K)) = u;
 }
 
+// the bias K-step of an A operand: chunk kc = (1, 0, ..., 0), chunk kc + 1 = 0
+__device__ __forceinline__ void store_bias_step(__nv_bfloat16* base, int r, int kc, int K)
+{
+    *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8, K)) = make_uint4(0x00003f80u, 0u, 0u, 0u);      // bf16(1.0) = 0x3f80
+    *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8 + 8, K)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // issue the K/16 MMAs of one layer (one elected thread), then commit to the mbarrier
 __device__ __forceinline__ void issue_layer(const __nv_bfloat16* A, const __nv_bfloat16* B, int K, int N, uint32_t tmem_d,
                                             unsigned long long* bar)
@@ -181,9 +193,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
         const uint4* src = reinterpret_cast<const uint4*>(Wp);
         uint4* dst = reinterpret_cast<uint4*>(s.wc);        // wc, w1, w2, w3 are contiguous in Smem and in the packed buffer
         for (int i = t; i < kPackedTcEl / 8; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = t; i < kFeat; i += kThreads) s.bc[i] = P[oCB + i];
-        if (t < kHid) { s.b1[t] = P[oH1B + t]; s.b2[t] = P[oH2B + t]; }
-        if (t < kN4) s.b3[t] = t < kAct ? P[oOB + t] : 0.f;
+        for (int i = t; i < oCW; i += kThreads) s.enc[i] = P[i];
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(kTmemCols) : "memory");
@@ -229,15 +239,15 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
             const int e = idx / kFeat, f = idx % kFeat;
             const float* x = gs.x + e * 28;
             float v;
-            if (f < 16) v = fmaf(__ldg(P + oVW + f * 2 + 1), x[1], fmaf(__ldg(P + oVW + f * 2), x[0], __ldg(P + oVB + f)));
+            if (f < 16) v = fmaf(s.enc[oVW + f * 2 + 1], x[1], fmaf(s.enc[oVW + f * 2], x[0], s.enc[oVB + f]));
             else if (f < 32) {
                 const int q = f - 16;
-                v = fmaf(__ldg(P + oGW + q * 2 + 1), x[3], fmaf(__ldg(P + oGW + q * 2), x[2], __ldg(P + oGB + q)));
+                v = fmaf(s.enc[oGW + q * 2 + 1], x[3], fmaf(s.enc[oGW + q * 2], x[2], s.enc[oGB + q]));
             } else {
                 const int q = f - 32;
-                v = __ldg(P + oSB + q);
+                v = s.enc[oSB + q];
 #pragma unroll
-                for (int k = 0; k < 22; ++k) v = fmaf(__ldg(P + oSW + q * 22 + k), x[4 + k], v);
+                for (int k = 0; k < 22; ++k) v = fmaf(s.enc[oSW + q * 22 + k], x[4 + k], v);
             }
             gs.feat[idx] = v;
         }
@@ -257,16 +267,22 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                     const float c2 = fmaf(c, c1, -sn * s1), s2 = fmaf(sn, c1, c * s1);
                     c = c2; sn = s2;
                 }
-                store_chunk(gs.x0, row, half * 4 + kc, kCos, v);
+                store_chunk(gs.a1, row, half * 4 + kc, kK0, v);
             }
+            if (half == 0) store_bias_step(gs.a1, row, kCos / 8, kK0);
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
 
         // ---- layer 1: D1[128 x 208] = A0 . Wc^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.x0, s.wc, kCos, kFeat, tmem + kD1, &gs.bar); }
-        mbar_wait(&gs.bar, phase); phase ^= 1;
+        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
+            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.wc, kK0, kFeat, tmem + kD1, &gs.bar); }
+            __syncwarp();
+            mbar_wait(&gs.bar, phase);
+        }
+        phase ^= 1;
+        group_sync(g);
         tc_fence_after();
         {
             // this warp's 104 columns [104 half, 104 half + 104) = 3 x 32 + 8
@@ -282,9 +298,11 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float u[8];
+                    const float4 f0 = *reinterpret_cast<const float4*>(feat + col + q * 8), f1 = *reinterpret_cast<const float4*>(feat + col + q * 8 + 4);
+                    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j] + s.bc[col + q * 8 + j], 0.f) * feat[col + q * 8 + j];   // model.py:177-180
-                    store_chunk(gs.a1, row, (col >> 3) + q, kFeat, u);
+                    for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j], 0.f) * fv[j];   // model.py:177-180 (bias already in D1)
+                    store_chunk(gs.a1, row, (col >> 3) + q, kK1, u);
                 }
             }
             {
@@ -294,17 +312,23 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                 if (debug != nullptr && tile == 0)
                     for (int j = 0; j < 8; ++j) debug[row * kFeat + col + j] = v[j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + s.bc[col + j], 0.f) * feat[col + j];
-                store_chunk(gs.a1, row, col >> 3, kFeat, v);
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f) * feat[col + j];
+                store_chunk(gs.a1, row, col >> 3, kK1, v);
             }
+            if (half == 1) store_bias_step(gs.a1, row, kFeat / 8, kK1);
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
 
         // ---- layer 2: D2[128 x 64] = A1 . W1^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kFeat, kHid, tmem + kD2, &gs.bar); }
-        mbar_wait(&gs.bar, phase); phase ^= 1;
+        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
+            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kK1, kHid, tmem + kD2, &gs.bar); }
+            __syncwarp();
+            mbar_wait(&gs.bar, phase);
+        }
+        phase ^= 1;
+        group_sync(g);
         tc_fence_after();
         {
             float v[32];
@@ -316,17 +340,23 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
             for (int q = 0; q < 4; ++q) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j] + s.b1[col + q * 8 + j], 0.f);
-                store_chunk(gs.x0, row, (col >> 3) + q, kHid, u);          // A2 over the (consumed) A0
+                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j], 0.f);
+                store_chunk(gs.a1, row, (col >> 3) + q, kK2, u);           // A2 over the (consumed) A1
             }
+            if (half == 0) store_bias_step(gs.a1, row, kHid / 8, kK2);
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
 
         // ---- layer 3: D3[128 x 64] = A2 . W2^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.x0, s.w2, kHid, kHid, tmem + kD3, &gs.bar); }
-        mbar_wait(&gs.bar, phase); phase ^= 1;
+        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
+            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w2, kK2, kHid, tmem + kD3, &gs.bar); }
+            __syncwarp();
+            mbar_wait(&gs.bar, phase);
+        }
+        phase ^= 1;
+        group_sync(g);
         tc_fence_after();
         {
             float v[32];
@@ -338,17 +368,23 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
             for (int q = 0; q < 4; ++q) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j] + s.b2[col + q * 8 + j], 0.f);
-                store_chunk(gs.x0, row, (col >> 3) + q, kHid, u);          // A3 over the (consumed) A2
+                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j], 0.f);
+                store_chunk(gs.a1, row, (col >> 3) + q, kK3, u);           // A3 over the (consumed) A2
             }
+            if (half == 0) store_bias_step(gs.a1, row, kHid / 8, kK3);
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
 
         // ---- output layer: D4[128 x 16] = A3 . W3^T, then mean over the 32 taus of each env (one warp) + argmax ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.x0, s.w3, kHid, kN4, tmem + kD4, &gs.bar); }
-        mbar_wait(&gs.bar, phase); phase ^= 1;
+        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
+            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w3, kK3, kN4, tmem + kD4, &gs.bar); }
+            __syncwarp();
+            mbar_wait(&gs.bar, phase);
+        }
+        phase ^= 1;
+        group_sync(g);
         tc_fence_after();
         if (half == 0) {
             float q[kN4];
@@ -368,7 +404,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                 float v = q[a];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                q[a] = v * (1.f / kTaus) + s.b3[a];                                      // get_qvals: mean over taus (model.py:190)
+                q[a] = v * (1.f / kTaus);                                                // get_qvals: mean over taus (model.py:190); bias inside D4
             }
             const long long b = env0 + (warp & 3);
             if (lane == 0 && b < B) {
@@ -394,17 +430,20 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
     }
 }
 
-// fp32 parameters -> bf16 K-major core-matrix tiles: Wc [208][64], W1 [64][208], W2 [64][64], W3 [16][64] (rows >= 9 zero)
+// fp32 parameters -> bf16 K-major core-matrix tiles with the bias column appended:
+//   Wc [208][80], W1 [64][224], W2 [64][80], W3 [16][80] (rows >= 9 zero); column K_orig = bias, the other pad columns = 0
 __global__ void __launch_bounds__(256) iqn_pack_tc_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ W)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < kWcEl) { const int n = i / kCos, k = i % kCos; W[tile_offset(n, k, kCos)] = __float2bfloat16(P[oCW + i]); }
-    else if (i < kWcEl + kW1El) { const int j = i - kWcEl, n = j / kFeat, k = j % kFeat; W[kWcEl + tile_offset(n, k, kFeat)] = __float2bfloat16(P[oH1W + j]); }
-    else if (i < kWcEl + kW1El + kW2El) { const int j = i - kWcEl - kW1El, n = j / kHid, k = j % kHid; W[kWcEl + kW1El + tile_offset(n, k, kHid)] = __float2bfloat16(P[oH2W + j]); }
-    else if (i < kPackedTcEl) {
-        const int j = i - kWcEl - kW1El - kW2El, n = j / kHid, k = j % kHid;
-        W[kWcEl + kW1El + kW2El + tile_offset(n, k, kHid)] = __float2bfloat16(n < kAct ? P[oOW + n * kHid + k] : 0.f);
-    }
+    int base, n, k, K, Korig, rows, ow, ob;
+    if (i < kWcEl) { base = 0; K = kK0; Korig = kCos; rows = kFeat; ow = oCW; ob = oCB; n = i / K; k = i % K; }
+    else if (i < kWcEl + kW1El) { base = kWcEl; K = kK1; Korig = kFeat; rows = kHid; ow = oH1W; ob = oH1B; n = (i - base) / K; k = (i - base) % K; }
+    else if (i < kWcEl + kW1El + kW2El) { base = kWcEl + kW1El; K = kK2; Korig = kHid; rows = kHid; ow = oH2W; ob = oH2B; n = (i - base) / K; k = (i - base) % K; }
+    else if (i < kPackedTcEl) { base = kWcEl + kW1El + kW2El; K = kK3; Korig = kHid; rows = kAct; ow = oOW; ob = oOB; n = (i - base) / K; k = (i - base) % K; }
+    else return;
+    float v = 0.f;
+    if (n < rows) v = k < Korig ? P[ow + n * Korig + k] : (k == Korig ? P[ob + n] : 0.f);
+    W[base + tile_offset(n, k, K)] = __float2bfloat16(v);
 }
 
 }  // namespace

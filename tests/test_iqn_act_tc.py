@@ -32,12 +32,13 @@ def emulate(P, x, taus, cvar=1.0):
                            x[:, 2:4] @ P["goal_encoder.weight"].T + P["goal_encoder.bias"],
                            x[:, 4:26] @ P["sensor_encoder.weight"].T + P["sensor_encoder.bias"]], axis=1).astype(np.float32)
     cos = np.cos(np.pi * np.arange(64)[None, None, :] * t[:, :, None].astype(np.float64)).astype(np.float32).reshape(B * K, 64)
-    d1 = bf(cos) @ bf(P["cos_embedding.weight"]).T
-    h0 = np.maximum(d1 + P["cos_embedding.bias"], 0) * np.repeat(feat, K, axis=0)
-    d2 = bf(h0) @ bf(P["hidden_layer.weight"]).T
-    d3 = bf(np.maximum(d2 + P["hidden_layer.bias"], 0)) @ bf(P["hidden_layer_2.weight"]).T
-    d4 = bf(np.maximum(d3 + P["hidden_layer_2.bias"], 0)) @ bf(P["output_layer.weight"]).T
-    q = d4.reshape(B, K, 9).mean(axis=1) + P["output_layer.bias"]
+    # the biases ride inside the GEMMs as one extra reduction column (bf16-rounded like the weights)
+    d1 = bf(cos) @ bf(P["cos_embedding.weight"]).T + bf(P["cos_embedding.bias"])
+    h0 = np.maximum(d1, 0) * np.repeat(feat, K, axis=0)
+    d2 = bf(h0) @ bf(P["hidden_layer.weight"]).T + bf(P["hidden_layer.bias"])
+    d3 = bf(np.maximum(d2, 0)) @ bf(P["hidden_layer_2.weight"]).T + bf(P["hidden_layer_2.bias"])
+    d4 = bf(np.maximum(d3, 0)) @ bf(P["output_layer.weight"]).T + bf(P["output_layer.bias"])
+    q = d4.reshape(B, K, 9).mean(axis=1)
     return d1, d2, d3, d4, q
 
 
