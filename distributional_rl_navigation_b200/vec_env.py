@@ -81,6 +81,17 @@ class VecMarineNavEnv:
         return [seed]
 
     def params(self):
+        """mnv_params of the current attribute values (cached: rebuilt only when an attribute changed)."""
+        key = (self.num_beams, self.dt, self.N, tuple(float(v) for v in self.a), tuple(float(v) for v in self.w), self.max_speed,
+               self.robot_r, self.r, self.goal_dis, self.timestep_penalty, self.collision_penalty, self.goal_reward,
+               self.sonar_range, self.sonar_angle, bool(self.set_boundary), self.width, self.height)
+        if getattr(self, "_params_key", None) == key:
+            return self._params_cache
+        p = self._build_params()
+        self._params_key, self._params_cache = key, p
+        return p
+
+    def _build_params(self):
         p = _lib.default_params(self.num_beams)
         p.dt, p.n_substeps = self.dt, self.N
         for i in range(3):
@@ -148,7 +159,9 @@ class VecMarineNavEnv:
         return self._pinned
 
     def step_host(self, actions, auto_reset=True):
-        """numpy int actions [E] -> (obs f32 [E,D], reward f32 [E], done bool [E], info u8 [E]) numpy views of pinned buffers."""
+        """numpy int actions [E] -> (obs f32 [E,D], reward f32 [E], done bool [E], info u8 [E]) numpy views of pinned buffers.
+        (Overlapping the 7 MB device->host copy with the masked reset on a side stream and patching the re-observed rows on
+        the host was tried: the extra synchronisation points cost more than the overlap saves, 460 vs 340 us per step.)"""
         pin = self._pin()
         pin["action"].copy_(torch.as_tensor(actions, dtype=torch.int32))
         with torch.cuda.device(self.device):

@@ -167,3 +167,25 @@ def test_learn_single_env_and_vectorised_smoke(tmp_path, golden_dir):
                      updates_per_step=2)
     assert agent2.learning_timestep == 2 * 12 and len(agent2.device_memory) == min(50000, 2048 * 13)
     assert torch.isfinite(agent2.qnetwork_local.flat).all() and agent2.optimizer.step_count == agent2.learning_timestep
+
+
+def test_step_host_matches_device_step():
+    """The overlapped host-buffer path returns exactly what the plain device path computes (incl. auto-reset rows)."""
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+    E = 3000
+    a = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+    b = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+    o_a, o_b = a.reset_host().copy(), b.reset().cpu().numpy()
+    assert np.array_equal(o_a, o_b)
+    rng = np.random.RandomState(0)
+    n_done = 0
+    for t in range(60):
+        act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)   # full ahead: collisions happen
+        obs_h, rew_h, done_h, info_h = a.step_host(act)
+        obs_d, rew_d, done_d, info_d = b.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(obs_h, obs_d.cpu().numpy())
+        assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy().astype(bool))
+        assert np.array_equal(info_h, info_d.cpu().numpy())
+        assert torch.equal(a.buf["state"], b.buf["state"]) and torch.equal(a.buf["obs"], b.buf["obs"])
+        n_done += int(done_h.sum())
+    assert n_done > 0
