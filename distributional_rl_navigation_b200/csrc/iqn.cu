@@ -18,7 +18,9 @@ namespace {
 
 using namespace iqn;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;     // 8 warps per 64-row tile, thread tiles 4x13 / 4x4 / 13x4 (512 threads with 2x13 / 2x4 tiles measured slower: 145 vs 135 us per update, shared-memory-load bound)
+constexpr int kMT = 64 * 16 / kThreads;   // rows per thread tile: (64 / kMT) * 16 column groups == kThreads
+constexpr int kGroups = 64 / kMT;  // row groups of a tile (d(feat) partial sums)
 constexpr int R = 64;              // rows per tile
 constexpr int LD64 = 68;           // padded leading dimension of [64][64] activation tiles (== 4 mod 32, multiple of 4)
 constexpr int LD208 = 212;         // padded leading dimension of [64][208] activation tiles
@@ -30,7 +32,7 @@ struct Smem {
     float h2[R * LD64];            // ... overwritten with dz2
     float w[13312];                // weight stage: two halves (reduction rows [0,RED/2) and [RED/2,RED)), filled by cp.async
     float w3[kAct * kHid + 12];    // output layer weights + bias of the network being evaluated
-    float dfp[16 * kFeat];         // per row-group partial sums of d(feat)
+    float dfp[kGroups * kFeat];    // per row-group partial sums of d(feat)
     float feat[8 * kFeat];
     float dfeat[8 * kFeat];
     float x[8 * 28];
@@ -187,15 +189,15 @@ __device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* 
     for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads)     // output layer of this network -> shared memory
         s.w3[idx] = __ldg(P + oOW + idx);                          // (output_layer.weight and .bias are contiguous)
     // c = relu(cos_embedding(cos))  (model.py:177)      [the staged GEMM starts with a barrier: cos / feat are visible]
-    tile_mm_staged<kCos, R, kFeat, 4, 13>(s, PT + ptWc, PT + ptW1, kFeat, kHid,
+    tile_mm_staged<kCos, R, kFeat, kMT, 13>(s, PT + ptWc, PT + ptW1, kFeat, kHid,
                                           [&](int k, int row) { return s.cos[row * LD64 + k]; },
                                           [&](int row, int f, float a) { s.c[row * LD208 + f] = fmaxf(a + __ldg(P + oCB + f), 0.f); });
     // h1 = relu(hidden_layer(feat * c))  (model.py:180-182)
-    tile_mm_staged<kFeat, R, kHid, 4, 4>(s, PT + ptW1, PT + ptW2, kHid, kHid,
+    tile_mm_staged<kFeat, R, kHid, kMT, 4>(s, PT + ptW1, PT + ptW2, kHid, kHid,
                                          [&](int k, int row) { return s.c[row * LD208 + k] * s.feat[(row / n_tau) * kFeat + k]; },
                                          [&](int row, int o, float a) { s.h1[row * LD64 + o] = fmaxf(a + __ldg(P + oH1B + o), 0.f); });
     // h2 = relu(hidden_layer_2(h1))  (model.py:183)
-    tile_mm_staged<kHid, R, kHid, 4, 4>(s, PT + ptW2, next, next_red, next_n,
+    tile_mm_staged<kHid, R, kHid, kMT, 4>(s, PT + ptW2, next, next_red, next_n,
                                         [&](int k, int row) { return s.h1[row * LD64 + k]; },
                                         [&](int row, int o, float a) { s.h2[row * LD64 + o] = fmaxf(a + __ldg(P + oH2B + o), 0.f); });
     __syncthreads();
@@ -345,7 +347,7 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) li += __shfl_xor_sync(0xffffffffu, li, off);
     if ((t & 31) == 0) s.red[t >> 5] = li;
-    for (int idx = t; idx < 16 * kFeat; idx += kThreads) s.dfp[idx] = 0.f;
+    for (int idx = t; idx < kGroups * kFeat; idx += kThreads) s.dfp[idx] = 0.f;
     __syncthreads();
     if (t == 0) loss_part[tile] = s.red[0] + s.red[1];
 
@@ -374,7 +376,7 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     }
     __syncthreads();
     // dW2[o][k] = sum_r dz2[r][o] h1[r][k] ; db2
-    tile_mm<R, kHid, kHid, 4, 4>([&](int r, int o) { return s.h2[r * LD64 + o]; }, YMat<4>{s.h1, LD64},
+    tile_mm<R, kHid, kHid, kMT, 4>([&](int r, int o) { return s.h2[r * LD64 + o]; }, YMat<4>{s.h1, LD64},
                                  [&](int o, int k, float a) { g[oH2W + o * kHid + k] = a; });
     if (t < kHid) {
         float acc = 0.f;
@@ -384,12 +386,12 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     __syncthreads();
     // dz1 = (dz2 W2) * (h1 > 0), in place over h1  (W2 in torch layout [o][k], prefetched during the forward pass;
     // W1 in torch layout is prefetched for dh0 meanwhile)
-    tile_mm_staged<kHid, R, kHid, 4, 4>(s, PL + oH2W, PL + oH1W, kHid, kFeat,
+    tile_mm_staged<kHid, R, kHid, kMT, 4>(s, PL + oH2W, PL + oH1W, kHid, kFeat,
                                         [&](int o, int r) { return s.h2[r * LD64 + o]; },
                                         [&](int r, int k, float a) { float& h = s.h1[r * LD64 + k]; h = h > 0.f ? a : 0.f; });
     __syncthreads();
     // dW1[o][k] = sum_r dz1[r][o] h0[r][k], h0 = feat * c ; db1
-    tile_mm<R, kHid, kFeat, 4, 13>([&](int r, int o) { return s.h1[r * LD64 + o]; },
+    tile_mm<R, kHid, kFeat, kMT, 13>([&](int r, int o) { return s.h1[r * LD64 + o]; },
                                    [&](int r, int n0, float (&yv)[13]) {
 #pragma unroll
                                        for (int j = 0; j < 13; ++j)
@@ -404,8 +406,8 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     __syncthreads();
     // dh0 = dz1 W1 ; dzc = dh0 * feat * (c > 0) in place over c ; d(feat) += dh0 * c
     {
-        const int tm = threadIdx.x / 16;                                             // row group of 4 rows (one sample = 2 groups)
-        tile_mm_staged<kHid, R, kFeat, 4, 13>(s, PL + oH1W, nullptr, 0, 0, [&](int o, int r) { return s.h1[r * LD64 + o]; },
+        const int tm = threadIdx.x / 16;                                             // row group of kMT rows (one sample = 8 / kMT groups)
+        tile_mm_staged<kHid, R, kFeat, kMT, 13>(s, PL + oH1W, nullptr, 0, 0, [&](int o, int r) { return s.h1[r * LD64 + o]; },
                                        [&](int r, int k, float a) {
                                            float& cv = s.c[r * LD208 + k];
                                            const float c0 = cv;
@@ -416,10 +418,13 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     __syncthreads();
     for (int idx = t; idx < 8 * kFeat; idx += kThreads) {
         const int smp = idx / kFeat, k = idx % kFeat;
-        s.dfeat[idx] = s.dfp[(2 * smp) * kFeat + k] + s.dfp[(2 * smp + 1) * kFeat + k];
+        float acc = 0.f;
+#pragma unroll
+        for (int gq = 0; gq < 8 / kMT; ++gq) acc += s.dfp[((8 / kMT) * smp + gq) * kFeat + k];      // fixed order: deterministic
+        s.dfeat[idx] = acc;
     }
     // dWc[f][i] = sum_r dzc[r][f] cos[r][i] ; dbc
-    tile_mm<R, kFeat, kCos, 13, 4>([&](int r, int f) { return s.c[r * LD208 + f]; }, YMat<4>{s.cos, LD64},
+    tile_mm<R, kFeat, kCos, 13, kMT>([&](int r, int f) { return s.c[r * LD208 + f]; }, YMat<kMT>{s.cos, LD64},
                                    [&](int f, int i, float a) { g[oCW + f * kCos + i] = a; });
     if (t < kFeat) {
         float acc = 0.f;
