@@ -306,7 +306,7 @@ def iqn_bench(args, dev, world):
     out = {}
     B, E = 1024, args.envs
     agent = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B)
-    g = torch.Generator(device=dev); g.manual_seed(3)
+    g = torch.Generator(device=dev); g.manual_seed(3 + int(os.environ.get("RANK", 0)))   # every replica trains on its own data
     n_sets = 64                                                            # 64 different batches (26 MB) rotated
     st = torch.randn(n_sets, B, 26, device=dev, generator=g) * 3; ns = torch.randn(n_sets, B, 26, device=dev, generator=g) * 3
     ac = torch.randint(0, 9, (n_sets, B), device=dev, generator=g); rw = torch.randn(n_sets, B, device=dev, generator=g)
@@ -343,6 +343,14 @@ def iqn_bench(args, dev, world):
     out["update_tflops_fp32"] = IQN_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
     out["samples_per_s_all_gpus"] = world * B * 1e3 / ms
     out["loss_finite"] = bool(torch.isfinite(agent._loss).all().item())
+    if world > 1:
+        # data-parallel replicas: different batches per rank, one gradient all-reduce per update -> bit-identical weights
+        chk = agent.qnetwork_local.flat.double().sum().reshape(1)
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        pmax, pmin = agent.qnetwork_local.flat.clone(), agent.qnetwork_local.flat.clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX); dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        out["replicas_bit_identical"] = bool(torch.equal(pmax, pmin) and hi.item() == lo.item())
 
     # act: K = 32 forward + argmax for a whole env batch: tcgen05 kernel (bf16 operands) and the fp32 parity kernel
     obs = torch.randn(E, 26, device=dev, generator=g) * 3

@@ -513,12 +513,13 @@ __global__ void __launch_bounds__(256) iqn_pack_kernel(const float* __restrict__
 template <class K>
 int set_smem(K kern)
 {
-    static bool done = false;      // one attribute per kernel instantiation
-    if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute(iqn): %s", cudaGetErrorString(e)); return (int)e; }
-        done = true;
-    }
+    static unsigned long long done_mask = 0;      // per kernel instantiation, one bit per device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && ((done_mask >> dev) & 1ull)) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute(iqn): %s", cudaGetErrorString(e)); return (int)e; }
+    if (dev < 64) done_mask |= 1ull << dev;
     return 0;
 }
 

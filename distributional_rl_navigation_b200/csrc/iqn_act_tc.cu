@@ -465,14 +465,14 @@ extern "C" int iqn_act_tc(const float* d_params, const void* d_packed_tc, const 
     if (n_tau != kTaus) { mnv_set_error("iqn_act_tc: n_tau must be 32 (ObsEncoder.K), got %d", n_tau); return MNV_E_CAPACITY; }
     MNV_CHECK_PTR(d_params); MNV_CHECK_PTR(d_packed_tc); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_taus);
     if (d_qmean == nullptr && d_greedy == nullptr) { mnv_set_error("iqn_act_tc: no output"); return MNV_E_NULL; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(iqn_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute(iqn_act_tc): %s", cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    static unsigned long long attr_mask = 0;                       // the attribute is per device
+    if (dev >= 64 || !((attr_mask >> dev) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(iqn_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute(iqn_act_tc): %s", cudaGetErrorString(e)); return (int)e; }
+        if (dev < 64) attr_mask |= 1ull << dev;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long n_tiles = (B + kEnvsPerTile - 1) / kEnvsPerTile;
     const long long pairs = (n_tiles + 1) / 2;                     // two tile groups per CTA
