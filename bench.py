@@ -373,7 +373,7 @@ def iqn_bench(args, dev, world):
     env = VecMarineNavEnv(E, seed=12345 + E * (int(os.environ.get("RANK", 0))), device=dev, num_cores=N_CORES, num_obs=N_OBS,
                           min_start_goal_dis=30.0, num_beams=N_BEAMS)
     agent2 = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B, BUFFER_SIZE=4 * E)
-    n_roll = 6
+    n_roll = 41
     agent2.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
     sync()
     t0 = time.perf_counter()
