@@ -111,6 +111,16 @@ class VecMarineNavEnv:
             self.num_cores = self.schedule["num_cores"][idx]
             self.num_obs = self.schedule["num_obstacles"][idx]
             self.min_start_goal_dis = self.schedule["min_start_goal_dis"][idx]
+        key = (self.width, self.height, self.r, self.v_rel_max, self.p, tuple(self.v_range), tuple(self.obs_r_range), self.clear_r,
+               bool(self.reset_start_and_goal), float(self.start[0]), float(self.start[1]), float(self.goal[0]), float(self.goal[1]),
+               bool(self.random_reset_state), self.init_theta, self.init_speed, self.max_speed, int(self.num_cores),
+               int(self.num_obs), float(self.min_start_goal_dis))
+        if getattr(self, "_reset_key", None) == key:
+            return self._reset_cache
+        self._reset_key, self._reset_cache = key, self._build_reset_params()
+        return self._reset_cache
+
+    def _build_reset_params(self):
         r = _lib.default_reset_params()
         r.width, r.height, r.core_r, r.v_rel_max, r.p = self.width, self.height, self.r, self.v_rel_max, self.p
         r.v_range[0], r.v_range[1] = self.v_range
