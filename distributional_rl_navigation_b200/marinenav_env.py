@@ -181,7 +181,6 @@ class MarineNavEnv(_gym.Env):
             setattr(v, name, getattr(self, name))
         v.dt, v.N, v.robot_r, v.max_speed, v.a, v.w = rb.dt, rb.N, rb.r, rb.max_speed, np.asarray(rb.a), np.asarray(rb.w)
         v.sonar_range, v.sonar_angle = rb.sonar.range, rb.sonar.angle
-        v.buf["episode_step"][0] = int(self.episode_timesteps)
 
     def _obs_out(self, obs_t):
         return obs_t[0].double().cpu().numpy()
@@ -231,18 +230,42 @@ class MarineNavEnv(_gym.Env):
         self.robot.action_history.append(action)
         self._sync()
         v = self._vec
-        v.buf["action"][0] = a
-        traj = torch.zeros(self.robot.N, 2, 1, dtype=torch.float64, device=v.device)
-        v.step(v.buf["action"], auto_reset=False, trajectory=traj)
         b = v.buf
-        obs = b["next_obs"][0].double().cpu().numpy()
-        reward = float(b["reward"][0].double().cpu())
-        done = bool(b["done"][0].cpu())
-        info = {"state": _lib.INFO_STRINGS[int(b["info"][0].cpu())]}
-        self.robot.trajectory.extend(traj[:, :, 0].cpu().numpy().tolist())
+        pin = self._step_pins()
+        pin["in"][0], pin["in"][1] = a, int(self.episode_timesteps)
+        with torch.cuda.device(v.device):
+            self._dev_in.copy_(pin["in"], non_blocking=True)    # action + episode_timesteps in one 8-byte copy
+            b["action"].copy_(self._dev_in[0:1]); b["episode_step"].copy_(self._dev_in[1:2])
+            env_ops.step(b, v.params(), action=b["action"], obs=b["next_obs"], trajectory=self._traj)
+            b["obs"].copy_(b["next_obs"])
+            v.total_timesteps += 1
+            pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["reward"].copy_(b["reward"], non_blocking=True)
+            pin["done"].copy_(b["done"], non_blocking=True); pin["info"].copy_(b["info"], non_blocking=True)
+            pin["traj"].copy_(self._traj, non_blocking=True)
+            torch.cuda.current_stream().synchronize()           # ONE host sync per step
+        obs = pin["obs"][0].double().numpy().copy()
+        reward = float(pin["reward"][0])
+        done = bool(pin["done"][0])
+        info = {"state": _lib.INFO_STRINGS[int(pin["info"][0])]}
+        self.robot.trajectory.extend(pin["traj"][:, :, 0].tolist())
         self.episode_timesteps += 1
         self.total_timesteps += 1
         return obs, reward, done, info
+
+    def _step_pins(self):
+        """Pinned staging buffers of the single-env step (re-made when N or the number of beams changes)."""
+        v = self._vec
+        key = (int(self.robot.N), v.obs_dim)
+        if getattr(self, "_pins_key", None) != key:
+            self._pins_key = key
+            self._pins = dict(obs=torch.zeros(1, v.obs_dim, dtype=torch.float32).pin_memory(),
+                              reward=torch.zeros(1, dtype=torch.float32).pin_memory(), done=torch.zeros(1, dtype=torch.uint8).pin_memory(),
+                              info=torch.zeros(1, dtype=torch.uint8).pin_memory(),
+                              traj=torch.zeros(key[0], 2, 1, dtype=torch.float64).pin_memory(),
+                              **{"in": torch.zeros(2, dtype=torch.int32).pin_memory()})
+            self._traj = torch.zeros(key[0], 2, 1, dtype=torch.float64, device=v.device)
+            self._dev_in = torch.zeros(2, dtype=torch.int32, device=v.device)
+        return self._pins
 
     def close(self):
         self._vec.close()
