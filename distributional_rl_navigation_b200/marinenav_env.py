@@ -181,6 +181,10 @@ class MarineNavEnv(_gym.Env):
             setattr(v, name, getattr(self, name))
         v.dt, v.N, v.robot_r, v.max_speed, v.a, v.w = rb.dt, rb.N, rb.r, rb.max_speed, np.asarray(rb.a), np.asarray(rb.w)
         v.sonar_range, v.sonar_angle = rb.sonar.range, rb.sonar.angle
+        goal = (float(self.goal[0]), float(self.goal[1]))      # callers assign env.goal directly (run_experiments.py:134,196)
+        if getattr(self, "_goal_pushed", None) != goal:
+            v.buf["goal"][:, 0] = torch.tensor(goal, dtype=torch.float64, device=v.device)
+            self._goal_pushed = goal
 
     def _obs_out(self, obs_t):
         return obs_t[0].double().cpu().numpy()
@@ -219,6 +223,7 @@ class MarineNavEnv(_gym.Env):
         b = self._vec.buf
         sp = b["start_pose"][:, 0].cpu().numpy(); goal = b["goal"][:, 0].cpu().numpy()
         self.start, self.goal = np.array(sp[:2]), np.array(goal)
+        self._goal_pushed = (float(goal[0]), float(goal[1]))
         self.robot.init_theta, self.robot.init_speed = float(sp[2]), float(sp[3])
         self.robot.action_history.clear(); self.robot.trajectory.clear()
         return self._obs_out(obs)
@@ -303,17 +308,28 @@ class MarineNavEnv(_gym.Env):
         b["obstacles"][:, 0] = torch.from_numpy(t).to(self._vec.device)
         b["n_placed"][1, 0] = len(obstacles)
 
+    # The reference keeps scipy KDTrees of the centres (marinenav_env.py:155,181) and callers re-assign them after editing
+    # the lists (run_experiments.py:160,178).  The kernels do not need them: reading builds one on demand, writing is accepted
+    # and ignored (the tables written by the cores / obstacles setters are the source of truth).
     @property
     def core_centers(self):
         import scipy.spatial
         cs = self.cores
         return scipy.spatial.KDTree(np.array([[c.x, c.y] for c in cs])) if cs else None
 
+    @core_centers.setter
+    def core_centers(self, tree):
+        pass
+
     @property
     def obs_centers(self):
         import scipy.spatial
         os_ = self.obstacles
         return scipy.spatial.KDTree(np.array([[o.x, o.y] for o in os_])) if os_ else None
+
+    @obs_centers.setter
+    def obs_centers(self, tree):
+        pass
 
     def get_velocity(self, x: float, y: float):
         """marinenav_env.py:422-455: current at (x, y) -- evaluated by the device kernel on a scratch copy of the map."""
@@ -371,6 +387,7 @@ class MarineNavEnv(_gym.Env):
         self._set_spaces()
         self._sync()
         self._vec.load_eval_configs([eval_config])
+        self._goal_pushed = (float(self.goal[0]), float(self.goal[1]))
         rb.action_history.clear(); rb.trajectory.clear()
         return self._obs_out(self._vec.observe_all())
 

@@ -189,3 +189,43 @@ def test_step_host_matches_device_step():
         assert torch.equal(a.buf["state"], b.buf["state"]) and torch.equal(a.buf["obs"], b.buf["obs"])
         n_done += int(done_h.sum())
     assert n_done > 0
+
+
+def test_facade_supports_run_experiments_style_edits():
+    """run_experiments.py:126-210 edits the env in place: cores / obstacles / KD-trees / start / goal / robot.N assignments."""
+    import marinenav_env.envs.marinenav_env as ref_mod           # the reference's module path
+    env = make_env(3)
+    env.reset()
+    env.cores.clear(); env.obstacles.clear()
+    env.start, env.goal = np.array([15.0, 10.0]), np.array([45.0, 35.0])
+    env.cores = [ref_mod.Core(14.0, 1.0, 0, np.pi * 10.0), ref_mod.Core(25.0, 23.0, 1, np.pi * 10.0)]
+    env.core_centers = object()                                    # accepted and ignored
+    env.obstacles = [ref_mod.Obstacle(20.0, 36.0, 1.5), ref_mod.Obstacle(22.0, 14.0, 1.5)]
+    env.obs_centers = object()
+    env.robot.init_theta, env.robot.init_speed = 3 * np.pi / 4, 1.0
+    cur = env.get_velocity(env.start[0], env.start[1])
+    env.robot.reset_state(env.start[0], env.start[1], current_velocity=cur)
+    obs = env.get_observation()
+    orc = mo.OracleEnv(seed=3)
+    e = orc.e
+    e.n_cores_placed, e.n_obs_placed = 2, 2
+    for i, (x, y, cw, G) in enumerate([(14.0, 1.0, 0, np.pi * 10.0), (25.0, 23.0, 1, np.pi * 10.0)]):
+        e.cores[i].x, e.cores[i].y, e.cores[i].clockwise, e.cores[i].Gamma = x, y, cw, G
+    for i, (x, y, r) in enumerate([(20.0, 36.0, 1.5), (22.0, 14.0, 1.5)]):
+        e.obstacles[i].x, e.obstacles[i].y, e.obstacles[i].r = x, y, r
+    e.start[0], e.start[1], e.goal[0], e.goal[1] = 15.0, 10.0, 45.0, 35.0
+    e.robot_init_theta, e.robot_init_speed = 3 * np.pi / 4, 1.0
+    import ctypes
+    want = np.zeros(26)
+    orc.L.orc_restart_episode(ctypes.byref(e), want.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    close(obs, want)
+    close(cur, orc.get_velocity(15.0, 10.0), 1e-10)
+    env.robot.N = 5                                                # exp_setup_5
+    e.N = 5
+    for a in (8, 7, 8, 5, 8):
+        o1, r1, d1, i1 = env.step(a)
+        o2, r2, d2, i2 = orc.step(a)
+        close(o1, o2); close(r1, r2)
+        assert d1 == d2 and i1 == i2
+    assert len(env.robot.trajectory) == 25
+    assert len(env.core_centers.data) == 2 and len(env.obs_centers.data) == 2
