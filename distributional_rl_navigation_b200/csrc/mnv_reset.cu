@@ -168,18 +168,25 @@ mnv_reset_kernel(const ResetPtrs P, const mnv_reset_params R, long long E, int m
                     // check_core, marinenav_env.py:344-383 (the y test uses width, sic)
                     bool ok = !(x - R.core_r < 0.0 || x + R.core_r > R.width) && !(y - R.core_r < 0.0 || y + R.core_r > R.width);
                     ok = ok && !(dist2d(x, y, sx, sy) < R.core_r + R.clear_r) && !(dist2d(x, y, gx, gy) < R.core_r + R.clear_r);
-                    for (int i = 0; ok && i < nc; ++i) {
-                        const double dx = S.cx[i] - x, dy = S.cy[i] - y;
-                        const double dis = sqrt(dx * dx + dy * dy);
-                        if (S.ccw[i] == clockwise) {
-                            const double bi = S.cG[i] / (kTwoPi * R.v_rel_max), bj = Gamma / (kTwoPi * R.v_rel_max);
-                            if (dis < bi + bj) ok = false;
-                        } else {
-                            const double Gl = S.cG[i] > Gamma ? S.cG[i] : Gamma, Gs = S.cG[i] < Gamma ? S.cG[i] : Gamma;
-                            const double v1 = Gl / (kTwoPi * (dis - 2 * R.core_r));      // Q7: negative when dis < 2r -> accepted
-                            const double v2 = Gs / (kTwoPi * R.core_r);
-                            if (v1 > R.p * v2) ok = false;
+                    // pairwise constraints against the accepted cores: lane i checks core i (same arithmetic per pair as the
+                    // reference's loop, marinenav_env.py:361-381), the verdict is a warp vote
+                    {
+                        bool fail = false;
+                        if (ok && lane < nc) {
+                            const int i = lane;
+                            const double dx = S.cx[i] - x, dy = S.cy[i] - y;
+                            const double dis = sqrt(dx * dx + dy * dy);
+                            if (S.ccw[i] == clockwise) {
+                                const double bi = S.cG[i] / (kTwoPi * R.v_rel_max), bj = Gamma / (kTwoPi * R.v_rel_max);
+                                if (dis < bi + bj) fail = true;
+                            } else {
+                                const double Gl = S.cG[i] > Gamma ? S.cG[i] : Gamma, Gs = S.cG[i] < Gamma ? S.cG[i] : Gamma;
+                                const double v1 = Gl / (kTwoPi * (dis - 2 * R.core_r));      // Q7: negative when dis < 2r -> accepted
+                                const double v2 = Gs / (kTwoPi * R.core_r);
+                                if (v1 > R.p * v2) fail = true;
+                            }
                         }
+                        ok = ok && !__any_sync(0xffffffffu, fail);
                     }
                     if (ok) {
                         __syncwarp();
@@ -202,13 +209,17 @@ mnv_reset_kernel(const ResetPtrs P, const mnv_reset_params R, long long E, int m
                     // check_obstacle, marinenav_env.py:385-420
                     bool ok = !(x - r < 0.0 || x + r > R.width) && !(y - r < 0.0 || y + r > R.height);
                     ok = ok && !(dist2d(x, y, sx, sy) < r + R.clear_r) && !(dist2d(x, y, gx, gy) < r + R.clear_r);
-                    for (int i = 0; ok && i < nc; ++i) {
-                        const double dx = S.cx[i] - x, dy = S.cy[i] - y;
-                        if (sqrt(dx * dx + dy * dy) <= R.core_r + r) ok = false;
-                    }
-                    for (int i = 0; ok && i < no; ++i) {
-                        const double dx = S.ox[i] - x, dy = S.oy[i] - y;
-                        if (sqrt(dx * dx + dy * dy) <= S.orr[i] + r) ok = false;
+                    {   // lane i checks vortex core i and obstacle i (marinenav_env.py:402-418), warp vote
+                        bool fail = false;
+                        if (ok && lane < nc) {
+                            const double dx = S.cx[lane] - x, dy = S.cy[lane] - y;
+                            if (sqrt(dx * dx + dy * dy) <= R.core_r + r) fail = true;
+                        }
+                        if (ok && lane < no) {
+                            const double dx = S.ox[lane] - x, dy = S.oy[lane] - y;
+                            if (sqrt(dx * dx + dy * dy) <= S.orr[lane] + r) fail = true;
+                        }
+                        ok = ok && !__any_sync(0xffffffffu, fail);
                     }
                     if (ok) {
                         __syncwarp();
