@@ -229,3 +229,33 @@ def test_facade_supports_run_experiments_style_edits():
         assert d1 == d2 and i1 == i2
     assert len(env.robot.trajectory) == 25
     assert len(env.core_centers.data) == 2 and len(env.obs_centers.data) == 2
+
+
+def test_training_driver_reference_config_format(tmp_path):
+    """scripts/train_iqn.py: the reference's config JSON (list-valued seeds -> one trial each), single-env and vectorised."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = {"agent": "IQN", "seed": [0, 1], "total_timesteps": 60, "eval_freq": 100000, "save_dir": str(tmp_path / "single")}
+    (tmp_path / "c1.json").write_text(json.dumps(cfg))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "train_iqn.py"), "-C", str(tmp_path / "c1.json")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    runs = list((tmp_path / "single").glob("training_*/seed_*"))
+    assert len(runs) == 2
+    for r in runs:
+        ec = json.load(open(r / "eval_config.json"))
+        assert len(ec) == 30 and len(ec["env_29"]["env"]["cores"]["positions"]) == 8
+        assert json.load(open(r / "training_schedule.json"))["num_cores"] == [4, 6, 8]
+    # the eval maps come from seed 348 and must equal the reference's shipped eval_config.json
+    ref_cfg = json.load(open(os.path.join(root, "tests", "golden", "eval_config.json")))
+    got = json.load(open(runs[0] / "eval_config.json"))
+    for k in ref_cfg:
+        assert got[k]["env"]["cores"] == ref_cfg[k]["env"]["cores"] and got[k]["env"]["obstacles"] == ref_cfg[k]["env"]["obstacles"]
+        assert got[k]["robot"]["init_theta"] == ref_cfg[k]["robot"]["init_theta"]
+    cfg2 = {"agent": "IQN", "seed": 3, "total_timesteps": 1024 * 30, "eval_freq": 10, "save_dir": str(tmp_path / "vec")}
+    (tmp_path / "c2.json").write_text(json.dumps(cfg2))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "train_iqn.py"), "-C", str(tmp_path / "c2.json"),
+                          "--num-envs", "1024", "--batch-size", "256"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    run = next((tmp_path / "vec").glob("training_*/seed_3"))
+    assert (run / "network_params.pth").is_file() and (run / "greedy_evaluations.npz").is_file() and (run / "adaptive_evaluations.npz").is_file()
