@@ -339,7 +339,7 @@ def iqn_bench(args, dev, world):
     ms = float(ms.item())
     out["updates_per_s"] = 1e3 / ms
     out["update_ms"] = ms
-    out["update_config"] = f"batch {B} per GPU, N=N'=8, fp32 FFMA, loss_grad + " + ("NCCL all-reduce(35785 f32) + " if world > 1 else "") + "clip_adam + pack"
+    out["update_config"] = f"batch {B} per GPU, N=N'=8, fp32 FFMA, loss_grad + " + ("NCCL all-reduce(35785 f32) + " if world > 1 else "") + "clip_adam (kernel-side weight copies refreshed in the same kernel)"
     out["update_tflops_fp32"] = IQN_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
     out["samples_per_s_all_gpus"] = world * B * 1e3 / ms
     out["loss_finite"] = bool(torch.isfinite(agent._loss).all().item())

@@ -56,7 +56,7 @@ _SIGNATURES = {
     "iqn_forward": (C.c_int, [_vp] * 5 + [C.c_float] + [_vp] * 3 + [_i64, _i32, _vp]),
     "iqn_train_scratch_floats": (C.c_int64, [_i64]),
     "iqn_loss_grad": (C.c_int, [_vp] * 11 + [C.c_float] + [_vp] * 3 + [_i64, _vp]),
-    "iqn_clip_adam": (C.c_int, [_vp] * 5 + [C.c_float] * 6 + [_i64, _vp, _vp]),
+    "iqn_clip_adam": (C.c_int, [_vp] * 6 + [C.c_float] * 6 + [_i64, _vp, _vp]),
     "iqn_packed_tc_bytes": (C.c_int, []),
     "iqn_pack_tc": (C.c_int, [_vp, _vp, _vp]),
     "iqn_act_tc": (C.c_int, [_vp] * 5 + [C.c_float] + [_vp] * 3 + [_i64, _i32, _vp]),

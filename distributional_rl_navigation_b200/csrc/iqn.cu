@@ -12,6 +12,8 @@
 // operands do not give; tensor cores are for the acting path where only the argmax is consumed.
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "iqn_common.cuh"
 
 namespace {
@@ -455,9 +457,15 @@ iqn_reduce_kernel(const float* __restrict__ gpart, const float* __restrict__ los
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < kParams) {
-        float acc = 0.f;
-        for (int tile = 0; tile < n_tiles; ++tile) acc += gpart[(long long)tile * kParams + i];
-        grad[i] = acc;
+        // four independent partial sums (tiles = 0,1,2,3 mod 4) keep several loads in flight; fixed order -> deterministic
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* p = gpart + i;
+        int tile = 0;
+        for (; tile + 4 <= n_tiles; tile += 4, p += 4ll * kParams) {
+            a0 += p[0]; a1 += p[kParams]; a2 += p[2ll * kParams]; a3 += p[3ll * kParams];
+        }
+        for (; tile < n_tiles; ++tile, p += kParams) a0 += p[0];
+        grad[i] = (a0 + a1) + (a2 + a3);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         float acc = 0.f;
@@ -470,7 +478,7 @@ iqn_reduce_kernel(const float* __restrict__ gpart, const float* __restrict__ los
 __global__ void __launch_bounds__(1024)
 iqn_clip_adam_kernel(float* __restrict__ P, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                      float grad_scale, float max_norm, float step_size, float beta1, float beta2, float inv_sqrt_bc2, float eps,
-                     float* __restrict__ grad_norm)
+                     float* __restrict__ grad_norm, float* __restrict__ PT, __nv_bfloat16* __restrict__ Wtc)
 {
     __shared__ float red[32];
     const int t = threadIdx.x;
@@ -497,7 +505,14 @@ iqn_clip_adam_kernel(float* __restrict__ P, const float* __restrict__ grad, floa
         const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
         m[i] = mi; v[i] = vi;
         const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-        P[i] = P[i] - step_size * (mi / denom);
+        const float pn = P[i] - step_size * (mi / denom);
+        P[i] = pn;
+        // keep the kernel-side copies of the parameters current: fp32 transposes (iqn_pack layout) and the bf16 tensor-core
+        // tiles (iqn_pack_tc layout; their zero / one padding never changes)
+        int pt, tc;
+        packed_slots(i, pt, tc);
+        if (PT != nullptr && pt >= 0) PT[pt] = pn;
+        if (Wtc != nullptr && tc >= 0) Wtc[tc] = __float2bfloat16(pn);
     }
 }
 
@@ -585,18 +600,17 @@ extern "C" int iqn_loss_grad(const float* d_params_local, const float* d_packed_
     return mnv_launch_status("iqn_loss_grad(reduce)");
 }
 
-extern "C" int iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d_v, float* d_packed,
+extern "C" int iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
                              float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                              float* d_grad_norm, void* stream)
 {
     if (step < 1) { mnv_set_error("iqn_clip_adam: step must be >= 1"); return MNV_E_PARAM; }
     MNV_CHECK_PTR(d_params); MNV_CHECK_PTR(d_grad); MNV_CHECK_PTR(d_m); MNV_CHECK_PTR(d_v);
+    MNV_CHECK_PTR_OPT(d_packed); MNV_CHECK_PTR_OPT(d_packed_tc);
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     iqn_clip_adam_kernel<<<(kParams + 1023) / 1024, 1024, 0, (cudaStream_t)stream>>>(
-        d_params, d_grad, d_m, d_v, grad_scale, max_norm, step_size, beta1, beta2, inv_sqrt_bc2, eps, d_grad_norm);
-    int rc = mnv_launch_status("iqn_clip_adam");
-    if (rc) return rc;
-    if (d_packed != nullptr) return iqn_pack(d_params, d_packed, stream);
-    return 0;
+        d_params, d_grad, d_m, d_v, grad_scale, max_norm, step_size, beta1, beta2, inv_sqrt_bc2, eps, d_grad_norm, d_packed,
+        (__nv_bfloat16*)d_packed_tc);
+    return mnv_launch_status("iqn_clip_adam");
 }

@@ -33,27 +33,11 @@ constexpr int kGroupThreads = 256;
 constexpr int kRows = 128;              // rows per tile (UMMA M)
 constexpr int kTaus = 32;               // quantile samples per environment (ObsEncoder.K)
 constexpr int kEnvsPerTile = kRows / kTaus;
-constexpr int kN4 = 16;                 // output layer padded 9 -> 16 (UMMA N granularity at M = 128)
 constexpr int kTmemCols = 512;
-
-// The biases ride inside the GEMMs: every A operand carries one extra K-step whose first column is 1.0 (rest 0) and the
-// weight tiles carry the bias in that column, so the accumulators already hold W x + b and the epilogues are relu (and the
-// feature product) only.  Reduction lengths including that step:
-constexpr int kK0 = kCos + 16, kK1 = kFeat + 16, kK2 = kHid + 16, kK3 = kHid + 16;      // 80, 224, 80, 80
-// bf16 element counts of the packed weight tiles (core-matrix layout, see tile_offset)
-constexpr int kWcEl = kFeat * kK0, kW1El = kHid * kK1, kW2El = kHid * kK2, kW3El = kN4 * kK3;
-constexpr int kPackedTcEl = kWcEl + kW1El + kW2El + kW3El;       // 37 376 bf16 = 74 752 bytes
 
 // TMEM column bases of the four accumulators
 // (per tile group: 256 columns; D2 / D3 / D4 reuse D1's columns, which the first epilogue has drained by then)
 constexpr uint32_t kD1 = 0, kD2 = 0, kD3 = 64, kD4 = 128;
-
-// UMMA canonical K-major layout without swizzle: 8 x 8 (bf16) core matrices of 128 contiguous bytes; the core matrices of
-// one 8-row group are contiguous along K (LBO = 128 B) and row groups follow each other (SBO = (K/8) * 128 B).
-__host__ __device__ constexpr int tile_offset(int r, int k, int K)       // in elements
-{
-    return (r >> 3) * (K * 8) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
-}
 
 // per tile-group buffers (two groups of 256 threads keep two tiles in flight per CTA)
 struct __align__(128) GroupSmem {

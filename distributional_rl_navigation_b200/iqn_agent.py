@@ -211,8 +211,8 @@ class IQNAgent:
             world = mdist.all_reduce_sum_(self._grad)             # no-op (returns 1) unless torch.distributed is initialised
             opt.step_count += 1
             iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
-                              grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm)
-            iqn_ops.pack_tc(L.flat, L.packed_tc)
+                              grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm,
+                              packed_tc=L.packed_tc)
         return self._loss.detach().cpu().numpy()[0]
 
     def train_async(self, experiences, taus):
@@ -228,8 +228,8 @@ class IQNAgent:
         world = mdist.all_reduce_sum_(self._grad)
         opt.step_count += 1
         iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
-                          grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm)
-        iqn_ops.pack_tc(L.flat, L.packed_tc)
+                          grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm,
+                          packed_tc=L.packed_tc)
         return self._loss
 
     def soft_update(self, local_model, target_model):

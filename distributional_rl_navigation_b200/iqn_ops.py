@@ -79,10 +79,11 @@ def loss_grad(params_l, packed_l, params_t, packed_t, states, actions, rewards, 
 
 
 def clip_adam(params, grad, m, v, packed, step, lr=1e-4, max_norm=0.5, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-8,
-              grad_norm=None):
+              grad_norm=None, packed_tc=None):
+    """clip_grad_norm_ + Adam.step; `packed` / `packed_tc` (optional) are kept current by the same kernel."""
     for t, n in ((params, "params"), (grad, "grad"), (m, "m"), (v, "v")):
         _f32(t, N_PARAMS, n)
-    rc = _lib.load().iqn_clip_adam(_lib.ptr(params), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), _lib.ptr(packed),
+    rc = _lib.load().iqn_clip_adam(_lib.ptr(params), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), _lib.ptr(packed), _lib.ptr(packed_tc),
                                    C.c_float(grad_scale), C.c_float(max_norm), C.c_float(lr), C.c_float(beta1),
                                    C.c_float(beta2), C.c_float(eps), int(step), _lib.ptr(grad_norm), _stream())
     _lib.check(rc, "iqn_clip_adam")

@@ -140,9 +140,10 @@ int     iqn_loss_grad(const float* d_params_local, const float* d_packed_local, 
 
 /* torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.Adam.step (agent.py:66,299-300) on the flat vectors;
  * the gradient is first multiplied by grad_scale (1/world_size after a summing all-reduce).  step = number of optimizer
- * steps including this one.  d_grad_norm (optional) receives the pre-clip total norm.  If d_packed != NULL it is
- * refreshed from the updated parameters. */
-int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d_v, float* d_packed,
+ * steps including this one.  d_grad_norm (optional) receives the pre-clip total norm.  d_packed (iqn_pack layout) and
+ * d_packed_tc (iqn_pack_tc layout, must have been initialised by iqn_pack_tc once) are optional: if given, the same
+ * kernel keeps them current, so no repacking launch is needed after the update. */
+int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
                       float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                       float* d_grad_norm, void* stream);
 

@@ -74,6 +74,8 @@ def test_train_loss_grad_adam_vs_reference(kat, weights, B):
     scratch = torch.empty(iqn_ops.train_scratch_floats(B), dtype=torch.float32, device=DEV)
     loss = torch.zeros(1, dtype=torch.float32, device=DEV); grad = torch.zeros(iqn_ops.N_PARAMS, dtype=torch.float32, device=DEV)
     m = torch.zeros_like(grad); v = torch.zeros_like(grad); gn = torch.zeros(1, dtype=torch.float32, device=DEV)
+    ptc = torch.empty(iqn_ops.packed_tc_bytes(), dtype=torch.uint8, device=DEV)
+    iqn_ops.pack_tc(flat, ptc)
     for k in range(3):
         iqn_ops.loss_grad(flat, packed, target, packed_t, st_d, ac_d, rw_d, ns_d, dn_d, dev(taus[2 * k]), dev(taus[2 * k + 1]),
                           0.99, scratch, loss, grad)
@@ -83,14 +85,17 @@ def test_train_loss_grad_adam_vs_reference(kat, weights, B):
             ref_g = kat[f"grad_B{B}"]
             err = np.abs(grad.cpu().numpy() - ref_g)
             assert err.max() <= 5e-5 * np.abs(ref_g).max(), err.max() / np.abs(ref_g).max()
-        iqn_ops.clip_adam(flat, grad, m, v, packed, step=k + 1, grad_norm=gn)
+        iqn_ops.clip_adam(flat, grad, m, v, packed, step=k + 1, grad_norm=gn, packed_tc=ptc)
         if k == 0:
             assert abs(gn.item() - float(kat[f"gradnorm_B{B}"])) <= 2e-5 * float(kat[f"gradnorm_B{B}"])
             np.testing.assert_allclose(flat.cpu().numpy(), kat[f"params_after1_B{B}"], rtol=0, atol=5e-7)
     np.testing.assert_allclose(flat.cpu().numpy(), kat[f"params_after3_B{B}"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(m.cpu().numpy(), kat[f"adam_m_after3_B{B}"], rtol=2e-3, atol=1e-8)
-    # packed transposes were refreshed by clip_adam
+    # the kernel-side copies (fp32 transposes, bf16 tensor-core tiles) were kept current by clip_adam itself
     assert torch.equal(packed, packed_of(flat))
+    fresh = torch.empty_like(ptc)
+    iqn_ops.pack_tc(flat, fresh)
+    assert torch.equal(ptc, fresh)
 
 
 def test_train_ragged_batch_vs_oracle(weights):
