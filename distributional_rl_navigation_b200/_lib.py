@@ -46,6 +46,8 @@ _SIGNATURES = {
     "mnv_last_error_string": (C.c_char_p, []),
     "mnv_default_params": (None, [C.POINTER(MnvParams)]),
     "mnv_default_reset_params": (None, [C.POINTER(MnvResetParams)]),
+    "mnv_set_option": (C.c_int, [C.c_char_p, _i32]),
+    "mnv_get_option": (C.c_int, [C.c_char_p]),
     "mnv_step": (C.c_int, [_vp] * 12 + [_i64, _i32, _i32, C.POINTER(MnvParams), _vp]),
     "mnv_observe": (C.c_int, [_vp] * 7 + [_i64, _i32, _i32, C.POINTER(MnvParams), _i32, _vp]),
     "mnv_seed": (C.c_int, [_vp] * 3 + [_i64, _vp]),

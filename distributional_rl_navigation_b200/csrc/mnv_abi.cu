@@ -1,6 +1,7 @@
 // Version, error string and default parameter blocks of libmarinenav_b200.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mnv_common.cuh"
@@ -13,6 +14,37 @@ void mnv_set_error(const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// tuning switches (mnv_set_option); MNV_TMA / MNV_PDL in the environment give the initial values
+static int g_opt[MNV_OPT_COUNT] = {-1, -1};
+static const char* const g_opt_name[MNV_OPT_COUNT] = {"tma", "pdl"};
+static const char* const g_opt_env[MNV_OPT_COUNT] = {"MNV_TMA", "MNV_PDL"};
+static const int g_opt_default[MNV_OPT_COUNT] = {0, 1};
+
+int mnv_option(int which)
+{
+    if (g_opt[which] < 0) {
+        const char* e = getenv(g_opt_env[which]);
+        g_opt[which] = (e != nullptr && e[0] != 0) ? atoi(e) : g_opt_default[which];
+    }
+    return g_opt[which];
+}
+
+extern "C" int mnv_set_option(const char* key, int32_t value)
+{
+    for (int i = 0; key != nullptr && i < MNV_OPT_COUNT; ++i)
+        if (strcmp(key, g_opt_name[i]) == 0) { g_opt[i] = value < 0 ? 0 : value; return 0; }
+    mnv_set_error("mnv_set_option: unknown key '%s'", key ? key : "(null)");
+    return MNV_E_PARAM;
+}
+
+extern "C" int mnv_get_option(const char* key)
+{
+    for (int i = 0; key != nullptr && i < MNV_OPT_COUNT; ++i)
+        if (strcmp(key, g_opt_name[i]) == 0) return mnv_option(i);
+    mnv_set_error("mnv_get_option: unknown key '%s'", key ? key : "(null)");
+    return MNV_E_PARAM;
 }
 
 extern "C" int mnv_version(void) { return MNV_VERSION; }

@@ -9,6 +9,8 @@
 #define MNV_PI 3.14159265358979323846
 
 void mnv_set_error(const char* fmt, ...);
+enum { MNV_OPT_TMA = 0, MNV_OPT_PDL = 1, MNV_OPT_COUNT = 2 };
+int mnv_option(int which);     // tuning switches, see mnv_set_option
 
 #define MNV_CHECK_PTR(p)                                                            \
     do {                                                                            \

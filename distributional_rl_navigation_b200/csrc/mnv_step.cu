@@ -22,6 +22,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 #include "mnv_common.cuh"
 
@@ -39,9 +40,12 @@ struct KParams {
     int n_substeps, n_beams, max_ep_steps, set_boundary;
     int max_c, max_o, obs_dim, velocity_from_state, allow_tma;
     long long E;
+    double snap_t1, snap_t2;        // pi/2 - beam_angle[0], 3pi/2 - beam_angle[0]   (Q10 pre-test, see snap_beam)
+    float inv_phi, snap_tol;        // 1 / beam spacing, (1e-3 / spacing) + 1e-4 in beam-index units
     double beam_angle[MNV_MAX_BEAMS];
     double beam_cos[MNV_MAX_BEAMS];
     double beam_sin[MNV_MAX_BEAMS];
+    float2 beam_dirf[MNV_MAX_BEAMS];   // (cos, sin) of the beam in the robot frame, fp32, for the candidate filter
 };
 
 struct EnvPtrs {
@@ -50,15 +54,43 @@ struct EnvPtrs {
     float* obs; float* reward; uint8_t* done; uint8_t* info;
 };
 
-// 1/a to ~1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps; a is a squared distance in [1e-300, 1e300] here.
+// 1/a to ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + one cubic step r(1 + e + e^2), e = 1 - a r  (e^3 <= 2^-60);
+// a is a squared distance in [1e-300, 1e300] here.
 __device__ __forceinline__ double fast_rcp(double a)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    r = fma(r, fma(-a, r, 1.0), r);
-    r = fma(r, fma(-a, r, 1.0), r);
+    const double e = fma(-a, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
+
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: one issue slot for two lanes of the candidate filter) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
+__device__ __forceinline__ void unpack2(f32x2 v, unsigned& lo, unsigned& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// programmatic dependent launch: no-ops unless the launch carries the programmatic-stream-serialization attribute
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
 {
@@ -98,19 +130,22 @@ template <int MAXC, int MAXO, bool STEP>
 __global__ void __launch_bounds__(kBlock, 8)
 mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
+    static_assert((MAXO & 1) == 0 && MAXO <= 32, "obstacle pairs are packed for FFMA2; the candidate mask is one word");
     extern __shared__ __align__(16) float s_obs[];           // [kBlock][obs_dim]
+    pdl_launch_dependents();                                  // the next launch on the stream may be scheduled while this one drains
     const long long E = K.E;
     const long long e0 = (long long)blockIdx.x * kBlock;
     const int tid = threadIdx.x;
     const long long e = e0 + tid;
-    const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
     const int D = K.obs_dim;
     float* my_obs = s_obs + tid * D;
     double* s_ob = reinterpret_cast<double*>(s_obs + ((kBlock * D + 3) & ~3));   // obstacle rows of this CTA
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ob + 3 * K.max_o * kBlock);
     const int max_o = K.max_o;
+    pdl_wait();                                               // everything below reads what earlier launches wrote
+    const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
 
-    // ---- (optional, MNV_TMA=1) obstacle table slice of every warp -> shared memory with the TMA bulk-copy engine: 3*max_o rows of 32 consecutive
+    // ---- (optional, "tma" = 1) obstacle table slice of every warp -> shared memory with the TMA bulk-copy engine: 3*max_o rows of 32 consecutive
     //      environments (256 contiguous bytes each), issued by the warp's lane 0 and tracked by the warp's own mbarrier.  The rows are first
     //      needed after the sub-step loop, so this DRAM round trip overlaps the integration.  Ragged / masked / odd-E
     //      launches (rows not 16-byte aligned or not full) use per-thread cp.async instead. ----
@@ -179,30 +214,38 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
             const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
             vx = 0.0; vy = 0.0;
-            double* ptraj = P.traj != nullptr ? P.traj + e : nullptr;
-            for (int it = 0; it < K.n_substeps; ++it) {
-                double ux, uy;
-                current(x, y, ux, uy);
-                vx = fma(sp, c, ux);                          // robot.py:98-100 (pre-update speed / heading: Q6)
-                vy = fma(sp, s, uy);
-                x = fma(vx, K.dt, x);                         // robot.py:105-107
-                y = fma(vy, K.dt, y);
-                sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
-                sp = sp < 0.0 ? 0.0 : sp;                     // robot.py:114 (np.clip)
-                sp = sp > K.max_speed ? K.max_speed : sp;
-                th = __dadd_rn(th, wdt);                      // robot.py:117
-                if (th < 0.0 || th >= 2.0 * MNV_PI) {         // robot.py:120-123
+            auto substeps = [&](auto with_traj) {
+                double* ptraj = decltype(with_traj)::value ? P.traj + e : nullptr;
+                for (int it = 0; it < K.n_substeps; ++it) {
+                    double ux, uy;
+                    current(x, y, ux, uy);
+                    vx = fma(sp, c, ux);                          // robot.py:98-100 (pre-update speed / heading: Q6)
+                    vy = fma(sp, s, uy);
+                    x = fma(vx, K.dt, x);                         // robot.py:105-107
+                    y = fma(vy, K.dt, y);
+                    sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
+                    sp = sp < 0.0 ? 0.0 : sp;                     // robot.py:114 (np.clip)
+                    sp = sp > K.max_speed ? K.max_speed : sp;
+                    th = __dadd_rn(th, wdt);                      // robot.py:117
+                    // robot.py:120-123: the two while loops; |w dt| << 2 pi, so one conditional add / subtract each is
+                    // the whole loop unless theta came in far outside [0, 2 pi) (then the loops below finish the job
+                    // with the reference's own sequence of additions)
+                    th = th < 0.0 ? __dadd_rn(th, 2.0 * MNV_PI) : th;
+                    th = th >= 2.0 * MNV_PI ? __dsub_rn(th, 2.0 * MNV_PI) : th;
+                    if (th < 0.0 || th >= 2.0 * MNV_PI) {
 #pragma unroll 1
-                    while (th < 0.0) th += 2.0 * MNV_PI;
+                        while (th < 0.0) th += 2.0 * MNV_PI;
 #pragma unroll 1
-                    while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                        while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                    }
+                    const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
+                    c = c2; s = s2;
+                    if (decltype(with_traj)::value) {             // Robot.trajectory (marinenav_env.py:212), optional
+                        ptraj[0] = x; ptraj[E] = y; ptraj += 2 * E;
+                    }
                 }
-                const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
-                c = c2; s = s2;
-                if (ptraj != nullptr) {                       // Robot.trajectory (marinenav_env.py:212), optional
-                    ptraj[0] = x; ptraj[E] = y; ptraj += 2 * E;
-                }
-            }
+            };
+            if (P.traj != nullptr) substeps(std::true_type{}); else substeps(std::false_type{});
             const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
             reward = K.pen_step + (dis_before - dis_after);   // marinenav_env.py:220,229
         } else {
@@ -220,86 +263,131 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         my_obs[2] = (float)fma(c, gx - x, s * (gy - y));
         my_obs[3] = (float)fma(c, gy - y, -s * (gx - x));
 
-        // ---- obstacles -> robot frame, registers.  q is pre-multiplied by sigma = +1 (robot outside the circle) or -1
-        //      (inside) so that "the nearer root can be in front" reads tc >= 0 in both cases; obstacles that cannot be
-        //      reached within the sonar range get r2 = -1 (discriminant always negative). ----
+        // ---- Q10 pre-test (robot.py:134-162): beam b is snapped to the vertical iff |theta + beam_angle[b] - T| < 1e-3,
+        //      T = pi/2 or 3pi/2, i.e. iff u = (T - beam_angle[0] - theta) / spacing is within 1e-3 / spacing of the
+        //      integer b.  One fp32 evaluation of u per T (error < 1e-5 index units, tolerance widened by 1e-4) names the
+        //      only beam that can be snapped; the exact fp64 test runs for that beam alone. ----
+        int bs1, bs2;
+        {
+            const float u1 = (float)(K.snap_t1 - th) * K.inv_phi, u2 = (float)(K.snap_t2 - th) * K.inv_phi;
+            const float n1 = rintf(u1), n2 = rintf(u2);
+            bs1 = fabsf(u1 - n1) < K.snap_tol ? (int)n1 : -1;
+            bs2 = fabsf(u2 - n2) < K.snap_tol ? (int)n2 : -1;
+        }
+
+        // ---- obstacles -> robot frame, fp32 pairs for the candidate filter.  q is pre-multiplied by sigma = +1 (robot
+        //      outside the circle) or -1 (inside) so that "the nearer root can be in front" reads tc >= 0 in both cases;
+        //      nr2 = -(r^2 + 1e-3), or +1e30 for empty slots and obstacles that cannot be reached within the sonar range
+        //      (discriminant test always fails). ----
         if (use_tma) mbar_wait(my_bar, 0); else cp_async_wait_all();
         const double* ob = s_ob + tid;
-        float qx[MAXO], qy[MAXO], r2[MAXO];                     // fp32: only the conservative candidate filter uses them
+        f32x2 qx2[MAXO / 2], qy2[MAXO / 2], nr2[MAXO / 2];      // fp32: only the conservative candidate filter uses them
         bool force_slow = false;                                // robot within 1e-9 of a circle: decide everything exactly
         double best_d2 = INFINITY, best_r = 0.0;               // Q4: nearest CENTRE only (marinenav_env.py:329-336)
+        {
+            const float cf = (float)c, sf = (float)s;
+            const f32x2 c2 = pack2(cf, cf), s2 = pack2(sf, sf), ns2 = pack2(-sf, -sf);
 #pragma unroll
-        for (int j = 0; j < MAXO; ++j) {
-            double r = -1.0, ox = 0.0, oy = 0.0;
-            if (j < max_o) { ox = ob[j * kBlock]; oy = ob[(max_o + j) * kBlock]; r = ob[(2 * max_o + j) * kBlock]; }
-            const double dx = ox - x, dy = oy - y;
-            const bool on = r > 0.0;
-            const double d2 = fma(dx, dx, dy * dy);
-            const double rr = r * r, lim = K.range_slack + r;
-            if (on && d2 < best_d2) { best_d2 = d2; best_r = r; }
-            const bool inside = d2 < rr;
-            force_slow |= on && (fabs(d2 - rr) <= 1e-9 * rr);
-            const double sg = inside ? -1.0 : 1.0;
-            qx[j] = (float)(sg * fma(c, dx, s * dy));
-            qy[j] = (float)(sg * fma(c, dy, -s * dx));
-            r2[j] = (on && d2 <= lim * lim) ? (float)rr : -1.0f;
+            for (int jj = 0; jj < MAXO / 2; ++jj) {
+                float dxf[2], dyf[2], nrf[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 2 * jj + h;
+                    double r = -1.0, ox = 0.0, oy = 0.0;
+                    if (j < max_o) { ox = ob[j * kBlock]; oy = ob[(max_o + j) * kBlock]; r = ob[(2 * max_o + j) * kBlock]; }
+                    const double dx = ox - x, dy = oy - y;
+                    const bool on = r > 0.0;
+                    const double d2 = fma(dx, dx, dy * dy);
+                    const double rr = r * r, lim = K.range_slack + r;
+                    if (on && d2 < best_d2) { best_d2 = d2; best_r = r; }
+                    force_slow |= on && (fabs(d2 - rr) <= 1e-9 * rr);
+                    const float sg = d2 < rr ? -1.0f : 1.0f;
+                    dxf[h] = sg * (float)dx; dyf[h] = sg * (float)dy;
+                    nrf[h] = (on && d2 <= lim * lim) ? -((float)rr + 1e-3f) : 1e30f;
+                }
+                const f32x2 dx2 = pack2(dxf[0], dxf[1]), dy2 = pack2(dyf[0], dyf[1]);
+                qx2[jj] = fma2(c2, dx2, mul2(s2, dy2));          // R^T (centre - pos), fp32 (error ~1e-5 << the 1e-3 margin)
+                qy2[jj] = fma2(c2, dy2, mul2(ns2, dx2));
+                nr2[jj] = pack2(nrf[0], nrf[1]);
+            }
         }
 
         // ---- sonar (robot.py:125-198) ----
+        const f32x2 margin2 = pack2(1e-3f, 1e-3f);
         for (int b = 0; b < K.n_beams; ++b) {
-            const double ang = th + K.beam_angle[b];           // robot.py:131 (not wrapped)
-            double bx = K.beam_cos[b], by = K.beam_sin[b];      // beam direction in the robot frame
-            if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }            // Q10: exactly (0,+1) in the world frame
-            else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }     // Q10: exactly (0,-1)
-            int cnt = 0, jsel = 0;
-            const float bxf = (float)bx, byf = (float)by;
+            // conservative candidate filter in fp32 (no sqrt): "real roots and the nearer root not behind the robot" with a
+            // 1e-3 margin, >= 30x the fp32 rounding error of these expressions near the decision boundary (|q| <= range + r);
+            // every candidate is then decided exactly in fp64 below, so the filter can only cost time, never a result.
+            // Two obstacles per FFMA2; bit j of m <=> obstacle j is a candidate:  cr^2 - r^2 - 1e-3 < 0  and  tc + 1e-3 >= 0.
+            const float2 bd = K.beam_dirf[b];
+            const f32x2 bx2 = pack2(bd.x, bd.x), by2 = pack2(bd.y, bd.y), nby2 = pack2(-bd.y, -bd.y);
+            unsigned m = 0;
 #pragma unroll
-            for (int j = 0; j < MAXO; ++j) {
-                // conservative candidate filter in fp32 (no sqrt): "real roots and the nearer root not behind the robot"
-                // with a 1e-3 margin, ~100x the fp32 rounding error of these expressions (|q| <= range + r); every
-                // candidate is then decided exactly in fp64 below, so the filter can only cost time, never a result
-                const float tc = fmaf(qx[j], bxf, qy[j] * byf);
-                const float cr = fmaf(qx[j], byf, -qy[j] * bxf);
-                const float disc = fmaf(-cr, cr, r2[j]);
-                if (fminf(disc, tc) >= -1e-3f) { ++cnt; jsel = j; }
+            for (int jj = MAXO / 2 - 1; jj >= 0; --jj) {
+                const f32x2 tc = fma2(qx2[jj], bx2, fma2(qy2[jj], by2, margin2));
+                const f32x2 ncr = fma2(qy2[jj], bx2, mul2(qx2[jj], nby2));
+                const f32x2 nd = fma2(ncr, ncr, nr2[jj]);
+                unsigned tlo, thi, dlo, dhi;
+                unpack2(tc, tlo, thi); unpack2(nd, dlo, dhi);
+                m = __funnelshift_l(dhi & ~thi, m, 1);           // sign bit of (nd < 0 && tc >= 0) shifted in: obstacle 2jj+1
+                m = __funnelshift_l(dlo & ~tlo, m, 1);           // obstacle 2jj
             }
+            const bool maybe_snap = (b == bs1) || (b == bs2);
             bool hit = false;
-            double t = 0.0;
-            if (cnt == 1 && !force_slow) {
-                const double r = ob[(2 * max_o + jsel) * kBlock];
-                const double dx = ob[jsel * kBlock] - x, dy = ob[(max_o + jsel) * kBlock] - y;
-                const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
-                const double tc = fma(ax, bx, ay * by);
-                const double cr = fma(ax, by, -ay * bx);
-                const double disc = fma(-cr, cr, r * r);
-                if (disc >= 0.0) {                               // robot.py:172-174
-                    const double h = sqrt(disc);
-                    t = tc > 0.0 ? tc - h : tc + h;              // nearer root first (robot.py:184)
-                    hit = (t <= K.range) && (t >= 0.0);          // robot.py:185-190
+            double t = 0.0, bx = 0.0, by = 0.0;
+            if (m != 0u || force_slow || maybe_snap) {
+                bx = K.beam_cos[b]; by = K.beam_sin[b];         // beam direction in the robot frame
+                bool scan_all = force_slow;
+                if (maybe_snap) {
+                    const double ang = th + K.beam_angle[b];       // robot.py:131 (not wrapped)
+                    if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; scan_all = true; }            // Q10: exactly (0,+1) in the world frame
+                    else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; scan_all = true; }     // Q10: exactly (0,-1)
                 }
-            } else if (cnt > 1 || force_slow) {
-                // several obstacles on this beam: replay the reference's ordered scan (Q3) exactly
-                double best = INFINITY;
-                for (int j = 0; j < max_o; ++j) {
-                    const double r = ob[(2 * max_o + j) * kBlock];
-                    if (!(r > 0.0)) continue;
-                    const double dx = ob[j * kBlock] - x, dy = ob[(max_o + j) * kBlock] - y;
-                    const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
-                    const double tc = fma(ax, bx, ay * by);
-                    const double cr = fma(ax, by, -ay * bx);
-                    const double disc = fma(-cr, cr, r * r);
-                    if (disc < 0.0) continue;                    // robot.py:172-174
-                    const double h = sqrt(disc);
-                    const double tj = tc > 0.0 ? tc - h : tc + h;
-                    if (fabs(tj) > K.range) continue;            // robot.py:185-187
-                    if (tj < 0.0) continue;                      // robot.py:188-190
-                    if (hit && tj >= best) break;                // robot.py:192-195
-                    best = tj; hit = true;
+                if (!scan_all && (m & (m - 1u)) == 0u) {
+                    // one candidate (m != 0 here: scan_all is false and maybe_snap alone does not bring us here with m == 0)
+                    if (m != 0u) {
+                        const int jsel = 31 - __clz(m);
+                        const double r = ob[(2 * max_o + jsel) * kBlock];
+                        const double dx = ob[jsel * kBlock] - x, dy = ob[(max_o + jsel) * kBlock] - y;
+                        const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
+                        const double tc = fma(ax, bx, ay * by);
+                        const double cr = fma(ax, by, -ay * bx);
+                        const double disc = fma(-cr, cr, r * r);
+                        if (disc >= 0.0) {                               // robot.py:172-174
+                            const double h = sqrt(disc);
+                            t = tc > 0.0 ? tc - h : tc + h;              // nearer root first (robot.py:184)
+                            hit = (t <= K.range) && (t >= 0.0);          // robot.py:185-190
+                        }
+                    }
+                } else {
+                    // several candidates (or an exact-only case): replay the reference's ordered scan (Q3) over them in list order
+                    unsigned mm = scan_all ? (max_o >= 32 ? 0xffffffffu : ((1u << max_o) - 1u)) : m;
+                    double best = INFINITY;
+                    while (mm != 0u) {
+                        const int j = __ffs(mm) - 1;
+                        mm &= mm - 1u;
+                        const double r = ob[(2 * max_o + j) * kBlock];
+                        if (!(r > 0.0)) continue;
+                        const double dx = ob[j * kBlock] - x, dy = ob[(max_o + j) * kBlock] - y;
+                        const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
+                        const double tc = fma(ax, bx, ay * by);
+                        const double cr = fma(ax, by, -ay * bx);
+                        const double disc = fma(-cr, cr, r * r);
+                        if (disc < 0.0) continue;                    // robot.py:172-174
+                        const double h = sqrt(disc);
+                        const double tj = tc > 0.0 ? tc - h : tc + h;
+                        if (fabs(tj) > K.range) continue;            // robot.py:185-187
+                        if (tj < 0.0) continue;                      // robot.py:188-190
+                        if (hit && tj >= best) break;                // robot.py:192-195
+                        best = tj; hit = true;
+                    }
+                    t = best;
                 }
-                t = best;
             }
-            my_obs[4 + 2 * b] = hit ? (float)(t * bx) : 0.0f;   // marinenav_env.py:314-320
-            my_obs[5 + 2 * b] = hit ? (float)(t * by) : 0.0f;
+            float2 o2;                                              // marinenav_env.py:314-320
+            o2.x = hit ? (float)(t * bx) : 0.0f;
+            o2.y = hit ? (float)(t * by) : 0.0f;
+            *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = o2;    // rows are 8-byte aligned (obs_dim is even)
         }
 
         if (STEP) {
@@ -357,6 +445,8 @@ __global__ void __launch_bounds__(kDenseWarps * 32)
 mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
     extern __shared__ __align__(16) float s_obs[];                 // [kDenseWarps][obs_dim]
+    pdl_launch_dependents();
+    pdl_wait();                                                    // everything below reads what earlier launches wrote
     const long long E = K.E;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long e = (long long)blockIdx.x * kDenseWarps + w;
@@ -530,12 +620,27 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         reinterpret_cast<float2*>(dst)[i] = reinterpret_cast<const float2*>(my_obs)[i];
 }
 
+// One launch, optionally with programmatic stream serialization (PDL): the kernels call griddepcontrol.launch_dependents
+// at entry and griddepcontrol.wait before their first global access, so the next launch's CTAs are placed while this grid drains.
+template <typename Kern>
+cudaError_t launch_one(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t st, const EnvPtrs& P, const KParams& K)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = mnv_option(MNV_OPT_PDL) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, P, K);
+}
+
 template <bool STEP>
 int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
 {
     if (K.max_o > 16) {                                            // dense maps: one warp per environment
         const unsigned dgrid = (unsigned)((K.E + kDenseWarps - 1) / kDenseWarps);
-        mnv_env_dense_kernel<STEP><<<dgrid, kDenseWarps * 32, (size_t)kDenseWarps * K.obs_dim * sizeof(float), st>>>(P, K);
+        launch_one(mnv_env_dense_kernel<STEP>, dgrid, kDenseWarps * 32, (size_t)kDenseWarps * K.obs_dim * sizeof(float), st, P, K);
         return mnv_launch_status(STEP ? "mnv_step(dense)" : "mnv_observe(dense)");
     }
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
@@ -547,7 +652,7 @@ int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
             cudaError_t a = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (a != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(a)); return (int)a; } \
         }                                                                                                    \
-        kern<<<grid, kBlock, smem, st>>>(P, K);                                                              \
+        launch_one(kern, grid, kBlock, smem, st, P, K);                                                      \
     } while (0)
     if (K.max_c <= 4 && K.max_o <= 8) MNV_LAUNCH(4, 8);
     else if (K.max_c <= 8 && K.max_o <= 10) MNV_LAUNCH(8, 10);
@@ -580,15 +685,18 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
     K.width = p->width; K.height = p->height;
     K.n_beams = p->n_beams; K.max_ep_steps = p->max_episode_steps; K.set_boundary = p->set_boundary;
     K.max_c = max_c; K.max_o = max_o; K.obs_dim = 4 + 2 * p->n_beams; K.E = E;
-    { static int tma = -1; if (tma < 0) { const char* e = getenv("MNV_TMA"); tma = (e != nullptr && e[0] == '1') ? 1 : 0; } K.allow_tma = tma; }
-    // MNV_TMA=1 stages the obstacle rows with the TMA bulk-copy engine (UBLKCP) instead of per-thread cp.async (LDGSTS).
+    K.allow_tma = mnv_option(MNV_OPT_TMA) ? 1 : 0;
+    // "tma" = 1 stages the obstacle rows with the TMA bulk-copy engine (UBLKCP) instead of per-thread cp.async (LDGSTS).
     // Measured A/B in one process (profiles/README.md): 25.03 us vs 24.18 us per step -> cp.async is the default.
     // Sonar.compute_phi / compute_beam_angles (robot.py:14-21)
     const double phi = p->sonar_angle / (p->n_beams - 1), a0 = -p->sonar_angle / 2;
     for (int i = 0; i < p->n_beams; ++i) {
         K.beam_angle[i] = a0 + i * phi;
         K.beam_cos[i] = cos(K.beam_angle[i]); K.beam_sin[i] = sin(K.beam_angle[i]);
+        K.beam_dirf[i] = make_float2((float)K.beam_cos[i], (float)K.beam_sin[i]);
     }
+    K.snap_t1 = 0.5 * MNV_PI - a0; K.snap_t2 = 1.5 * MNV_PI - a0;      // Q10 pre-test (see the kernel)
+    K.inv_phi = (float)(1.0 / phi); K.snap_tol = (float)(1e-3 / phi + 1e-4);
     return 0;
 }
 

@@ -71,6 +71,15 @@ const char* mnv_last_error_string(void);
 void        mnv_default_params(mnv_params* p);
 void        mnv_default_reset_params(mnv_reset_params* p);
 
+/* Process-wide tuning switches of the kernels (results are identical for every setting; parity tests run all of them).
+ *   "pdl" 0|1  launch mnv_step / mnv_observe with programmatic stream serialization: the next launch on the stream is
+ *              scheduled while this one drains and blocks in griddepcontrol.wait before its first global access (default 1)
+ *   "tma" 0|1  stage the obstacle rows with the TMA bulk-copy engine (cp.async.bulk) instead of per-thread cp.async
+ *              (default 0: measured slower, profiles/README.md)
+ * Returns 0, or MNV_E_PARAM for an unknown key.  mnv_get_option returns the value or MNV_E_PARAM. */
+int         mnv_set_option(const char* key, int32_t value);
+int         mnv_get_option(const char* key);
+
 /* MarineNavEnv.step (marinenav_env.py:199-262) for E environments: N sub-steps of get_velocity (:422-455) +
  * Robot.update_state (robot.py:102-123), then get_observation (:273-326, sonar robot.py:125-198), reward and the
  * termination priority of :240-257.  In/out: d_state, d_episode_step (+1).  Out: d_velocity (last sub-step's, Q6),
