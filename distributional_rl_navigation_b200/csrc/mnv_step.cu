@@ -64,6 +64,16 @@ __device__ __forceinline__ double fast_rcp(double a)
     return fma(r, fma(e, e, e), r);
 }
 
+// check_collision (marinenav_env.py:329-336): sqrt(d2) <= thr, decided on the squares unless d2 is within 1e-15 (relative)
+// of thr^2 -- only there can the rounding of the square root matter, and only there is it evaluated.
+__device__ __forceinline__ bool collides(double d2, double thr)
+{
+    const double t2 = thr * thr;
+    if (d2 <= t2 * (1.0 - 1e-15)) return true;
+    if (!(d2 <= t2 * (1.0 + 1e-15))) return false;                 // also d2 = inf (no obstacle) and NaN
+    return sqrt(d2) <= thr;
+}
+
 // ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: one issue slot for two lanes of the candidate filter) ----
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi)
@@ -125,22 +135,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Dynamic shared memory: [kBlock * obs_dim floats, padded to 16 B][3 * max_o rows x kBlock doubles]
+// Dynamic shared memory: [kBlock * obs_dim floats, padded to 16 B][3 * max_o rows x kBlock doubles][mbarriers][exact-test rings]
+constexpr int kRing = 64;       // per-warp ring of pending exact sonar tests: < 32 pending + <= 32 pushed per beam
+
 template <int MAXC, int MAXO, bool STEP>
 __global__ void __launch_bounds__(kBlock, 8)
 mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
-    static_assert((MAXO & 1) == 0 && MAXO <= 32, "obstacle pairs are packed for FFMA2; the candidate mask is one word");
+    static_assert((MAXO & 1) == 0 && MAXO <= 16, "obstacle pairs are packed for FFMA2; the candidate mask is 16 bits of a ring entry");
     extern __shared__ __align__(16) float s_obs[];           // [kBlock][obs_dim]
     pdl_launch_dependents();                                  // the next launch on the stream may be scheduled while this one drains
     const long long E = K.E;
     const long long e0 = (long long)blockIdx.x * kBlock;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, w0 = tid & ~31;               // w0 = first row of this warp inside the CTA
     const long long e = e0 + tid;
     const int D = K.obs_dim;
     float* my_obs = s_obs + tid * D;
     double* s_ob = reinterpret_cast<double*>(s_obs + ((kBlock * D + 3) & ~3));   // obstacle rows of this CTA
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ob + 3 * K.max_o * kBlock);
+    unsigned* ring = reinterpret_cast<unsigned*>(s_bar + kBlock / 32) + (tid >> 5) * kRing;
     const int max_o = K.max_o;
     pdl_wait();                                               // everything below reads what earlier launches wrote
     const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
@@ -153,7 +167,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     const int warp_in_cta = tid >> 5;
     unsigned long long* my_bar = s_bar + warp_in_cta;             // one mbarrier per warp: no CTA-wide sync needed
     if (use_tma) {
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             mbar_init(my_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             mbar_expect_tx(my_bar, (unsigned)(3 * max_o * 32 * sizeof(double)));
@@ -164,36 +178,49 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         }
         __syncwarp();                                              // the warp's barrier is initialised before its lanes poll it
     }
-    if (live) {
-        double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
-        const double gx = P.goal[e], gy = P.goal[E + e];
-        double c, s;
-        sincos(th, &s, &c);
-        double vx, vy, reward = 0.0;
-        int ep = 0;
 
-        // ---- vortex cores -> registers; k = Gs/(2pi) carries the spin in its sign ----
+    // state that crosses the three phases (per-lane integration / warp-wide sonar / per-lane termination); lanes without a
+    // live environment carry inert values through the warp-wide phase (no candidates, nothing pushed)
+    double x = 0.0, y = 0.0, th = 0.0, sp = 0.0, gx = 0.0, gy = 0.0, c = 1.0, s = 0.0;
+    double vx = 0.0, vy = 0.0, reward = 0.0, dis_after = 0.0;
+    int ep = 0, bs1 = -1, bs2 = -1;
+    f32x2 qx2[MAXO / 2], qy2[MAXO / 2], nr2[MAXO / 2];      // fp32: only the conservative candidate filter uses them
+#pragma unroll
+    for (int jj = 0; jj < MAXO / 2; ++jj) { qx2[jj] = 0ull; qy2[jj] = 0ull; nr2[jj] = pack2(1e30f, 1e30f); }
+    bool force_slow = false;                                // robot within 1e-9 of a circle: decide everything exactly
+    double best_d2 = INFINITY, best_r = 0.0;               // Q4: nearest CENTRE only (marinenav_env.py:329-336)
+
+    if (live) {
+        // ---- every global load of this environment is issued before the first use of any of them, so that the kernel entry
+        //      costs ONE DRAM round trip (the ncu source page of the previous version showed three in a row: state -> sincos,
+        //      cores -> first sub-step, action -> accel / yaw tables) ----
+        x = P.state[e]; y = P.state[E + e]; th = P.state[2 * E + e]; sp = P.state[3 * E + e];
+        gx = P.goal[e]; gy = P.goal[E + e];
+        int action = 0;
+        if (STEP) { action = P.action[e]; ep = P.ep_step[e]; }
+        // vortex cores -> registers; k = Gs/(2pi) carries the spin in its sign
         double cx[MAXC], cy[MAXC], ck[MAXC];
         {
             const double* pc = P.cores + e;
             const long long rowstride = (long long)K.max_c * E;
 #pragma unroll
             for (int i = 0; i < MAXC; ++i) {
-                if (i < K.max_c) {
-                    cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride);
-                    ck[i] = __ldg(pc + 2 * rowstride) * (1.0 / (2.0 * MNV_PI));
-                } else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+                if (i < K.max_c) { cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride); ck[i] = __ldg(pc + 2 * rowstride); }
+                else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
                 pc += E;
             }
         }
-        // ---- staging of the obstacle rows with per-thread cp.async (each thread copies, and later reads, only its own column):
-        //      issued after the loads the integration is waiting for; first needed after the sub-step loop, so this DRAM
-        //      round trip overlaps the integration ----
+        // ---- staging of the obstacle rows with per-thread cp.async (each thread copies its own column): issued right behind
+        //      the loads the integration is waiting for; first needed after the sub-step loop, so this DRAM round trip
+        //      overlaps the integration ----
         if (!use_tma) {
             const double* po = P.obst + e;
             for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
             cp_async_commit();
         }
+        sincos(th, &s, &c);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) ck[i] *= (1.0 / (2.0 * MNV_PI));
         auto current = [&](double px, double py, double& ux, double& uy) {
             ux = 0.0; uy = 0.0;
 #pragma unroll
@@ -208,12 +235,9 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         };
 
         if (STEP) {
-            const int action = P.action[e];
-            ep = P.ep_step[e];
             const int ai = action / 3, wi = action - 3 * ai;
             const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
             const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
-            vx = 0.0; vy = 0.0;
             auto substeps = [&](auto with_traj) {
                 double* ptraj = decltype(with_traj)::value ? P.traj + e : nullptr;
                 for (int it = 0; it < K.n_substeps; ++it) {
@@ -246,7 +270,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 }
             };
             if (P.traj != nullptr) substeps(std::true_type{}); else substeps(std::false_type{});
-            const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+            dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
             reward = K.pen_step + (dis_before - dis_after);   // marinenav_env.py:220,229
         } else {
             if (K.velocity_from_state) {
@@ -267,7 +291,6 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         //      T = pi/2 or 3pi/2, i.e. iff u = (T - beam_angle[0] - theta) / spacing is within 1e-3 / spacing of the
         //      integer b.  One fp32 evaluation of u per T (error < 1e-5 index units, tolerance widened by 1e-4) names the
         //      only beam that can be snapped; the exact fp64 test runs for that beam alone. ----
-        int bs1, bs2;
         {
             const float u1 = (float)(K.snap_t1 - th) * K.inv_phi, u2 = (float)(K.snap_t2 - th) * K.inv_phi;
             const float n1 = rintf(u1), n2 = rintf(u2);
@@ -281,9 +304,6 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         //      (discriminant test always fails). ----
         if (use_tma) mbar_wait(my_bar, 0); else cp_async_wait_all();
         const double* ob = s_ob + tid;
-        f32x2 qx2[MAXO / 2], qy2[MAXO / 2], nr2[MAXO / 2];      // fp32: only the conservative candidate filter uses them
-        bool force_slow = false;                                // robot within 1e-9 of a circle: decide everything exactly
-        double best_d2 = INFINITY, best_r = 0.0;               // Q4: nearest CENTRE only (marinenav_env.py:329-336)
         {
             const float cf = (float)c, sf = (float)s;
             const f32x2 c2 = pack2(cf, cf), s2 = pack2(sf, sf), ns2 = pack2(-sf, -sf);
@@ -311,106 +331,122 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 nr2[jj] = pack2(nrf[0], nrf[1]);
             }
         }
+    }
 
-        // ---- sonar (robot.py:125-198) ----
+    // ================= sonar (robot.py:125-198), warp-wide =================
+    // Per (environment, beam): a conservative candidate filter in fp32 (no sqrt): "real roots and the nearer root not behind
+    // the robot" with a 1e-3 margin, >= 30x the fp32 rounding error of these expressions near the decision boundary
+    // (|q| <= range + r); two obstacles per FFMA2; bit j of m <=> obstacle j is a candidate: cr^2 - r^2 - 1e-3 < 0 and
+    // tc + 1e-3 >= 0.  Every (environment, beam) with a candidate is then decided EXACTLY in fp64, so the filter can only
+    // cost time, never a result.  Few lanes have a candidate on a given beam (~1.5 of 32), but most beams have one in some
+    // lane, so the exact tests are not run in place: they are pushed to a per-warp ring in shared memory and drained 32 at
+    // a time with every lane busy -- the fp64 square-root chain is walked ~once per warp and step instead of ~7 times.
+    {
         const f32x2 margin2 = pack2(1e-3f, 1e-3f);
-        for (int b = 0; b < K.n_beams; ++b) {
-            // conservative candidate filter in fp32 (no sqrt): "real roots and the nearer root not behind the robot" with a
-            // 1e-3 margin, >= 30x the fp32 rounding error of these expressions near the decision boundary (|q| <= range + r);
-            // every candidate is then decided exactly in fp64 below, so the filter can only cost time, never a result.
-            // Two obstacles per FFMA2; bit j of m <=> obstacle j is a candidate:  cr^2 - r^2 - 1e-3 < 0  and  tc + 1e-3 >= 0.
-            const float2 bd = K.beam_dirf[b];
-            const f32x2 bx2 = pack2(bd.x, bd.x), by2 = pack2(bd.y, bd.y), nby2 = pack2(-bd.y, -bd.y);
-            unsigned m = 0;
+        const double* obw = s_ob + w0;                          // obstacle columns of this warp's environments
+        const unsigned lt_mask = (1u << lane) - 1u;
+        int n_pend = 0, head = 0;                               // warp-uniform ring state
+        const int n_beams = K.n_beams;
+        for (int b = 0;; ++b) {
+            const bool last = b >= n_beams;
+            if (!last) {
+                const float2 bd = K.beam_dirf[b];
+                const f32x2 bx2 = pack2(bd.x, bd.x), by2 = pack2(bd.y, bd.y), nby2 = pack2(-bd.y, -bd.y);
+                unsigned m = 0;
 #pragma unroll
-            for (int jj = MAXO / 2 - 1; jj >= 0; --jj) {
-                const f32x2 tc = fma2(qx2[jj], bx2, fma2(qy2[jj], by2, margin2));
-                const f32x2 ncr = fma2(qy2[jj], bx2, mul2(qx2[jj], nby2));
-                const f32x2 nd = fma2(ncr, ncr, nr2[jj]);
-                unsigned tlo, thi, dlo, dhi;
-                unpack2(tc, tlo, thi); unpack2(nd, dlo, dhi);
-                m = __funnelshift_l(dhi & ~thi, m, 1);           // sign bit of (nd < 0 && tc >= 0) shifted in: obstacle 2jj+1
-                m = __funnelshift_l(dlo & ~tlo, m, 1);           // obstacle 2jj
-            }
-            const bool maybe_snap = (b == bs1) || (b == bs2);
-            bool hit = false;
-            double t = 0.0, bx = 0.0, by = 0.0;
-            if (m != 0u || force_slow || maybe_snap) {
-                bx = K.beam_cos[b]; by = K.beam_sin[b];         // beam direction in the robot frame
-                bool scan_all = force_slow;
-                if (maybe_snap) {
-                    const double ang = th + K.beam_angle[b];       // robot.py:131 (not wrapped)
-                    if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; scan_all = true; }            // Q10: exactly (0,+1) in the world frame
-                    else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; scan_all = true; }     // Q10: exactly (0,-1)
+                for (int jj = MAXO / 2 - 1; jj >= 0; --jj) {
+                    const f32x2 tc = fma2(qx2[jj], bx2, fma2(qy2[jj], by2, margin2));
+                    const f32x2 ncr = fma2(qy2[jj], bx2, mul2(qx2[jj], nby2));
+                    const f32x2 nd = fma2(ncr, ncr, nr2[jj]);
+                    unsigned tlo, thi, dlo, dhi;
+                    unpack2(tc, tlo, thi); unpack2(nd, dlo, dhi);
+                    m = __funnelshift_l(dhi & ~thi, m, 1);       // sign bit of (nd < 0 && tc >= 0) shifted in: obstacle 2jj+1
+                    m = __funnelshift_l(dlo & ~tlo, m, 1);       // obstacle 2jj
                 }
-                if (!scan_all && (m & (m - 1u)) == 0u) {
-                    // one candidate (m != 0 here: scan_all is false and maybe_snap alone does not bring us here with m == 0)
-                    if (m != 0u) {
-                        const int jsel = 31 - __clz(m);
-                        const double r = ob[(2 * max_o + jsel) * kBlock];
-                        const double dx = ob[jsel * kBlock] - x, dy = ob[(max_o + jsel) * kBlock] - y;
-                        const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
-                        const double tc = fma(ax, bx, ay * by);
-                        const double cr = fma(ax, by, -ay * bx);
-                        const double disc = fma(-cr, cr, r * r);
-                        if (disc >= 0.0) {                               // robot.py:172-174
-                            const double h = sqrt(disc);
-                            t = tc > 0.0 ? tc - h : tc + h;              // nearer root first (robot.py:184)
-                            hit = (t <= K.range) && (t >= 0.0);          // robot.py:185-190
-                        }
+                const bool maybe_snap = (b == bs1) || (b == bs2);
+                const bool pend = live && (m != 0u || force_slow || maybe_snap);
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if (pend)      // ring entry: [4:0] owner lane, [12:5] beam, [13] Q10 candidate, [14] exact-only, [31:16] candidate mask
+                    ring[(head + n_pend + __popc(bal & lt_mask)) & (kRing - 1)] =
+                        (unsigned)lane | ((unsigned)b << 5) | (maybe_snap ? 1u << 13 : 0u) | (force_slow ? 1u << 14 : 0u) | (m << 16);
+                else if (live)
+                    *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);   // no return (marinenav_env.py:318-320)
+                n_pend += __popc(bal);
+            }
+            if (n_pend >= 32 || (last && n_pend > 0)) {
+                __syncwarp();                                    // ring entries of other lanes are visible
+                const int n_now = n_pend < 32 ? n_pend : 32;
+                const bool mine = lane < n_now;
+                const unsigned ent = mine ? ring[(head + lane) & (kRing - 1)] : (unsigned)lane;
+                const int owner = ent & 31, bb = (ent >> 5) & 0xff;
+                const unsigned m = ent >> 16;
+                // the owner's pose after the sub-steps
+                const double ox_ = __shfl_sync(0xffffffffu, x, owner), oy_ = __shfl_sync(0xffffffffu, y, owner);
+                const double oc = __shfl_sync(0xffffffffu, c, owner), os = __shfl_sync(0xffffffffu, s, owner);
+                const double oth = __shfl_sync(0xffffffffu, th, owner);
+                if (mine) {
+                    const double* ob = obw + owner;
+                    double bx = K.beam_cos[bb], by = K.beam_sin[bb];    // beam direction in the robot frame
+                    bool scan_all = (ent & (1u << 14)) != 0u;
+                    if (ent & (1u << 13)) {
+                        const double ang = oth + K.beam_angle[bb];       // robot.py:131 (not wrapped)
+                        if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = os; by = oc; scan_all = true; }            // Q10: exactly (0,+1) in the world frame
+                        else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -os; by = -oc; scan_all = true; }     // Q10: exactly (0,-1)
                     }
-                } else {
-                    // several candidates (or an exact-only case): replay the reference's ordered scan (Q3) over them in list order
-                    unsigned mm = scan_all ? (max_o >= 32 ? 0xffffffffu : ((1u << max_o) - 1u)) : m;
+                    // the reference's ordered scan (Q3, robot.py:149-195) over the candidates in list order; for the usual
+                    // single candidate this is one pass
+                    unsigned mm = scan_all ? ((1u << max_o) - 1u) : m;
+                    bool hit = false;
                     double best = INFINITY;
                     while (mm != 0u) {
                         const int j = __ffs(mm) - 1;
                         mm &= mm - 1u;
                         const double r = ob[(2 * max_o + j) * kBlock];
                         if (!(r > 0.0)) continue;
-                        const double dx = ob[j * kBlock] - x, dy = ob[(max_o + j) * kBlock] - y;
-                        const double ax = fma(c, dx, s * dy), ay = fma(c, dy, -s * dx);
+                        const double dx = ob[j * kBlock] - ox_, dy = ob[(max_o + j) * kBlock] - oy_;
+                        const double ax = fma(oc, dx, os * dy), ay = fma(oc, dy, -os * dx);
                         const double tc = fma(ax, bx, ay * by);
                         const double cr = fma(ax, by, -ay * bx);
                         const double disc = fma(-cr, cr, r * r);
                         if (disc < 0.0) continue;                    // robot.py:172-174
-                        const double h = sqrt(disc);
-                        const double tj = tc > 0.0 ? tc - h : tc + h;
+                        const double hh = sqrt(disc);
+                        const double tj = tc > 0.0 ? tc - hh : tc + hh;   // nearer root first (robot.py:184)
                         if (fabs(tj) > K.range) continue;            // robot.py:185-187
                         if (tj < 0.0) continue;                      // robot.py:188-190
                         if (hit && tj >= best) break;                // robot.py:192-195
                         best = tj; hit = true;
                     }
-                    t = best;
+                    float2 o2;                                        // marinenav_env.py:314-320
+                    o2.x = hit ? (float)(best * bx) : 0.0f;
+                    o2.y = hit ? (float)(best * by) : 0.0f;
+                    *reinterpret_cast<float2*>(s_obs + (w0 + owner) * D + 4 + 2 * bb) = o2;   // rows are 8-byte aligned (obs_dim is even)
                 }
+                head += n_now; n_pend -= n_now;
+                __syncwarp();                                    // ring slots may be overwritten by the next pushes
             }
-            float2 o2;                                              // marinenav_env.py:314-320
-            o2.x = hit ? (float)(t * bx) : 0.0f;
-            o2.y = hit ? (float)(t * by) : 0.0f;
-            *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = o2;    // rows are 8-byte aligned (obs_dim is even)
-        }
-
-        if (STEP) {
-            // ---- termination priority (marinenav_env.py:240-257, Q5) ----
-            int done = 0, info = MNV_INFO_NORMAL;
-            const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
-            if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
-            else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
-            else if (best_d2 < INFINITY && sqrt(best_d2) <= best_r + K.robot_r) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
-            else if (sqrt(fma(x - gx, x - gx, (y - gy) * (y - gy))) <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
-            P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
-            P.velocity[e] = vx; P.velocity[E + e] = vy;
-            P.ep_step[e] = ep + 1;                                // marinenav_env.py:259
-            P.reward[e] = (float)reward;
-            P.done[e] = (uint8_t)done;
-            P.info[e] = (uint8_t)info;
+            if (last) break;
         }
     }
 
+    if (STEP && live) {
+        // ---- termination priority (marinenav_env.py:240-257, Q5) ----
+        int done = 0, info = MNV_INFO_NORMAL;
+        const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
+        if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
+        else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
+        else if (collides(best_d2, best_r + K.robot_r)) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
+        else if (dis_after <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }   // same norm as the reward's (marinenav_env.py:270,340)
+        P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
+        P.velocity[e] = vx; P.velocity[E + e] = vy;
+        P.ep_step[e] = ep + 1;                                // marinenav_env.py:259
+        P.reward[e] = (float)reward;
+        P.done[e] = (uint8_t)done;
+        P.info[e] = (uint8_t)info;
+    }
+
     // ---- observation rows: every warp streams out its own 32 rows (one contiguous 32*D*4-byte block, float4 stores);
-    //      only a warp-level sync is needed because a thread's row was written by that thread ----
+    //      only a warp-level sync is needed because a warp's rows were written by that warp ----
     __syncwarp();
-    const int lane = tid & 31, w0 = tid & ~31;                   // first row of this warp inside the CTA
     const long long left = E - (e0 + w0);
     const int rows = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
     const int n = rows * D;
@@ -644,7 +680,7 @@ int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
         return mnv_launch_status(STEP ? "mnv_step(dense)" : "mnv_observe(dense)");
     }
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
-    const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + 8 * (kBlock / 32);
+    const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + 8 * (kBlock / 32) + (size_t)(kBlock / 32) * kRing * sizeof(unsigned);
 #define MNV_LAUNCH(MC, MO)                                                                                   \
     do {                                                                                                     \
         auto kern = mnv_env_kernel<MC, MO, STEP>;                                                            \
