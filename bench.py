@@ -25,7 +25,7 @@ UNIT = "env_steps/s"
 N_CORES, N_OBS, N_BEAMS = 4, 8, 11
 ENVS_PER_GPU = 65536
 N_BATCHES = 8
-NCU_DRAM_BYTES_PER_LAUNCH = 22.575e6     # measured, profiles/r1_step_kernel_v3_ncu_full.csv (algorithmic read volume: 22.5 MB)
+NCU_DRAM_BYTES_PER_LAUNCH = 22.587e6     # measured, profiles/r1_step_kernel_v5_ncu_full.csv (algorithmic read volume: 22.5 MB)
 
 
 def algorithmic_bytes_per_env_step(n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS, s=8):
@@ -159,8 +159,6 @@ def run_b200(args):
                               min_start_goal_dis=30.0, num_beams=N_BEAMS)
         env.reset()
         batches.append(env)
-    for env in batches[1:]:
-        env.rng_key = None                         # 164 MB each; only batch 0 is used for the e2e (auto-reset) leg
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     actions = torch.randint(0, 9, (W + K, E), generator=g, device=dev, dtype=torch.int32)
     params = batches[0].params()
@@ -208,6 +206,16 @@ def run_b200(args):
         while time.perf_counter() - t_pre < args.preload:
             timed_region()
             torch.cuda.synchronize()
+        # The untimed preload above ran tens of thousands of steps without resets, so the robots have long left their
+        # maps.  Put every batch back into the stationary rollout distribution (fresh maps, then MIX auto-reset steps of the
+        # random policy: episodes in every phase, finished ones re-drawn) right before the timed region; the timed region
+        # itself then steps each batch K / N_BATCHES times without resets.
+        for bi, env in enumerate(batches):
+            env.reset()
+            for i in range(args.mix):
+                env.step(actions[(bi + i) % actions.shape[0]], auto_reset=True)
+        for i in range(N_BATCHES):                   # caches / instruction memory warm again after the reset kernels
+            one_step(W + i)
         barrier()
         ev0.record(stream)
         timed_region()
@@ -259,18 +267,18 @@ def run_b200(args):
                                    "11 beams, random actions (BASELINE configs[1])",
                        "envs_per_gpu": E, "l2": f"rotating {N_BATCHES} env batches ({N_BATCHES * E * abytes / 1e6:.0f} MB "
                                                 "> 126 MB L2), one batch per step",
-                       "auto_reset": "in e2e only", "parallelism": f"env-sharded x{world}, no collective in step",
+                       "auto_reset": "in e2e only; every batch is reset and mixed with %d auto-reset steps right before the timed region" % args.mix, "parallelism": f"env-sharded x{world}, no collective in step",
                        "launch": f"CUDA graph of {chunk} mnv_step launches x {n_rep} replays + {rem} eager",
                        "timed_region_ms": round(times[0], 4)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E == ENVS_PER_GPU else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                           "(profiles/r1_step_kernel_v3_ncu_full.csv); the 9.6 MB of writes were still in L2 "
+                                           "(profiles/r1_step_kernel_v5_ncu_full.csv); the 9.6 MB of writes were still in L2 "
                                            "when the profiled launch ended", "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": "mnv_env_kernel<4,8,true>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env0.h2d_bytes_per_step() * world,
                     "d2h_bytes_per_step": env0.d2h_bytes_per_step() * world, "checksum": checksum,
-                    "api": "VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset)"},
+                    "api": "VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step)"},
             "gpu_launches": K,
             "clocks": clk.summary(),
         }
@@ -412,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-iqn", action="store_true", help="skip the IQN legs")
+    ap.add_argument("--mix", type=int, default=200, help="auto-reset steps per env batch between the preload and the timed region")
     ap.add_argument("--preload", type=float, default=1.0, help="seconds of untimed identical load before the timed region (clock sampling)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -91,3 +91,14 @@ def reset(buf, rng_key, rng_pos, reset_params, mask=None):
                                _lib.ptr(buf["start_pose"]), _lib.ptr(buf["episode_step"]), _lib.ptr(buf["n_placed"]),
                                E, max_c, max_o, C.byref(reset_params), _stream())
     _lib.check(rc, "mnv_reset")
+
+
+def gather_rows(mask, rows, compact, index, count):
+    """Rows of `rows` (f32 [E, D]) where mask != 0 -> compact[:n], their env indices -> index[:n], n (total) -> count[0]."""
+    E, D = rows.shape
+    _chk(mask, torch.uint8, (E,), "mask"); _chk(rows, torch.float32, (E, D), "rows")
+    cap = compact.shape[0]
+    _chk(compact, torch.float32, (cap, D), "compact"); _chk(index, torch.int32, (cap,), "index"); _chk(count, torch.int32, (1,), "count")
+    rc = _lib.load().mnv_gather_rows(_lib.ptr(mask), _lib.ptr(rows), E, D, cap, _lib.ptr(compact), _lib.ptr(index),
+                                     _lib.ptr(count), _stream())
+    _lib.check(rc, "mnv_gather_rows")

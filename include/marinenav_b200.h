@@ -118,6 +118,14 @@ int mnv_reset(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint8_t* d_mask,
               double* d_start_pose, int32_t* d_episode_step, uint8_t* d_n_placed,
               int64_t E, int32_t max_c, int32_t max_o, const mnv_reset_params* rp, void* stream);
 
+/* Host-boundary helper of the vectorised env (no counterpart in the reference, which steps ONE env and returns numpy):
+ * compacts the rows d_rows[e][0:row_len] (f32, row-major, e.g. the observations) of every environment with d_mask[e] != 0
+ * into d_compact[k][0:row_len], k < min(count, cap), writes their environment indices to d_index[k] (order between
+ * warps is arbitrary, rows and indices agree) and the TOTAL number of selected environments to d_count (may exceed cap:
+ * the caller then falls back to a full copy).  One memset node + one kernel on `stream`. */
+int mnv_gather_rows(const uint8_t* d_mask, const float* d_rows, int64_t E, int32_t row_len, int32_t cap,
+                    float* d_compact, int32_t* d_index, int32_t* d_count, void* stream);
+
 /* ======================================= IQN (thirdparty/IQN) ============================================
  * Parameters: ONE flat fp32 vector of iqn_param_count() = 35 785 floats = the 14 tensors of ObsEncoder.state_dict() in
  * order (velocity_encoder.weight [16,2], .bias, goal_encoder.*, sensor_encoder.* [176,22], cos_embedding.* [208,64],

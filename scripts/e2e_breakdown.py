@@ -23,7 +23,8 @@ def timeit(fn, n=40):
 
 pin = env._pin()
 a_dev = torch.from_numpy(acts[0]).cuda()
-print("step_host total            %8.1f us" % timeit(lambda i: env.step_host(acts[10 + i % 50])))
+print("step_host (CUDA graph)     %8.1f us" % timeit(lambda i: env.step_host(acts[10 + i % 50])))
+print("step_host (eager)          %8.1f us" % timeit(lambda i: env.step_host(acts[10 + i % 50], graph=False)))
 print("device step(auto_reset)    %8.1f us" % timeit(lambda i: env.step(a_dev, auto_reset=True)))
 print("device step(no reset)      %8.1f us" % timeit(lambda i: env.step(a_dev, auto_reset=False)))
 print("H2D actions (pinned)       %8.1f us" % timeit(lambda i: env.buf["action"].copy_(pin["action"], non_blocking=True)))
