@@ -73,7 +73,8 @@ void        mnv_default_reset_params(mnv_reset_params* p);
 
 /* Process-wide tuning switches of the kernels (results are identical for every setting; parity tests run all of them).
  *   "pdl" 0|1  launch mnv_step / mnv_observe with programmatic stream serialization: the next launch on the stream is
- *              scheduled while this one drains and blocks in griddepcontrol.wait before its first global access (default 1)
+ *              scheduled while this one drains and blocks in griddepcontrol.wait before its first global access
+ *              (default 0: measured 1 % slower on back-to-back steps, profiles/README.md)
  *   "tma" 0|1  stage the obstacle rows with the TMA bulk-copy engine (cp.async.bulk) instead of per-thread cp.async
  *              (default 0: measured slower, profiles/README.md)
  * Returns 0, or MNV_E_PARAM for an unknown key.  mnv_get_option returns the value or MNV_E_PARAM. */

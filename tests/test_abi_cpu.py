@@ -59,6 +59,23 @@ def test_argument_errors_before_any_launch(lib):
         _lib.check(-4, "mnv_step")
 
 
+def test_kernel_options_roundtrip(lib):
+    for key in (b"tma", b"pdl"):
+        old = lib.mnv_get_option(key)
+        assert old in (0, 1)
+        assert lib.mnv_set_option(key, 1 - old) == 0 and lib.mnv_get_option(key) == 1 - old
+        assert lib.mnv_set_option(key, old) == 0
+    assert lib.mnv_set_option(b"no-such-switch", 1) == -5 and lib.mnv_get_option(b"no-such-switch") == -5
+    assert b"unknown key" in lib.mnv_last_error_string()
+
+
+def test_gather_rows_argument_errors(lib):
+    ok = C.c_void_p(4096)
+    assert lib.mnv_gather_rows(None, ok, 16, 26, 4, ok, ok, ok, None) == -1
+    assert lib.mnv_gather_rows(ok, ok, 0, 26, 4, ok, ok, ok, None) == -3
+    assert lib.mnv_gather_rows(ok, C.c_void_p(4100), 16, 26, 4, ok, ok, ok, None) == -2
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "distributional_rl_navigation_b200")
     extra = [os.path.join(ROOT, d) for d in ("marinenav_env", "thirdparty")]

@@ -86,6 +86,20 @@ def test_step_golden_vectors(golden_dir):
     run_step_vectors(np.load(os.path.join(golden_dir, "step_vectors.npz")), 11)
 
 
+@pytest.mark.parametrize("opts", [dict(tma=1, pdl=1), dict(tma=0, pdl=0), dict(tma=1, pdl=0)])
+def test_step_golden_vectors_every_kernel_option(golden_dir, opts):
+    """mnv_set_option switches (TMA bulk-copy staging of the obstacle rows, programmatic dependent launch) never change a result."""
+    L = _lib.load()
+    old = {k: L.mnv_get_option(k.encode()) for k in opts}
+    try:
+        for k, v in opts.items():
+            assert L.mnv_set_option(k.encode(), v) == 0 and L.mnv_get_option(k.encode()) == v
+        run_step_vectors(np.load(os.path.join(golden_dir, "step_vectors.npz")), 11)
+    finally:
+        for k, v in old.items():
+            L.mnv_set_option(k.encode(), v)
+
+
 def test_step_dense_golden_vectors(golden_dir):
     run_step_vectors(np.load(os.path.join(golden_dir, "dense_vectors.npz")), 64)
 
