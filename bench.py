@@ -268,7 +268,8 @@ def run_b200(args):
                        "envs_per_gpu": E, "l2": f"rotating {N_BATCHES} env batches ({N_BATCHES * E * abytes / 1e6:.0f} MB "
                                                 "> 126 MB L2), one batch per step",
                        "auto_reset": "in e2e only; every batch is reset and mixed with %d auto-reset steps right before the timed region" % args.mix, "parallelism": f"env-sharded x{world}, no collective in step",
-                       "launch": f"CUDA graph of {chunk} mnv_step launches x {n_rep} replays + {rem} eager",
+                       "launch": f"CUDA graph of {chunk} mnv_step launches x {n_rep} replays + {rem} eager; launch mode pdl={_lib.get_option('pdl')} "
+                                 "(VecMarineNavEnv default 2: programmatic dependent launch, map tables fetched ahead of the grid dependency)",
                        "timed_region_ms": round(times[0], 4)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E == ENVS_PER_GPU else None,

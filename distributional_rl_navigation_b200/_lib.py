@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "lib", "libmarinenav_b200.so")
+SO_PATH = os.environ.get("MNV_LIB") or os.path.join(_PKG, "lib", "libmarinenav_b200.so")   # MNV_LIB: A/B of two builds (lab use)
 
 INFO_STRINGS = ("normal", "too long episode", "collision", "reach goal", "out of boundary")   # marinenav_env.py:243-257
 MAX_CORES, MAX_OBSTACLES, MAX_BEAMS = 8, 32, 128
@@ -91,6 +91,18 @@ def check(rc, what):
     if rc != 0:
         msg = load().mnv_last_error_string().decode()
         raise MarinenavError(f"{what} failed (rc={rc}): {msg}")
+
+
+def set_option(key, value):
+    """mnv_set_option: process-wide kernel switches ("tma", "pdl"), see include/marinenav_b200.h."""
+    check(load().mnv_set_option(key.encode(), int(value)), f"mnv_set_option({key})")
+
+
+def get_option(key):
+    v = load().mnv_get_option(key.encode())
+    if v < 0:
+        check(v, f"mnv_get_option({key})")
+    return v
 
 
 def default_params(n_beams=11):

@@ -38,7 +38,7 @@ struct KParams {
     double range, range_slack;
     double width, height;
     int n_substeps, n_beams, max_ep_steps, set_boundary;
-    int max_c, max_o, obs_dim, velocity_from_state, allow_tma;
+    int max_c, max_o, obs_dim, velocity_from_state, allow_tma, pdl_prefetch;
     long long E;
     double snap_t1, snap_t2;        // pi/2 - beam_angle[0], 3pi/2 - beam_angle[0]   (Q10 pre-test, see snap_beam)
     float inv_phi, snap_tol;        // 1 / beam spacing, (1e-3 / spacing) + 1e-4 in beam-index units
@@ -138,13 +138,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Dynamic shared memory: [kBlock * obs_dim floats, padded to 16 B][3 * max_o rows x kBlock doubles][mbarriers][exact-test rings]
 constexpr int kRing = 64;       // per-warp ring of pending exact sonar tests: < 32 pending + <= 32 pushed per beam
 
-template <int MAXC, int MAXO, bool STEP>
-__global__ void __launch_bounds__(kBlock, 8)
+#ifndef MNV_MIN_CTAS
+#define MNV_MIN_CTAS 8
+#endif
+template <int MAXC, int MAXO, bool STEP, bool PREFETCH>
+__global__ void __launch_bounds__(kBlock, MNV_MIN_CTAS)
 mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
+    static_assert(STEP || !PREFETCH, "only the step launch fetches the map tables ahead of its grid dependency");
     static_assert((MAXO & 1) == 0 && MAXO <= 16, "obstacle pairs are packed for FFMA2; the candidate mask is 16 bits of a ring entry");
     extern __shared__ __align__(16) float s_obs[];           // [kBlock][obs_dim]
-    pdl_launch_dependents();                                  // the next launch on the stream may be scheduled while this one drains
     const long long E = K.E;
     const long long e0 = (long long)blockIdx.x * kBlock;
     const int tid = threadIdx.x;
@@ -156,14 +159,36 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ob + 3 * K.max_o * kBlock);
     unsigned* ring = reinterpret_cast<unsigned*>(s_bar + kBlock / 32) + (tid >> 5) * kRing;
     const int max_o = K.max_o;
+    // vortex cores (registers), goal and obstacle rows (shared memory, per-thread cp.async: each thread copies its own
+    // column; first needed after the sub-step loop, so that DRAM round trip hides under the integration)
+    double cx[MAXC], cy[MAXC], ck[MAXC], gx = 0.0, gy = 0.0;
+    auto load_tables = [&]() {
+        gx = P.goal[e]; gy = P.goal[E + e];
+        const double* pc = P.cores + e;
+        const long long rowstride = (long long)K.max_c * E;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            if (i < K.max_c) { cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride); ck[i] = __ldg(pc + 2 * rowstride); }
+            else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+            pc += E;
+        }
+        const double* po = P.obst + e;
+        for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
+        cp_async_commit();
+    };
+    // "pdl" = 2: the map tables (goal, cores, obstacles) are not written by the launch right before this one (the caller's
+    // contract; true for step -> step and for step after anything but mnv_reset / a table upload), so they are fetched
+    // while that launch still drains; everything else waits for it.
+    if (PREFETCH && e < E) load_tables();
     pdl_wait();                                               // everything below reads what earlier launches wrote
+    pdl_launch_dependents();                                  // the next launch may be scheduled while this one runs (it waits like this one)
     const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
 
     // ---- (optional, "tma" = 1) obstacle table slice of every warp -> shared memory with the TMA bulk-copy engine: 3*max_o rows of 32 consecutive
     //      environments (256 contiguous bytes each), issued by the warp's lane 0 and tracked by the warp's own mbarrier.  The rows are first
     //      needed after the sub-step loop, so this DRAM round trip overlaps the integration.  Ragged / masked / odd-E
     //      launches (rows not 16-byte aligned or not full) use per-thread cp.async instead. ----
-    const bool use_tma = K.allow_tma && (e0 + kBlock <= E) && ((E & 1) == 0) && (STEP || P.mask == nullptr) && max_o > 0;
+    const bool use_tma = !PREFETCH && K.allow_tma && (e0 + kBlock <= E) && ((E & 1) == 0) && (STEP || P.mask == nullptr) && max_o > 0;
     const int warp_in_cta = tid >> 5;
     unsigned long long* my_bar = s_bar + warp_in_cta;             // one mbarrier per warp: no CTA-wide sync needed
     if (use_tma) {
@@ -181,7 +206,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 
     // state that crosses the three phases (per-lane integration / warp-wide sonar / per-lane termination); lanes without a
     // live environment carry inert values through the warp-wide phase (no candidates, nothing pushed)
-    double x = 0.0, y = 0.0, th = 0.0, sp = 0.0, gx = 0.0, gy = 0.0, c = 1.0, s = 0.0;
+    double x = 0.0, y = 0.0, th = 0.0, sp = 0.0, c = 1.0, s = 0.0;
     double vx = 0.0, vy = 0.0, reward = 0.0, dis_after = 0.0;
     int ep = 0, bs1 = -1, bs2 = -1;
     f32x2 qx2[MAXO / 2], qy2[MAXO / 2], nr2[MAXO / 2];      // fp32: only the conservative candidate filter uses them
@@ -195,28 +220,21 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         //      costs ONE DRAM round trip (the ncu source page of the previous version showed three in a row: state -> sincos,
         //      cores -> first sub-step, action -> accel / yaw tables) ----
         x = P.state[e]; y = P.state[E + e]; th = P.state[2 * E + e]; sp = P.state[3 * E + e];
-        gx = P.goal[e]; gy = P.goal[E + e];
         int action = 0;
         if (STEP) { action = P.action[e]; ep = P.ep_step[e]; }
-        // vortex cores -> registers; k = Gs/(2pi) carries the spin in its sign
-        double cx[MAXC], cy[MAXC], ck[MAXC];
-        {
-            const double* pc = P.cores + e;
-            const long long rowstride = (long long)K.max_c * E;
+        if (!PREFETCH) {
+            if (!use_tma) load_tables();
+            else {
+                gx = P.goal[e]; gy = P.goal[E + e];
+                const double* pc = P.cores + e;
+                const long long rowstride = (long long)K.max_c * E;
 #pragma unroll
-            for (int i = 0; i < MAXC; ++i) {
-                if (i < K.max_c) { cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride); ck[i] = __ldg(pc + 2 * rowstride); }
-                else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
-                pc += E;
+                for (int i = 0; i < MAXC; ++i) {
+                    if (i < K.max_c) { cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride); ck[i] = __ldg(pc + 2 * rowstride); }
+                    else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+                    pc += E;
+                }
             }
-        }
-        // ---- staging of the obstacle rows with per-thread cp.async (each thread copies its own column): issued right behind
-        //      the loads the integration is waiting for; first needed after the sub-step loop, so this DRAM round trip
-        //      overlaps the integration ----
-        if (!use_tma) {
-            const double* po = P.obst + e;
-            for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
-            cp_async_commit();
         }
         sincos(th, &s, &c);
 #pragma unroll
@@ -481,8 +499,8 @@ __global__ void __launch_bounds__(kDenseWarps * 32)
 mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
     extern __shared__ __align__(16) float s_obs[];                 // [kDenseWarps][obs_dim]
-    pdl_launch_dependents();
     pdl_wait();                                                    // everything below reads what earlier launches wrote
+    pdl_launch_dependents();
     const long long E = K.E;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long e = (long long)blockIdx.x * kDenseWarps + w;
@@ -683,7 +701,7 @@ int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
     const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + 8 * (kBlock / 32) + (size_t)(kBlock / 32) * kRing * sizeof(unsigned);
 #define MNV_LAUNCH(MC, MO)                                                                                   \
     do {                                                                                                     \
-        auto kern = mnv_env_kernel<MC, MO, STEP>;                                                            \
+        auto kern = (STEP && K.pdl_prefetch) ? mnv_env_kernel<MC, MO, STEP, STEP> : mnv_env_kernel<MC, MO, STEP, false>; \
         if (smem > 48 * 1024) {                                                                              \
             cudaError_t a = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (a != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(a)); return (int)a; } \
@@ -722,6 +740,7 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
     K.n_beams = p->n_beams; K.max_ep_steps = p->max_episode_steps; K.set_boundary = p->set_boundary;
     K.max_c = max_c; K.max_o = max_o; K.obs_dim = 4 + 2 * p->n_beams; K.E = E;
     K.allow_tma = mnv_option(MNV_OPT_TMA) ? 1 : 0;
+    K.pdl_prefetch = mnv_option(MNV_OPT_PDL) >= 2 ? 1 : 0;
     // "tma" = 1 stages the obstacle rows with the TMA bulk-copy engine (UBLKCP) instead of per-thread cp.async (LDGSTS).
     // Measured A/B in one process (profiles/README.md): 25.03 us vs 24.18 us per step -> cp.async is the default.
     // Sonar.compute_phi / compute_beam_angles (robot.py:14-21)

@@ -184,6 +184,7 @@ class MarineNavEnv(_gym.Env):
         goal = (float(self.goal[0]), float(self.goal[1]))      # callers assign env.goal directly (run_experiments.py:134,196)
         if getattr(self, "_goal_pushed", None) != goal:
             v.buf["goal"][:, 0] = torch.tensor(goal, dtype=torch.float64, device=v.device)
+            v.tables_written()
             self._goal_pushed = goal
 
     def _obs_out(self, obs_t):
@@ -291,6 +292,7 @@ class MarineNavEnv(_gym.Env):
             t[k], t[mc + k], t[2 * mc + k] = c.x, c.y, (c.Gamma if c.clockwise else -c.Gamma)
         b["cores"][:, 0] = torch.from_numpy(t).to(self._vec.device)
         b["n_placed"][0, 0] = len(cores)
+        self._vec.tables_written()
 
     @property
     def obstacles(self):
@@ -307,6 +309,7 @@ class MarineNavEnv(_gym.Env):
             t[k], t[mo + k], t[2 * mo + k] = o.x, o.y, o.r
         b["obstacles"][:, 0] = torch.from_numpy(t).to(self._vec.device)
         b["n_placed"][1, 0] = len(obstacles)
+        self._vec.tables_written()
 
     # The reference keeps scipy KDTrees of the centres (marinenav_env.py:155,181) and callers re-assign them after editing
     # the lists (run_experiments.py:160,178).  The kernels do not need them: reading builds one on demand, writing is accepted

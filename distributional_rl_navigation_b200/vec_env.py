@@ -6,6 +6,7 @@ device tensors laid out as include/marinenav_b200.h describes.  Environment e us
 stream seeded with ``seed + e`` -> its maps are the ones ``MarineNavEnv(seed=seed + e)`` of the reference generates.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -21,6 +22,12 @@ class VecMarineNavEnv:
         if not torch.cuda.is_available():
             raise _lib.MarinenavError("VecMarineNavEnv needs a CUDA device (there is no CPU fallback)")
         _lib.load()
+        # Launch mode of the step kernel: "pdl" = 2 lets a step fetch the map tables (goal, cores, obstacles) while the
+        # launch before it on the stream still drains (include/marinenav_b200.h).  Its contract -- the launch right before
+        # mnv_step does not write those tables -- holds for every sequence of this class: mnv_reset is always followed by
+        # mnv_observe, table uploads are host copies, and tables_written() fences device-side edits (the facade's setters).
+        if os.environ.get("MNV_PDL") is None and _lib.get_option("pdl") == 0:
+            _lib.set_option("pdl", 2)
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         self.sd = seed
@@ -243,6 +250,11 @@ class VecMarineNavEnv:
                 elif n > 0:
                     obs[pin["index"].numpy()[:n]] = pin["compact"].numpy()[:n]
         return obs, pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
+
+    def tables_written(self):
+        """Call after writing buf['goal'|'cores'|'obstacles'] with a device-side kernel (e.g. indexed assignment) if a step
+        may follow directly: the step kernel reads these tables ahead of its stream dependency ("pdl" = 2)."""
+        torch.cuda.current_stream(self.device).synchronize()
 
     def reset_host(self):
         pin = self._pin()

@@ -72,9 +72,14 @@ void        mnv_default_params(mnv_params* p);
 void        mnv_default_reset_params(mnv_reset_params* p);
 
 /* Process-wide tuning switches of the kernels (results are identical for every setting; parity tests run all of them).
- *   "pdl" 0|1  launch mnv_step / mnv_observe with programmatic stream serialization: the next launch on the stream is
- *              scheduled while this one drains and blocks in griddepcontrol.wait before its first global access
- *              (default 0: measured 1 % slower on back-to-back steps, profiles/README.md)
+ *   "pdl" 0|1|2  1: launch mnv_step / mnv_observe with programmatic stream serialization: the next launch on the stream
+ *              is scheduled while this one drains and blocks in griddepcontrol.wait before its first global access
+ *              (measured 1 % slower than 0 on back-to-back steps, profiles/README.md).  2: additionally mnv_step fetches
+ *              the map tables (d_goal, d_cores, d_obstacles) BEFORE that wait, i.e. while the previous launch still
+ *              runs: 15.1 -> 12.9 us per 65 536-env step.  CONTRACT of 2: the launch immediately before mnv_step on the
+ *              stream does not write those three tables (mnv_reset must be followed by mnv_observe or any other launch
+ *              first; host -> device copies are fine).  Default 0; VecMarineNavEnv, whose sequences satisfy the
+ *              contract, selects 2 unless MNV_PDL is set in the environment.
  *   "tma" 0|1  stage the obstacle rows with the TMA bulk-copy engine (cp.async.bulk) instead of per-thread cp.async
  *              (default 0: measured slower, profiles/README.md)
  * Returns 0, or MNV_E_PARAM for an unknown key.  mnv_get_option returns the value or MNV_E_PARAM. */
