@@ -251,6 +251,7 @@ def run_b200(args):
         env.buf = None
     batches = batches[:1]
     torch.cuda.empty_cache()
+    dense = None if args.no_dense else dense_leg(args, dev, world, rank)
     iqn = None if args.no_iqn else iqn_bench(args, dev, world)       # every rank takes part (all-reduce inside)
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
@@ -289,12 +290,61 @@ def run_b200(args):
                                     "sample": f"{E} envs x 40 steps of the same workload, oracle/marinenav_oracle.c "
                                               f"({cpu_dt:.1f} s on {cpu_cores} threads; the Python reference itself: "
                                               "330-385 steps/s/core, SURVEY.md section 6)"}
+        if dense is not None:
+            line["dense"] = dense
         if iqn is not None:
             line["iqn"] = iqn
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Dense-map leg (BASELINE configs[4]: 32 obstacles, 64 beams, 131 072 envs over 8 GPUs = 16 384 per GPU; ray-cast stress)
+# ---------------------------------------------------------------------------------------------------------------
+def dense_leg(args, dev, world, rank):
+    import torch
+    import torch.distributed as dist
+    from distributional_rl_navigation_b200 import env_ops
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+    E, n_c, n_o, n_b, nb = 16384, 4, 32, 64, 8                      # 8 batches x 24 MB > L2
+    batches = []
+    for b in range(nb):
+        env = VecMarineNavEnv(E, seed=(rank * nb + b) * E + 7_000_000, device=dev, num_cores=n_c, num_obs=n_o,
+                              min_start_goal_dis=30.0, num_beams=n_b)
+        env.reset()
+        batches.append(env)
+    g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+    actions = torch.randint(0, 9, (64, E), generator=g, device=dev, dtype=torch.int32)
+    params = batches[0].params()
+    for bi, env in enumerate(batches):
+        for i in range(20):
+            env.step(actions[(bi + i) % 64], auto_reset=True)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(64):
+                env_ops.step(batches[i % nb].buf, params, action=actions[i])
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 256], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    ab = algorithmic_bytes_per_env_step(n_c, n_o, n_b)
+    peak, _ = measured_peak_hbm()
+    return {"workload": "dense map: 32 obstacles, 64 sonar beams, 16384 envs/GPU (BASELINE configs[4] per-GPU shard), mnv_env_dense_kernel",
+            "ms_per_step": ms, "env_steps_per_s": world * E / (ms * 1e-3), "algorithmic_bytes_per_env_step": ab,
+            "hbm_roofline_frac": E * ab / (ms * 1e-3) / 1e9 / peak, "bound": "fp64 / issue (2048 ray-circle tests per env-step), not HBM"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -421,6 +471,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-iqn", action="store_true", help="skip the IQN legs")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-map leg")
     ap.add_argument("--mix", type=int, default=200, help="auto-reset steps per env batch between the preload and the timed region")
     ap.add_argument("--preload", type=float, default=1.0, help="seconds of untimed identical load before the timed region (clock sampling)")
     args = ap.parse_args()

@@ -46,6 +46,8 @@ struct KParams {
     double beam_cos[MNV_MAX_BEAMS];
     double beam_sin[MNV_MAX_BEAMS];
     float2 beam_dirf[MNV_MAX_BEAMS];   // (cos, sin) of the beam in the robot frame, fp32, for the candidate filter
+    alignas(8) float beam_cosf[MNV_MAX_BEAMS + 2];   // the same as two planar arrays (beam pairs of the dense kernel; zero padded)
+    alignas(8) float beam_sinf[MNV_MAX_BEAMS + 2];
 };
 
 struct EnvPtrs {
@@ -485,12 +487,17 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 // ---------------------------------------------------------------------------------------------------------------------
 // Dense maps (BASELINE configs[4]: 32 obstacles x 64 beams, few thousand envs per GPU): ONE WARP PER ENVIRONMENT.
 // A thread-per-env mapping leaves a 16 384-env batch with 3.5 warps per SM and 2 048 serial ray/circle tests per thread;
-// here lane j owns obstacle j (and, in the sub-steps, vortex core j), every beam is one warp-wide test, and the
-// reference's ordered first-hit scan (robot.py:192-195, Q3) is rebuilt from warp ballots:
-//   V  = ballot(valid hit on my obstacle)                      valid = real root, 0 <= t <= range (robot.py:172-190)
-//   p(j) = highest set bit of V below lane j                   the previously recorded hit when the scan reaches j
-//   Bk = ballot(valid_j && p(j) exists && t_j >= t_p(j))       the scan breaks at the first such j
-//   result = Bk ? p(ffs(Bk)) : highest set bit of V            (the recorded hits form a strictly decreasing run)
+// here lane j owns obstacle j (and, in the sub-steps, vortex core j).
+//   * candidate filter: every lane tests its obstacle against TWO beams per FFMA2 (same fp32 test as mnv_env_kernel);
+//   * the exact fp64 tests are not run beam by beam (a beam has ~1.4 candidates, i.e. ~1.4 busy lanes): the candidate
+//     (beam, obstacle) pairs are appended in (beam, obstacle) order to a 32-entry ring in shared memory and evaluated 32
+//     at a time, one pair per lane (the obstacle's robot-frame centre comes from its owner lane by shuffle);
+//   * the reference's ordered first-hit scan (robot.py:192-195, Q3) is rebuilt per beam from warp ballots restricted to
+//     the beam's SEGMENT of the batch (match.any on the beam index; a batch only holds complete beams):
+//       V  = ballot(valid hit) & segment                          valid = real root, 0 <= t <= range (robot.py:172-190)
+//       p(l) = highest set bit of V below lane l                  the previously recorded hit when the scan reaches l
+//       Bk = ballot(valid_l && p(l) exists && t_l >= t_p(l)) & segment     the scan breaks at the first such l
+//       result = Bk ? p(ffs(Bk)) : highest set bit of V           (the recorded hits form a strictly decreasing run)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDenseWarps = 4;
 
@@ -498,7 +505,7 @@ template <bool STEP>
 __global__ void __launch_bounds__(kDenseWarps * 32)
 mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
-    extern __shared__ __align__(16) float s_obs[];                 // [kDenseWarps][obs_dim]
+    extern __shared__ __align__(16) float s_obs[];                 // [kDenseWarps][obs_dim] floats, then [kDenseWarps][32] ring words
     pdl_wait();                                                    // everything below reads what earlier launches wrote
     pdl_launch_dependents();
     const long long E = K.E;
@@ -506,22 +513,21 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     const long long e = (long long)blockIdx.x * kDenseWarps + w;
     const int D = K.obs_dim;
     float* my_obs = s_obs + w * D;
+    unsigned* ring = reinterpret_cast<unsigned*>(s_obs + ((kDenseWarps * D + 3) & ~3)) + w * 32;
     if (e >= E) return;                                            // warp-uniform
     if (!STEP && P.mask != nullptr && P.mask[e] == 0) return;
 
+    // ---- all loads first: one DRAM round trip ----
     double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
     const double gx = P.goal[e], gy = P.goal[E + e];
-    double c, s;
-    sincos(th, &s, &c);
-    double vx, vy, reward = 0.0;
-    int ep = 0;
-
+    int action = 0, ep = 0;
+    if (STEP) { action = P.action[e]; ep = P.ep_step[e]; }
     // lane i < max_c owns vortex core i (k = Gs / 2pi carries the spin in its sign)
     double cx = 0.0, cy = 0.0, ck = 0.0;
     if (lane < K.max_c) {
         cx = __ldg(P.cores + (long long)lane * E + e);
         cy = __ldg(P.cores + (long long)(K.max_c + lane) * E + e);
-        ck = __ldg(P.cores + (long long)(2 * K.max_c + lane) * E + e) * (1.0 / (2.0 * MNV_PI));
+        ck = __ldg(P.cores + (long long)(2 * K.max_c + lane) * E + e);
     }
     // lane j < max_o owns obstacle j
     double ox = 0.0, oy = 0.0, orad = -1.0;
@@ -530,6 +536,10 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         oy = __ldg(P.obst + (long long)(K.max_o + lane) * E + e);
         orad = __ldg(P.obst + (long long)(2 * K.max_o + lane) * E + e);
     }
+    double c, s;
+    sincos(th, &s, &c);
+    ck *= (1.0 / (2.0 * MNV_PI));
+    double vx, vy, reward = 0.0, dis_after = 0.0;
     auto current = [&](double px, double py, double& ux, double& uy) {
         const double dx = cx - px, dy = cy - py;
         const double d2 = fma(dx, dx, dy * dy);
@@ -544,8 +554,6 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     };
 
     if (STEP) {
-        const int action = P.action[e];
-        ep = P.ep_step[e];
         const int ai = action / 3, wi = action - 3 * ai;
         const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
         const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
@@ -559,7 +567,9 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             sp = sp < 0.0 ? 0.0 : sp;                              // robot.py:114
             sp = sp > K.max_speed ? K.max_speed : sp;
             th = __dadd_rn(th, wdt);                               // robot.py:117
-            if (th < 0.0 || th >= 2.0 * MNV_PI) {                  // robot.py:120-123
+            th = th < 0.0 ? __dadd_rn(th, 2.0 * MNV_PI) : th;      // robot.py:120-123 (see mnv_env_kernel)
+            th = th >= 2.0 * MNV_PI ? __dsub_rn(th, 2.0 * MNV_PI) : th;
+            if (th < 0.0 || th >= 2.0 * MNV_PI) {
 #pragma unroll 1
                 while (th < 0.0) th += 2.0 * MNV_PI;
 #pragma unroll 1
@@ -571,7 +581,7 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 P.traj[(long long)(2 * it) * E + e] = x; P.traj[(long long)(2 * it + 1) * E + e] = y;
             }
         }
-        const double dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+        dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
         reward = K.pen_step + (dis_before - dis_after);            // marinenav_env.py:220,229
     } else {
         if (K.velocity_from_state) {
@@ -582,12 +592,15 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         } else { vx = P.velocity[e]; vy = P.velocity[E + e]; }
     }
 
+    const int n_beams = K.n_beams;
     if (lane == 0) {                                               // observation head (marinenav_env.py:278-293)
         my_obs[0] = (float)fma(c, vx, s * vy);
         my_obs[1] = (float)fma(c, vy, -s * vx);
         my_obs[2] = (float)fma(c, gx - x, s * (gy - y));
         my_obs[3] = (float)fma(c, gy - y, -s * (gx - x));
     }
+    for (int b = lane; b < n_beams; b += 32)                       // "no return" everywhere (marinenav_env.py:318-320); hits overwrite
+        *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);
 
     // ---- my obstacle in the robot frame ----
     const bool on = orad > 0.0;
@@ -596,9 +609,14 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     const double qx = fma(c, dxo, s * dyo), qy = fma(c, dyo, -s * dxo), rr = orad * orad;
     const double lim = K.range_slack + orad;
     const bool relevant = on && d2o <= lim * lim;                  // reachable within the sonar range at all
-    const bool borderline = on && fabs(d2o - rr) <= 1e-9 * rr;     // robot on the circle: never filter
-    const float sg = d2o < rr ? -1.f : 1.f;                        // inside the circle the nearer root is in front iff tc <= 0
-    const float qxf = sg * (float)qx, qyf = sg * (float)qy, r2f = (float)rr;
+    const bool borderline = relevant && fabs(d2o - rr) <= 1e-9 * rr;   // robot on the circle: never filter
+    // fp32 filter operands: sigma q (inside the circle the nearer root is in front iff tc <= 0), -(r^2 + 1e-3);
+    // "always a candidate" = q = 0 with a very negative nr, "never" = nr = +1e30
+    const float sg = d2o < rr ? -1.f : 1.f;
+    const float qxf = borderline ? 0.f : sg * (float)qx, qyf = borderline ? 0.f : sg * (float)qy;
+    const float nrf = !relevant ? 1e30f : (borderline ? -1e30f : -((float)rr + 1e-3f));
+    const f32x2 qx2 = pack2(qxf, qxf), qy2 = pack2(qyf, qyf), nqx2 = pack2(-qxf, -qxf), nr2 = pack2(nrf, nrf);
+    const f32x2 margin2 = pack2(1e-3f, 1e-3f);
 
     // ---- Q4: collision against the nearest CENTRE only (marinenav_env.py:329-336): warp arg-min ----
     double best_d2 = on ? d2o : INFINITY, best_r = orad;
@@ -611,56 +629,87 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         if (od < best_d2 || (od == best_d2 && oi < best_i)) { best_d2 = od; best_r = orr; best_i = oi; }
     }
 
-    // ---- sonar: one warp-wide ray/circle test per beam ----
-    for (int b = 0; b < K.n_beams; ++b) {
-        const double ang = th + K.beam_angle[b];                   // robot.py:131 (not wrapped)
-        double bx = K.beam_cos[b], by = K.beam_sin[b];
-        if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }             // Q10
-        else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }
-        const float bxf = (float)bx, byf = (float)by;
-        // conservative fp32 filter (see mnv_env_kernel): real roots and the nearer root not behind the robot, 1e-3 margin
-        const float tcf = fmaf(qxf, bxf, qyf * byf), crf = fmaf(qxf, byf, -qyf * bxf);
-        const bool cand = relevant && (borderline || fminf(fmaf(-crf, crf, r2f), tcf) >= -1e-3f);
-        float hx = 0.f, hy = 0.f;
-        if (__any_sync(0xffffffffu, cand)) {
-            bool valid = false;
-            double t = 0.0;
-            if (cand) {                                            // exact fp64 decision (robot.py:164-190)
-                const double tc = fma(qx, bx, qy * by), cr = fma(qx, by, -qy * bx);
-                const double disc = fma(-cr, cr, rr);
-                if (disc >= 0.0) {
-                    const double h = sqrt(disc);
-                    t = tc > 0.0 ? tc - h : tc + h;                // nearer root first (robot.py:184)
-                    valid = (t <= K.range) && (t >= 0.0);
-                }
+    // ---- Q10 pre-test (see mnv_env_kernel): the only beams that can be snapped to the vertical ----
+    int bs1, bs2;
+    {
+        const float u1 = (float)(K.snap_t1 - th) * K.inv_phi, u2 = (float)(K.snap_t2 - th) * K.inv_phi;
+        const float n1 = rintf(u1), n2 = rintf(u2);
+        bs1 = fabsf(u1 - n1) < K.snap_tol ? (int)n1 : -1;
+        bs2 = fabsf(u2 - n2) < K.snap_tol ? (int)n2 : -1;
+    }
+
+    // ---- sonar ----
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int n_pend = 0;                                                // warp-uniform
+    auto drain = [&]() {
+        __syncwarp();
+        const bool mine = lane < n_pend;
+        const unsigned ent = mine ? ring[lane] : 0u;               // [4:0] obstacle (owner lane), [12:5] beam
+        const int j = ent & 31, bb = ent >> 5;
+        const double oqx = __shfl_sync(0xffffffffu, qx, j), oqy = __shfl_sync(0xffffffffu, qy, j), orr2 = __shfl_sync(0xffffffffu, rr, j);
+        bool valid = false;
+        double t = 0.0, bx = 0.0, by = 0.0;
+        if (mine) {                                                // exact fp64 decision (robot.py:164-190)
+            bx = K.beam_cos[bb]; by = K.beam_sin[bb];
+            if (bb == bs1 || bb == bs2) {
+                const double ang = th + K.beam_angle[bb];          // robot.py:131 (not wrapped)
+                if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }             // Q10
+                else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }
             }
-            const unsigned V = __ballot_sync(0xffffffffu, valid);
-            if (V != 0u) {
-                const unsigned below = V & ((1u << lane) - 1u);
-                const int pj = below ? 31 - __clz(below) : -1;     // previous valid hit in list order
-                const double tp = __shfl_sync(0xffffffffu, t, pj < 0 ? 0 : pj);
-                const unsigned Bk = __ballot_sync(0xffffffffu, valid && pj >= 0 && t >= tp);
-                int res;
-                if (Bk == 0u) res = 31 - __clz(V);
-                else {
-                    const int f = __ffs(Bk) - 1;
-                    const unsigned bf = V & ((1u << f) - 1u);
-                    res = 31 - __clz(bf);                          // bf != 0: a breaking lane has a predecessor
-                }
-                const double tr = __shfl_sync(0xffffffffu, t, res);
-                hx = (float)(tr * bx); hy = (float)(tr * by);      // marinenav_env.py:314-320
+            const double tc = fma(oqx, bx, oqy * by), cr = fma(oqx, by, -oqy * bx);
+            const double disc = fma(-cr, cr, orr2);
+            if (disc >= 0.0) {
+                const double h = sqrt(disc);
+                t = tc > 0.0 ? tc - h : tc + h;                    // nearer root first (robot.py:184)
+                valid = (t <= K.range) && (t >= 0.0);
             }
         }
-        if (lane == 0) { my_obs[4 + 2 * b] = hx; my_obs[5 + 2 * b] = hy; }
+        // ordered scan per beam = per segment of equal beam index (entries are in (beam, obstacle) order)
+        const unsigned seg = __match_any_sync(0xffffffffu, mine ? bb : 0x1000 + lane);
+        const unsigned V = __ballot_sync(0xffffffffu, valid) & seg;
+        const unsigned below = V & lt_mask;
+        const int pj = below ? 31 - __clz(below) : -1;             // previous valid hit of my beam in list order
+        const double tp = __shfl_sync(0xffffffffu, t, pj < 0 ? 0 : pj);
+        const unsigned Bk = __ballot_sync(0xffffffffu, valid && pj >= 0 && t >= tp) & seg;
+        const int f = Bk ? __ffs(Bk) - 1 : 0;
+        const int pf = __shfl_sync(0xffffffffu, pj, f);            // predecessor of the first breaking lane (>= 0 when Bk != 0)
+        const int res = Bk ? pf : (V ? 31 - __clz(V) : -1);
+        if (mine && lane == res)                                   // marinenav_env.py:314-317
+            *reinterpret_cast<float2*>(my_obs + 4 + 2 * bb) = make_float2((float)(t * bx), (float)(t * by));
+        n_pend = 0;
+        __syncwarp();
+    };
+    auto push = [&](bool cand, int b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal == 0u) return;
+        const int cnt = __popc(bal);
+        if (n_pend + cnt > 32) drain();                            // a batch only holds complete beams (cnt <= 32)
+        if (cand) ring[n_pend + __popc(bal & lt_mask)] = (unsigned)lane | ((unsigned)b << 5);
+        n_pend += cnt;
+    };
+    for (int b = 0; b < n_beams; b += 2) {
+        // conservative fp32 filter (see mnv_env_kernel), two beams per FFMA2: cr^2 - r^2 - 1e-3 < 0 and tc + 1e-3 >= 0
+        const f32x2 bx2 = *reinterpret_cast<const f32x2*>(&K.beam_cosf[b]), by2 = *reinterpret_cast<const f32x2*>(&K.beam_sinf[b]);
+        const f32x2 tc = fma2(qx2, bx2, fma2(qy2, by2, margin2));
+        const f32x2 ncr = fma2(qy2, bx2, mul2(nqx2, by2));
+        const f32x2 nd = fma2(ncr, ncr, nr2);
+        unsigned t0, t1, d0, d1;
+        unpack2(tc, t0, t1); unpack2(nd, d0, d1);
+        bool c0 = (int)(d0 & ~t0) < 0, c1 = (int)(d1 & ~t1) < 0 && (b + 1 < n_beams);
+        if (b == bs1 || b == bs2) c0 = relevant;                   // possibly snapped beam: its direction is not the table's
+        if (b + 1 == bs1 || b + 1 == bs2) c1 = relevant && (b + 1 < n_beams);
+        push(c0, b);
+        push(c1, b + 1);
     }
+    if (n_pend > 0) drain();
 
     if (STEP && lane == 0) {
         int done = 0, info = MNV_INFO_NORMAL;                      // marinenav_env.py:240-257 (Q5)
         const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
         if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
         else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
-        else if (best_d2 < INFINITY && sqrt(best_d2) <= best_r + K.robot_r) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
-        else if (sqrt(fma(x - gx, x - gx, (y - gy) * (y - gy))) <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
+        else if (collides(best_d2, best_r + K.robot_r)) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
+        else if (dis_after <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
         P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
         P.velocity[e] = vx; P.velocity[E + e] = vy;
         P.ep_step[e] = ep + 1;
@@ -694,7 +743,7 @@ int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
 {
     if (K.max_o > 16) {                                            // dense maps: one warp per environment
         const unsigned dgrid = (unsigned)((K.E + kDenseWarps - 1) / kDenseWarps);
-        launch_one(mnv_env_dense_kernel<STEP>, dgrid, kDenseWarps * 32, (size_t)kDenseWarps * K.obs_dim * sizeof(float), st, P, K);
+        launch_one(mnv_env_dense_kernel<STEP>, dgrid, kDenseWarps * 32, (size_t)((kDenseWarps * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)kDenseWarps * 32 * sizeof(unsigned), st, P, K);
         return mnv_launch_status(STEP ? "mnv_step(dense)" : "mnv_observe(dense)");
     }
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
@@ -749,6 +798,7 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
         K.beam_angle[i] = a0 + i * phi;
         K.beam_cos[i] = cos(K.beam_angle[i]); K.beam_sin[i] = sin(K.beam_angle[i]);
         K.beam_dirf[i] = make_float2((float)K.beam_cos[i], (float)K.beam_sin[i]);
+        K.beam_cosf[i] = (float)K.beam_cos[i]; K.beam_sinf[i] = (float)K.beam_sin[i];
     }
     K.snap_t1 = 0.5 * MNV_PI - a0; K.snap_t2 = 1.5 * MNV_PI - a0;      // Q10 pre-test (see the kernel)
     K.inv_phi = (float)(1.0 / phi); K.snap_tol = (float)(1e-3 / phi + 1e-4);
