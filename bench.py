@@ -148,6 +148,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL's version banner goes to stderr)
         dist.init_process_group("nccl", device_id=dev)
     E, K, W = args.envs, args.steps, args.warmup
     W = max(W, 3)                                   # timing rules: at least 3 warm-up steps
