@@ -374,32 +374,56 @@ class IQNAgent:
         obs = train_env.reset().clone()
         losses = []
         next_eval = 0
+        # Two streams: the env stream (act -> fused step -> masked reset + re-observe) and the learner stream (replay append
+        # -> sample -> IQN update), forked right behind the step kernel.  The update does not depend on the reset and the
+        # reset does not depend on the update, so the two halves of a vector step overlap; act waits for the new weights.
+        env_stream = torch.cuda.current_stream(self.device)
+        if getattr(self, "_learn_stream", None) is None:
+            self._learn_stream = torch.cuda.Stream(device=self.device)
+        learn_stream = self._learn_stream
+        ev_step, ev_added, ev_update = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        learn_stream.wait_stream(env_stream)
         while self.current_timestep <= total_timesteps:
             eps = self.linear_eps(total_timesteps)
+            env_stream.wait_event(ev_update)                      # the weights of the last update (no-op before the first)
             action = self.act_batch(obs, eps)
-            _, reward, done, _ = train_env.step(action, auto_reset=True)
-            # buf['next_obs'] keeps the step's own (terminal) observation; buf['obs'] the post-auto-reset one (agent.py:122-124,170)
-            mem.add_batch(obs, action, reward, train_env.buf["next_obs"], done)
-            obs.copy_(train_env.buf["obs"])
+            next_obs, reward, done, _ = train_env.step_begin(action)
+            ev_step.record(env_stream)
             self.current_timestep += E
-            if self.current_timestep >= learning_starts and len(mem) > B:
-                for _ in range(updates_per_step):
-                    s, a, r, s2, d = mem.sample(B)
-                    taus_t = torch.rand(B, 8, device=self.device, generator=self.gen)
-                    taus_l = torch.rand(B, 8, device=self.device, generator=self.gen)
-                    if self.learning_timestep % target_update_interval == 0:
-                        self.soft_update(self.qnetwork_local, self.qnetwork_target)
-                    loss = self.train_async((s.contiguous(), a.contiguous(), r.contiguous(), s2.contiguous(), d.contiguous()),
-                                            (taus_t, taus_l))
-                    self.learning_timestep += 1
-                if verbose and self.learning_timestep % 100 == 0:
-                    losses.append(float(loss.item()))
-                if eval_config is not None and eval_freq and self.learning_timestep >= next_eval:
-                    self.evaluation_vec(eval_config, greedy=True, eval_log_path=eval_log_path)
-                    self.evaluation_vec(eval_config, greedy=False, eval_log_path=eval_log_path)
-                    if eval_log_path is not None:
-                        self.qnetwork_local.save(eval_log_path)
-                    next_eval += eval_freq
+            learn_stream.wait_event(ev_step)
+            action.record_stream(learn_stream)
+            with torch.cuda.stream(learn_stream):
+                # next_obs is the step's own (terminal) observation; the env's obs buffer gets the post-auto-reset one
+                # (agent.py:122-124,170)
+                mem.add_batch(obs, action, reward, next_obs, done)
+                ev_added.record(learn_stream)
+                do_eval = False
+                if self.current_timestep >= learning_starts and len(mem) > B:
+                    for _ in range(updates_per_step):
+                        s, a, r, s2, d = mem.sample(B)
+                        taus_t = torch.rand(B, 8, device=self.device, generator=self.gen)
+                        taus_l = torch.rand(B, 8, device=self.device, generator=self.gen)
+                        if self.learning_timestep % target_update_interval == 0:
+                            self.soft_update(self.qnetwork_local, self.qnetwork_target)
+                        loss = self.train_async((s.contiguous(), a.contiguous(), r.contiguous(), s2.contiguous(), d.contiguous()),
+                                                (taus_t, taus_l))
+                        self.learning_timestep += 1
+                    if verbose and self.learning_timestep % 100 == 0:
+                        losses.append(float(loss.item()))
+                    do_eval = eval_config is not None and eval_freq and self.learning_timestep >= next_eval
+                ev_update.record(learn_stream)
+            train_env.step_finish(auto_reset=True)                # env stream: overlaps the update
+            env_stream.wait_event(ev_added)                       # the replay append has read the previous obs
+            obs.copy_(train_env.buf["obs"])
+            if do_eval:
+                env_stream.wait_event(ev_update)
+                self.evaluation_vec(eval_config, greedy=True, eval_log_path=eval_log_path)
+                self.evaluation_vec(eval_config, greedy=False, eval_log_path=eval_log_path)
+                if eval_log_path is not None:
+                    self.qnetwork_local.save(eval_log_path)
+                next_eval += eval_freq
+                learn_stream.wait_stream(env_stream)
             if on_step is not None:
                 on_step(self)
+        env_stream.wait_stream(learn_stream)
         return losses

@@ -154,10 +154,22 @@ class VecMarineNavEnv:
         With auto_reset (the VecEnv convention) environments that finished are reset and ``obs`` holds the first
         observation of their next episode, while ``self.buf['next_obs']`` keeps the step's own (terminal) observation --
         what IQNAgent.learn stores as next_state before it calls reset() (agent.py:122-124,170)."""
+        self.step_begin(actions, trajectory=trajectory)
+        return self.step_finish(auto_reset=auto_reset)
+
+    def step_begin(self, actions, trajectory=None):
+        """First half of step(): the fused step kernel alone.  buf['next_obs'|'reward'|'done'|'info'] are final when it ends,
+        so a learner may consume them on another stream while step_finish() resets the finished environments."""
         b = self.buf
         with torch.cuda.device(self.device):
             env_ops.step(b, self.params(), action=actions, obs=b["next_obs"], trajectory=trajectory)
-            self.total_timesteps += self.num_envs
+        self.total_timesteps += self.num_envs
+        return b["next_obs"], b["reward"], b["done"], b["info"]
+
+    def step_finish(self, auto_reset=True):
+        """Second half of step(): obs <- next_obs, then (auto_reset) masked reset + re-observe of the finished environments."""
+        b = self.buf
+        with torch.cuda.device(self.device):
             b["obs"].copy_(b["next_obs"])
             if auto_reset:
                 env_ops.reset(b, self.rng_key, self.rng_pos, self.reset_params(), mask=b["done"])
