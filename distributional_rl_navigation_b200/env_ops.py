@@ -25,14 +25,18 @@ def _chk(t, dtype, shape, name):
 def alloc_env_buffers(E, max_c, max_o, n_beams, device):
     """All per-environment arrays of one env batch (layout: include/marinenav_b200.h)."""
     f64 = dict(dtype=torch.float64, device=device)
+    # reward | done | info share ONE allocation (16-byte aligned segments) so that the host boundary ships them with one copy
+    seg = lambda n: (n + 15) // 16 * 16
+    o_done, o_info, n_pack = seg(4 * E), seg(4 * E) + seg(E), seg(4 * E) + 2 * seg(E)
+    pack = torch.zeros(n_pack, dtype=torch.uint8, device=device)
     return dict(
+        rdi_pack=pack, rdi_offsets=torch.tensor([0, o_done, o_info]),
         state=torch.zeros(4, E, **f64), velocity=torch.zeros(2, E, **f64), goal=torch.zeros(2, E, **f64),
         cores=torch.zeros(3 * max_c, E, **f64), obstacles=torch.zeros(3 * max_o, E, **f64),
         start_pose=torch.zeros(4, E, **f64),
         action=torch.zeros(E, dtype=torch.int32, device=device), episode_step=torch.zeros(E, dtype=torch.int32, device=device),
         obs=torch.zeros(E, 4 + 2 * n_beams, dtype=torch.float32, device=device),
-        reward=torch.zeros(E, dtype=torch.float32, device=device),
-        done=torch.zeros(E, dtype=torch.uint8, device=device), info=torch.zeros(E, dtype=torch.uint8, device=device),
+        reward=pack[:4 * E].view(torch.float32), done=pack[o_done:o_done + E], info=pack[o_info:o_info + E],
         n_placed=torch.zeros(2, E, dtype=torch.uint8, device=device),
     )
 

@@ -181,18 +181,20 @@ class VecMarineNavEnv:
         if self._pinned is None:
             E, D = self.num_envs, self.obs_dim
             cap = self.host_patch_capacity = max(1024, E // 16)          # re-observed rows shipped per step (else: full copy)
+            o_r, o_d, o_i = self.buf["rdi_offsets"].tolist()
+            rdi = torch.zeros(self.buf["rdi_pack"].numel(), dtype=torch.uint8).pin_memory()      # reward | done | info: one D2H
+            # count (16 B) | index i32 [cap] | compact f32 [cap, D]: one allocation on each side, one D2H
+            n_patch = 16 + 4 * cap + 4 * cap * D
+            hp = torch.zeros(n_patch, dtype=torch.uint8).pin_memory()
+            views = lambda t: dict(count=t[:4].view(torch.int32), index=t[16:16 + 4 * cap].view(torch.int32),
+                                   compact=t[16 + 4 * cap:].view(torch.float32).view(cap, D))
             self._pinned = dict(action=torch.zeros(E, dtype=torch.int32).pin_memory(),
                                 obs=torch.zeros(E, D, dtype=torch.float32).pin_memory(),
-                                reward=torch.zeros(E, dtype=torch.float32).pin_memory(),
-                                done=torch.zeros(E, dtype=torch.uint8).pin_memory(),
-                                info=torch.zeros(E, dtype=torch.uint8).pin_memory(),
-                                compact=torch.zeros(cap, D, dtype=torch.float32).pin_memory(),
-                                index=torch.zeros(cap, dtype=torch.int32).pin_memory(),
-                                count=torch.zeros(1, dtype=torch.int32).pin_memory())
+                                rdi_pack=rdi, reward=rdi[o_r:o_r + 4 * E].view(torch.float32), done=rdi[o_d:o_d + E],
+                                info=rdi[o_i:o_i + E], patch_pack=hp, **views(hp))
             with torch.cuda.device(self.device):
-                self._dev_patch = dict(compact=torch.zeros(cap, D, dtype=torch.float32, device=self.device),
-                                       index=torch.zeros(cap, dtype=torch.int32, device=self.device),
-                                       count=torch.zeros(1, dtype=torch.int32, device=self.device))
+                dp = torch.zeros(n_patch, dtype=torch.uint8, device=self.device)
+            self._dev_patch = dict(patch_pack=dp, **views(dp))
             self._host_graphs = {}
         return self._pinned
 
@@ -215,8 +217,7 @@ class VecMarineNavEnv:
                 env_ops.step(b, params, action=b["action"], obs=b["next_obs"])
                 sb.wait_stream(sa)
                 with torch.cuda.stream(sb):
-                    pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["reward"].copy_(b["reward"], non_blocking=True)
-                    pin["done"].copy_(b["done"], non_blocking=True); pin["info"].copy_(b["info"], non_blocking=True)
+                    pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["rdi_pack"].copy_(b["rdi_pack"], non_blocking=True)
                 b["obs"].copy_(b["next_obs"])
                 if auto_reset:
                     env_ops.reset(b, self.rng_key, self.rng_pos, rp, mask=b["done"])
@@ -224,8 +225,7 @@ class VecMarineNavEnv:
                     env_ops.gather_rows(b["done"], b["obs"], dp["compact"], dp["index"], dp["count"])
                 sa.wait_stream(sb)
                 if auto_reset:
-                    pin["compact"].copy_(dp["compact"], non_blocking=True); pin["index"].copy_(dp["index"], non_blocking=True)
-                    pin["count"].copy_(dp["count"], non_blocking=True)
+                    pin["patch_pack"].copy_(dp["patch_pack"], non_blocking=True)
         cur.wait_stream(sa)
         return g, (sa, sb)
 
@@ -239,8 +239,7 @@ class VecMarineNavEnv:
             if not graph:
                 self.buf["action"].copy_(pin["action"], non_blocking=True)
                 obs, reward, done, info = self.step(self.buf["action"], auto_reset=auto_reset)
-                pin["obs"].copy_(obs, non_blocking=True); pin["reward"].copy_(reward, non_blocking=True)
-                pin["done"].copy_(done, non_blocking=True); pin["info"].copy_(info, non_blocking=True)
+                pin["obs"].copy_(obs, non_blocking=True); pin["rdi_pack"].copy_(self.buf["rdi_pack"], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
             self.params()
@@ -278,7 +277,7 @@ class VecMarineNavEnv:
 
     def d2h_bytes_per_step(self):
         self._pin()
-        return self.num_envs * (self.obs_dim * 4 + 4 + 1 + 1) + self.host_patch_capacity * (self.obs_dim * 4 + 4) + 4
+        return self.num_envs * self.obs_dim * 4 + self._pinned["rdi_pack"].numel() + self._pinned["patch_pack"].numel()
 
     def close(self):
         pass
