@@ -130,7 +130,7 @@ def main():
         for shp in filter(None, a.shape.split(";")):
             ns, nbm = [int(v) for v in shp.split(",")]
             for E in [int(x) for x in a.envs.split(",")]:
-                us, nb = period_us(E, a.steps, 4, 8, nbm, n_sub=ns)
+                us, nb = period_us(E, a.steps, 4, 32 if a.dense else 8, nbm, n_sub=ns)
                 print(f"   shape n_sub={ns} n_beams={nbm} E={E:7d} period={us:8.2f} us", flush=True)
         for E in [int(x) for x in a.envs.split(",")]:
             us, nb = period_us(E, a.steps, *((4, 32, 64) if a.dense else (4, 8, 11)), drift=a.drift)
