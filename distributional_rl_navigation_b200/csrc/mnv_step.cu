@@ -485,9 +485,14 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Dense maps (BASELINE configs[4]: 32 obstacles x 64 beams, few thousand envs per GPU): ONE WARP PER ENVIRONMENT.
-// A thread-per-env mapping leaves a 16 384-env batch with 3.5 warps per SM and 2 048 serial ray/circle tests per thread;
-// here lane j owns obstacle j (and, in the sub-steps, vortex core j).
+// Dense maps (BASELINE configs[4]: 32 obstacles x 64 beams, few thousand envs per GPU).  A thread-per-env mapping leaves
+// a 16 384-env batch with 3.5 warps per SM and 2 048 serial ray/circle tests per thread; a warp per env makes the sonar
+// parallel but would spend a whole warp on each environment's serial fp64 integration (40 % of the step).  So one CTA
+// (4 warps) owns 8 environments and works in TWO PHASES inside the one launch:
+//   phase 1  warp 0, one LANE per environment (8 lanes busy): loads, sincos, the N sub-steps (same code path as
+//            mnv_env_kernel); the pose after the sub-steps goes to shared memory.  The other warps have their obstacle table
+//            in flight meanwhile; CTAs of different waves are in different phases, so the SM stays busy.
+//   phase 2  every warp takes 2 of the environments in turn, one WARP per environment, lane j owning obstacle j:
 //   * candidate filter: every lane tests its obstacle against TWO beams per FFMA2 (same fp32 test as mnv_env_kernel);
 //   * the exact fp64 tests are not run beam by beam (a beam has ~1.4 candidates, i.e. ~1.4 busy lanes): the candidate
 //     (beam, obstacle) pairs are appended in (beam, obstacle) order to a 32-entry ring in shared memory and evaluated 32
@@ -498,229 +503,263 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 //       p(l) = highest set bit of V below lane l                  the previously recorded hit when the scan reaches l
 //       Bk = ballot(valid_l && p(l) exists && t_l >= t_p(l)) & segment     the scan breaks at the first such l
 //       result = Bk ? p(ffs(Bk)) : highest set bit of V           (the recorded hits form a strictly decreasing run)
+//   * nearest-centre collision test (Q4) = warp arg-min.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDenseWarps = 4;
+constexpr int kDenseEnvs = 8;                                      // environments per CTA (= active lanes of the integrating warp; 4 | 8 | 16 | 32 measured: 69.2 | 68.0 | 73.0 | 83.6 us)
 
-template <bool STEP>
+struct DensePose { double x, y, th, sp, c, s, vx, vy, reward, dis_after, gx, gy; int ep, live, pad0, pad1; };
+
+template <bool STEP, int MAXC>
 __global__ void __launch_bounds__(kDenseWarps * 32)
 mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
-    extern __shared__ __align__(16) float s_obs[];                 // [kDenseWarps][obs_dim] floats, then [kDenseWarps][32] ring words
+    extern __shared__ __align__(16) unsigned char s_raw[];        // [kDenseEnvs] DensePose | [kDenseWarps][obs_dim] floats | [kDenseWarps][32] ring words
     pdl_wait();                                                    // everything below reads what earlier launches wrote
     pdl_launch_dependents();
     const long long E = K.E;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long e = (long long)blockIdx.x * kDenseWarps + w;
+    const long long e0 = (long long)blockIdx.x * kDenseEnvs;
     const int D = K.obs_dim;
-    float* my_obs = s_obs + w * D;
-    unsigned* ring = reinterpret_cast<unsigned*>(s_obs + ((kDenseWarps * D + 3) & ~3)) + w * 32;
-    if (e >= E) return;                                            // warp-uniform
-    if (!STEP && P.mask != nullptr && P.mask[e] == 0) return;
+    DensePose* s_pose = reinterpret_cast<DensePose*>(s_raw);
+    float* my_obs = reinterpret_cast<float*>(s_pose + kDenseEnvs) + w * D;
+    unsigned* ring = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(s_pose + kDenseEnvs) + ((kDenseWarps * D + 3) & ~3)) + w * 32;
+    const int max_o = K.max_o;
 
-    // ---- all loads first: one DRAM round trip ----
-    double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
-    const double gx = P.goal[e], gy = P.goal[E + e];
-    int action = 0, ep = 0;
-    if (STEP) { action = P.action[e]; ep = P.ep_step[e]; }
-    // lane i < max_c owns vortex core i (k = Gs / 2pi carries the spin in its sign)
-    double cx = 0.0, cy = 0.0, ck = 0.0;
-    if (lane < K.max_c) {
-        cx = __ldg(P.cores + (long long)lane * E + e);
-        cy = __ldg(P.cores + (long long)(K.max_c + lane) * E + e);
-        ck = __ldg(P.cores + (long long)(2 * K.max_c + lane) * E + e);
-    }
-    // lane j < max_o owns obstacle j
-    double ox = 0.0, oy = 0.0, orad = -1.0;
-    if (lane < K.max_o) {
-        ox = __ldg(P.obst + (long long)lane * E + e);
-        oy = __ldg(P.obst + (long long)(K.max_o + lane) * E + e);
-        orad = __ldg(P.obst + (long long)(2 * K.max_o + lane) * E + e);
-    }
-    double c, s;
-    sincos(th, &s, &c);
-    ck *= (1.0 / (2.0 * MNV_PI));
-    double vx, vy, reward = 0.0, dis_after = 0.0;
-    auto current = [&](double px, double py, double& ux, double& uy) {
-        const double dx = cx - px, dy = cy - py;
-        const double d2 = fma(dx, dx, dy * dy);
-        const double f = ck * (d2 <= K.core_r2 ? K.inv_core_r2 : fast_rcp(d2 > 0.0 ? d2 : 1.0));   // empty lanes: ck = 0
-        ux = -dy * f; uy = dx * f;
-#pragma unroll
-        for (int off = 4; off > 0; off >>= 1) {                    // sum over the (<= 8) core lanes, every lane gets the total
-            ux += __shfl_xor_sync(0xffffffffu, ux, off);
-            uy += __shfl_xor_sync(0xffffffffu, uy, off);
+    // this warp's environments in phase 2: w, w + kDenseWarps, ...; lane j < max_o owns obstacle j
+    auto load_obstacle = [&](long long e, double& ox, double& oy, double& orad) {
+        ox = 0.0; oy = 0.0; orad = -1.0;
+        if (e < E && lane < max_o) {
+            ox = __ldg(P.obst + (long long)lane * E + e);
+            oy = __ldg(P.obst + (long long)(max_o + lane) * E + e);
+            orad = __ldg(P.obst + (long long)(2 * max_o + lane) * E + e);
         }
-        ux = __shfl_sync(0xffffffffu, ux, 0); uy = __shfl_sync(0xffffffffu, uy, 0);   // lanes 8..31 hold zeros: take group 0
     };
+    double nox, noy, norad;                                        // obstacle table of the next environment of this warp (prefetch)
+    load_obstacle(e0 + w, nox, noy, norad);
 
-    if (STEP) {
-        const int ai = action / 3, wi = action - 3 * ai;
-        const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
-        const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
-        vx = 0.0; vy = 0.0;
-        for (int it = 0; it < K.n_substeps; ++it) {
-            double ux, uy;
-            current(x, y, ux, uy);
-            vx = fma(sp, c, ux); vy = fma(sp, s, uy);              // robot.py:98-100 (Q6)
-            x = fma(vx, K.dt, x); y = fma(vy, K.dt, y);            // robot.py:105-107
-            sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
-            sp = sp < 0.0 ? 0.0 : sp;                              // robot.py:114
-            sp = sp > K.max_speed ? K.max_speed : sp;
-            th = __dadd_rn(th, wdt);                               // robot.py:117
-            th = th < 0.0 ? __dadd_rn(th, 2.0 * MNV_PI) : th;      // robot.py:120-123 (see mnv_env_kernel)
-            th = th >= 2.0 * MNV_PI ? __dsub_rn(th, 2.0 * MNV_PI) : th;
-            if (th < 0.0 || th >= 2.0 * MNV_PI) {
-#pragma unroll 1
-                while (th < 0.0) th += 2.0 * MNV_PI;
-#pragma unroll 1
-                while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+    // ================= phase 1: warp 0, one lane per environment =================
+    if (w == 0) {
+        const long long e = e0 + lane;
+        const bool live = (lane < kDenseEnvs) && (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
+        DensePose ps;
+        ps.live = live ? 1 : 0; ps.ep = 0;
+        ps.x = ps.y = ps.th = ps.sp = ps.vx = ps.vy = ps.reward = ps.dis_after = ps.gx = ps.gy = 0.0; ps.c = 1.0; ps.s = 0.0;
+        if (live) {
+            double x = P.state[e], y = P.state[E + e], th = P.state[2 * E + e], sp = P.state[3 * E + e];
+            const double gx = P.goal[e], gy = P.goal[E + e];
+            int action = 0, ep = 0;
+            if (STEP) { action = P.action[e]; ep = P.ep_step[e]; }
+            double cx[MAXC], cy[MAXC], ck[MAXC];
+            {
+                const double* pc = P.cores + e;
+                const long long rowstride = (long long)K.max_c * E;
+#pragma unroll
+                for (int i = 0; i < MAXC; ++i) {
+                    if (i < K.max_c) { cx[i] = __ldg(pc); cy[i] = __ldg(pc + rowstride); ck[i] = __ldg(pc + 2 * rowstride); }
+                    else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
+                    pc += E;
+                }
             }
-            const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
-            c = c2; s = s2;
-            if (P.traj != nullptr && lane == 0) {
-                P.traj[(long long)(2 * it) * E + e] = x; P.traj[(long long)(2 * it + 1) * E + e] = y;
+            double c, s;
+            sincos(th, &s, &c);
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) ck[i] *= (1.0 / (2.0 * MNV_PI));
+            auto current = [&](double px, double py, double& ux, double& uy) {
+                ux = 0.0; uy = 0.0;
+#pragma unroll
+                for (int i = 0; i < MAXC; ++i) {
+                    const double dx = cx[i] - px, dy = cy[i] - py;
+                    const double d2 = fma(dx, dx, dy * dy);
+                    const double f = ck[i] * (d2 <= K.core_r2 ? K.inv_core_r2 : fast_rcp(d2));   // marinenav_env.py:461-465
+                    ux = fma(-dy, f, ux);
+                    uy = fma(dx, f, uy);
+                }
+            };
+            double vx = 0.0, vy = 0.0, reward = 0.0, dis_after = 0.0;
+            if (STEP) {
+                const int ai = action / 3, wi = action - 3 * ai;
+                const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
+                const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+                for (int it = 0; it < K.n_substeps; ++it) {
+                    double ux, uy;
+                    current(x, y, ux, uy);
+                    vx = fma(sp, c, ux); vy = fma(sp, s, uy);              // robot.py:98-100 (Q6)
+                    x = fma(vx, K.dt, x); y = fma(vy, K.dt, y);            // robot.py:105-107
+                    sp = __dadd_rn(sp, __dmul_rn(__dsub_rn(acc, __dmul_rn(K.k_drag, sp)), K.dt));   // robot.py:113
+                    sp = sp < 0.0 ? 0.0 : sp;                              // robot.py:114
+                    sp = sp > K.max_speed ? K.max_speed : sp;
+                    th = __dadd_rn(th, wdt);                               // robot.py:117
+                    th = th < 0.0 ? __dadd_rn(th, 2.0 * MNV_PI) : th;      // robot.py:120-123 (see mnv_env_kernel)
+                    th = th >= 2.0 * MNV_PI ? __dsub_rn(th, 2.0 * MNV_PI) : th;
+                    if (th < 0.0 || th >= 2.0 * MNV_PI) {
+#pragma unroll 1
+                        while (th < 0.0) th += 2.0 * MNV_PI;
+#pragma unroll 1
+                        while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                    }
+                    const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
+                    c = c2; s = s2;
+                    if (P.traj != nullptr) { P.traj[(long long)(2 * it) * E + e] = x; P.traj[(long long)(2 * it + 1) * E + e] = y; }
+                }
+                dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+                reward = K.pen_step + (dis_before - dis_after);            // marinenav_env.py:220,229
+            } else {
+                if (K.velocity_from_state) {
+                    double ux, uy;
+                    current(x, y, ux, uy);
+                    vx = fma(sp, c, ux); vy = fma(sp, s, uy);
+                    P.velocity[e] = vx; P.velocity[E + e] = vy;
+                } else { vx = P.velocity[e]; vy = P.velocity[E + e]; }
             }
+            ps.x = x; ps.y = y; ps.th = th; ps.sp = sp; ps.c = c; ps.s = s; ps.vx = vx; ps.vy = vy;
+            ps.reward = reward; ps.dis_after = dis_after; ps.gx = gx; ps.gy = gy; ps.ep = ep;
         }
-        dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
-        reward = K.pen_step + (dis_before - dis_after);            // marinenav_env.py:220,229
-    } else {
-        if (K.velocity_from_state) {
-            double ux, uy;
-            current(x, y, ux, uy);
-            vx = fma(sp, c, ux); vy = fma(sp, s, uy);
-            if (lane == 0) { P.velocity[e] = vx; P.velocity[E + e] = vy; }
-        } else { vx = P.velocity[e]; vy = P.velocity[E + e]; }
+        if (lane < kDenseEnvs) s_pose[lane] = ps;
     }
+    __syncthreads();
 
+    // ================= phase 2: one warp per environment =================
     const int n_beams = K.n_beams;
-    if (lane == 0) {                                               // observation head (marinenav_env.py:278-293)
-        my_obs[0] = (float)fma(c, vx, s * vy);
-        my_obs[1] = (float)fma(c, vy, -s * vx);
-        my_obs[2] = (float)fma(c, gx - x, s * (gy - y));
-        my_obs[3] = (float)fma(c, gy - y, -s * (gx - x));
-    }
-    for (int b = lane; b < n_beams; b += 32)                       // "no return" everywhere (marinenav_env.py:318-320); hits overwrite
-        *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);
-
-    // ---- my obstacle in the robot frame ----
-    const bool on = orad > 0.0;
-    const double dxo = ox - x, dyo = oy - y;
-    const double d2o = fma(dxo, dxo, dyo * dyo);
-    const double qx = fma(c, dxo, s * dyo), qy = fma(c, dyo, -s * dxo), rr = orad * orad;
-    const double lim = K.range_slack + orad;
-    const bool relevant = on && d2o <= lim * lim;                  // reachable within the sonar range at all
-    const bool borderline = relevant && fabs(d2o - rr) <= 1e-9 * rr;   // robot on the circle: never filter
-    // fp32 filter operands: sigma q (inside the circle the nearer root is in front iff tc <= 0), -(r^2 + 1e-3);
-    // "always a candidate" = q = 0 with a very negative nr, "never" = nr = +1e30
-    const float sg = d2o < rr ? -1.f : 1.f;
-    const float qxf = borderline ? 0.f : sg * (float)qx, qyf = borderline ? 0.f : sg * (float)qy;
-    const float nrf = !relevant ? 1e30f : (borderline ? -1e30f : -((float)rr + 1e-3f));
-    const f32x2 qx2 = pack2(qxf, qxf), qy2 = pack2(qyf, qyf), nqx2 = pack2(-qxf, -qxf), nr2 = pack2(nrf, nrf);
-    const f32x2 margin2 = pack2(1e-3f, 1e-3f);
-
-    // ---- Q4: collision against the nearest CENTRE only (marinenav_env.py:329-336): warp arg-min ----
-    double best_d2 = on ? d2o : INFINITY, best_r = orad;
-    int best_i = lane;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, best_d2, off), orr = __shfl_xor_sync(0xffffffffu, best_r, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-        // ties: the lowest obstacle index wins, like the first minimum of a sequential scan
-        if (od < best_d2 || (od == best_d2 && oi < best_i)) { best_d2 = od; best_r = orr; best_i = oi; }
-    }
-
-    // ---- Q10 pre-test (see mnv_env_kernel): the only beams that can be snapped to the vertical ----
-    int bs1, bs2;
-    {
-        const float u1 = (float)(K.snap_t1 - th) * K.inv_phi, u2 = (float)(K.snap_t2 - th) * K.inv_phi;
-        const float n1 = rintf(u1), n2 = rintf(u2);
-        bs1 = fabsf(u1 - n1) < K.snap_tol ? (int)n1 : -1;
-        bs2 = fabsf(u2 - n2) < K.snap_tol ? (int)n2 : -1;
-    }
-
-    // ---- sonar ----
     const unsigned lt_mask = (1u << lane) - 1u;
-    int n_pend = 0;                                                // warp-uniform
-    auto drain = [&]() {
-        __syncwarp();
-        const bool mine = lane < n_pend;
-        const unsigned ent = mine ? ring[lane] : 0u;               // [4:0] obstacle (owner lane), [12:5] beam
-        const int j = ent & 31, bb = ent >> 5;
-        const double oqx = __shfl_sync(0xffffffffu, qx, j), oqy = __shfl_sync(0xffffffffu, qy, j), orr2 = __shfl_sync(0xffffffffu, rr, j);
-        bool valid = false;
-        double t = 0.0, bx = 0.0, by = 0.0;
-        if (mine) {                                                // exact fp64 decision (robot.py:164-190)
-            bx = K.beam_cos[bb]; by = K.beam_sin[bb];
-            if (bb == bs1 || bb == bs2) {
-                const double ang = th + K.beam_angle[bb];          // robot.py:131 (not wrapped)
-                if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }             // Q10
-                else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }
-            }
-            const double tc = fma(oqx, bx, oqy * by), cr = fma(oqx, by, -oqy * bx);
-            const double disc = fma(-cr, cr, orr2);
-            if (disc >= 0.0) {
-                const double h = sqrt(disc);
-                t = tc > 0.0 ? tc - h : tc + h;                    // nearer root first (robot.py:184)
-                valid = (t <= K.range) && (t >= 0.0);
-            }
-        }
-        // ordered scan per beam = per segment of equal beam index (entries are in (beam, obstacle) order)
-        const unsigned seg = __match_any_sync(0xffffffffu, mine ? bb : 0x1000 + lane);
-        const unsigned V = __ballot_sync(0xffffffffu, valid) & seg;
-        const unsigned below = V & lt_mask;
-        const int pj = below ? 31 - __clz(below) : -1;             // previous valid hit of my beam in list order
-        const double tp = __shfl_sync(0xffffffffu, t, pj < 0 ? 0 : pj);
-        const unsigned Bk = __ballot_sync(0xffffffffu, valid && pj >= 0 && t >= tp) & seg;
-        const int f = Bk ? __ffs(Bk) - 1 : 0;
-        const int pf = __shfl_sync(0xffffffffu, pj, f);            // predecessor of the first breaking lane (>= 0 when Bk != 0)
-        const int res = Bk ? pf : (V ? 31 - __clz(V) : -1);
-        if (mine && lane == res)                                   // marinenav_env.py:314-317
-            *reinterpret_cast<float2*>(my_obs + 4 + 2 * bb) = make_float2((float)(t * bx), (float)(t * by));
-        n_pend = 0;
-        __syncwarp();
-    };
-    auto push = [&](bool cand, int b) {
-        const unsigned bal = __ballot_sync(0xffffffffu, cand);
-        if (bal == 0u) return;
-        const int cnt = __popc(bal);
-        if (n_pend + cnt > 32) drain();                            // a batch only holds complete beams (cnt <= 32)
-        if (cand) ring[n_pend + __popc(bal & lt_mask)] = (unsigned)lane | ((unsigned)b << 5);
-        n_pend += cnt;
-    };
-    for (int b = 0; b < n_beams; b += 2) {
-        // conservative fp32 filter (see mnv_env_kernel), two beams per FFMA2: cr^2 - r^2 - 1e-3 < 0 and tc + 1e-3 >= 0
-        const f32x2 bx2 = *reinterpret_cast<const f32x2*>(&K.beam_cosf[b]), by2 = *reinterpret_cast<const f32x2*>(&K.beam_sinf[b]);
-        const f32x2 tc = fma2(qx2, bx2, fma2(qy2, by2, margin2));
-        const f32x2 ncr = fma2(qy2, bx2, mul2(nqx2, by2));
-        const f32x2 nd = fma2(ncr, ncr, nr2);
-        unsigned t0, t1, d0, d1;
-        unpack2(tc, t0, t1); unpack2(nd, d0, d1);
-        bool c0 = (int)(d0 & ~t0) < 0, c1 = (int)(d1 & ~t1) < 0 && (b + 1 < n_beams);
-        if (b == bs1 || b == bs2) c0 = relevant;                   // possibly snapped beam: its direction is not the table's
-        if (b + 1 == bs1 || b + 1 == bs2) c1 = relevant && (b + 1 < n_beams);
-        push(c0, b);
-        push(c1, b + 1);
-    }
-    if (n_pend > 0) drain();
+    for (int el = w; el < kDenseEnvs; el += kDenseWarps) {
+        const long long e = e0 + el;
+        const double ox = nox, oy = noy, orad = norad;
+        load_obstacle(e + kDenseWarps < e0 + kDenseEnvs ? e + kDenseWarps : E, nox, noy, norad);   // prefetch the next one
+        const DensePose& ps = s_pose[el];
+        if (!ps.live) continue;                                    // warp-uniform
+        const double x = ps.x, y = ps.y, th = ps.th, c = ps.c, s = ps.s;
 
-    if (STEP && lane == 0) {
-        int done = 0, info = MNV_INFO_NORMAL;                      // marinenav_env.py:240-257 (Q5)
-        const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
-        if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
-        else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
-        else if (collides(best_d2, best_r + K.robot_r)) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
-        else if (dis_after <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
-        P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
-        P.velocity[e] = vx; P.velocity[E + e] = vy;
-        P.ep_step[e] = ep + 1;
-        P.reward[e] = (float)reward;
-        P.done[e] = (uint8_t)done;
-        P.info[e] = (uint8_t)info;
+        if (lane == 0) {                                           // observation head (marinenav_env.py:278-293)
+            my_obs[0] = (float)fma(c, ps.vx, s * ps.vy);
+            my_obs[1] = (float)fma(c, ps.vy, -s * ps.vx);
+            my_obs[2] = (float)fma(c, ps.gx - x, s * (ps.gy - y));
+            my_obs[3] = (float)fma(c, ps.gy - y, -s * (ps.gx - x));
+        }
+        for (int b = lane; b < n_beams; b += 32)                   // "no return" everywhere (marinenav_env.py:318-320); hits overwrite
+            *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);
+
+        // ---- my obstacle in the robot frame ----
+        const bool on = orad > 0.0;
+        const double dxo = ox - x, dyo = oy - y;
+        const double d2o = fma(dxo, dxo, dyo * dyo);
+        const double qx = fma(c, dxo, s * dyo), qy = fma(c, dyo, -s * dxo), rr = orad * orad;
+        const double lim = K.range_slack + orad;
+        const bool relevant = on && d2o <= lim * lim;              // reachable within the sonar range at all
+        const bool borderline = relevant && fabs(d2o - rr) <= 1e-9 * rr;   // robot on the circle: never filter
+        // fp32 filter operands: sigma q (inside the circle the nearer root is in front iff tc <= 0), -(r^2 + 1e-3);
+        // "always a candidate" = q = 0 with a very negative nr, "never" = nr = +1e30
+        const float sg = d2o < rr ? -1.f : 1.f;
+        const float qxf = borderline ? 0.f : sg * (float)qx, qyf = borderline ? 0.f : sg * (float)qy;
+        const float nrf = !relevant ? 1e30f : (borderline ? -1e30f : -((float)rr + 1e-3f));
+        const f32x2 qx2 = pack2(qxf, qxf), qy2 = pack2(qyf, qyf), nqx2 = pack2(-qxf, -qxf), nr2 = pack2(nrf, nrf);
+        const f32x2 margin2 = pack2(1e-3f, 1e-3f);
+
+        // ---- Q4: collision against the nearest CENTRE only (marinenav_env.py:329-336): warp arg-min ----
+        double best_d2 = on ? d2o : INFINITY, best_r = orad;
+        int best_i = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, best_d2, off), orr = __shfl_xor_sync(0xffffffffu, best_r, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+            // ties: the lowest obstacle index wins, like the first minimum of a sequential scan
+            if (od < best_d2 || (od == best_d2 && oi < best_i)) { best_d2 = od; best_r = orr; best_i = oi; }
+        }
+
+        // ---- Q10 pre-test (see mnv_env_kernel): the only beams that can be snapped to the vertical ----
+        int bs1, bs2;
+        {
+            const float u1 = (float)(K.snap_t1 - th) * K.inv_phi, u2 = (float)(K.snap_t2 - th) * K.inv_phi;
+            const float n1 = rintf(u1), n2 = rintf(u2);
+            bs1 = fabsf(u1 - n1) < K.snap_tol ? (int)n1 : -1;
+            bs2 = fabsf(u2 - n2) < K.snap_tol ? (int)n2 : -1;
+        }
+
+        // ---- sonar ----
+        int n_pend = 0;                                            // warp-uniform
+        auto drain = [&]() {
+            __syncwarp();
+            const bool mine = lane < n_pend;
+            const unsigned ent = mine ? ring[lane] : 0u;           // [4:0] obstacle (owner lane), [12:5] beam
+            const int j = ent & 31, bb = ent >> 5;
+            const double oqx = __shfl_sync(0xffffffffu, qx, j), oqy = __shfl_sync(0xffffffffu, qy, j), orr2 = __shfl_sync(0xffffffffu, rr, j);
+            bool valid = false;
+            double t = 0.0, bx = 0.0, by = 0.0;
+            if (mine) {                                            // exact fp64 decision (robot.py:164-190)
+                bx = K.beam_cos[bb]; by = K.beam_sin[bb];
+                if (bb == bs1 || bb == bs2) {
+                    const double ang = th + K.beam_angle[bb];      // robot.py:131 (not wrapped)
+                    if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = s; by = c; }             // Q10
+                    else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -s; by = -c; }
+                }
+                const double tc = fma(oqx, bx, oqy * by), cr = fma(oqx, by, -oqy * bx);
+                const double disc = fma(-cr, cr, orr2);
+                if (disc >= 0.0) {
+                    const double h = sqrt(disc);
+                    t = tc > 0.0 ? tc - h : tc + h;                // nearer root first (robot.py:184)
+                    valid = (t <= K.range) && (t >= 0.0);
+                }
+            }
+            // ordered scan per beam = per segment of equal beam index (entries are in (beam, obstacle) order)
+            const unsigned seg = __match_any_sync(0xffffffffu, mine ? bb : 0x1000 + lane);
+            const unsigned V = __ballot_sync(0xffffffffu, valid) & seg;
+            const unsigned below = V & lt_mask;
+            const int pj = below ? 31 - __clz(below) : -1;         // previous valid hit of my beam in list order
+            const double tp = __shfl_sync(0xffffffffu, t, pj < 0 ? 0 : pj);
+            const unsigned Bk = __ballot_sync(0xffffffffu, valid && pj >= 0 && t >= tp) & seg;
+            const int f = Bk ? __ffs(Bk) - 1 : 0;
+            const int pf = __shfl_sync(0xffffffffu, pj, f);        // predecessor of the first breaking lane (>= 0 when Bk != 0)
+            const int res = Bk ? pf : (V ? 31 - __clz(V) : -1);
+            if (mine && lane == res)                               // marinenav_env.py:314-317
+                *reinterpret_cast<float2*>(my_obs + 4 + 2 * bb) = make_float2((float)(t * bx), (float)(t * by));
+            n_pend = 0;
+            __syncwarp();
+        };
+        auto push = [&](bool cand, int b) {
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (bal == 0u) return;
+            const int cnt = __popc(bal);
+            if (n_pend + cnt > 32) drain();                        // a batch only holds complete beams (cnt <= 32)
+            if (cand) ring[n_pend + __popc(bal & lt_mask)] = (unsigned)lane | ((unsigned)b << 5);
+            n_pend += cnt;
+        };
+        for (int b = 0; b < n_beams; b += 2) {
+            // conservative fp32 filter (see mnv_env_kernel), two beams per FFMA2: cr^2 - r^2 - 1e-3 < 0 and tc + 1e-3 >= 0
+            const f32x2 bx2 = *reinterpret_cast<const f32x2*>(&K.beam_cosf[b]), by2 = *reinterpret_cast<const f32x2*>(&K.beam_sinf[b]);
+            const f32x2 tc = fma2(qx2, bx2, fma2(qy2, by2, margin2));
+            const f32x2 ncr = fma2(qy2, bx2, mul2(nqx2, by2));
+            const f32x2 nd = fma2(ncr, ncr, nr2);
+            unsigned t0, t1, d0, d1;
+            unpack2(tc, t0, t1); unpack2(nd, d0, d1);
+            bool c0 = (int)(d0 & ~t0) < 0, c1 = (int)(d1 & ~t1) < 0 && (b + 1 < n_beams);
+            if (b == bs1 || b == bs2) c0 = relevant;               // possibly snapped beam: its direction is not the table's
+            if (b + 1 == bs1 || b + 1 == bs2) c1 = relevant && (b + 1 < n_beams);
+            push(c0, b);
+            push(c1, b + 1);
+        }
+        if (n_pend > 0) drain();
+
+        if (STEP && lane == 0) {
+            double reward = ps.reward;
+            int done = 0, info = MNV_INFO_NORMAL;                  // marinenav_env.py:240-257 (Q5)
+            const bool oob = (x < 0.0 || x > K.width) || (y < 0.0 || y > K.height);
+            if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
+            else if (ps.ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
+            else if (collides(best_d2, best_r + K.robot_r)) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
+            else if (ps.dis_after <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
+            P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = ps.sp;
+            P.velocity[e] = ps.vx; P.velocity[E + e] = ps.vy;
+            P.ep_step[e] = ps.ep + 1;
+            P.reward[e] = (float)reward;
+            P.done[e] = (uint8_t)done;
+            P.info[e] = (uint8_t)info;
+        }
+        __syncwarp();
+        float* dst = P.obs + e * D;                                // 8-byte aligned rows (D even): float2 stores
+        for (int i = lane; i < (D >> 1); i += 32)
+            reinterpret_cast<float2*>(dst)[i] = reinterpret_cast<const float2*>(my_obs)[i];
+        __syncwarp();                                              // the row buffer is reused by this warp's next environment
     }
-    __syncwarp();
-    float* dst = P.obs + e * D;                                    // 8-byte aligned rows (D even): float2 stores
-    for (int i = lane; i < (D >> 1); i += 32)
-        reinterpret_cast<float2*>(dst)[i] = reinterpret_cast<const float2*>(my_obs)[i];
 }
 
 // One launch, optionally with programmatic stream serialization (PDL): the kernels call griddepcontrol.launch_dependents
@@ -742,8 +781,11 @@ template <bool STEP>
 int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
 {
     if (K.max_o > 16) {                                            // dense maps: one warp per environment
-        const unsigned dgrid = (unsigned)((K.E + kDenseWarps - 1) / kDenseWarps);
-        launch_one(mnv_env_dense_kernel<STEP>, dgrid, kDenseWarps * 32, (size_t)((kDenseWarps * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)kDenseWarps * 32 * sizeof(unsigned), st, P, K);
+        const unsigned dgrid = (unsigned)((K.E + kDenseEnvs - 1) / kDenseEnvs);
+        const size_t dsmem = (size_t)kDenseEnvs * sizeof(DensePose) + (size_t)((kDenseWarps * K.obs_dim + 3) & ~3) * sizeof(float) +
+                             (size_t)kDenseWarps * 32 * sizeof(unsigned);
+        if (K.max_c <= 4) launch_one(mnv_env_dense_kernel<STEP, 4>, dgrid, kDenseWarps * 32, dsmem, st, P, K);
+        else launch_one(mnv_env_dense_kernel<STEP, 8>, dgrid, kDenseWarps * 32, dsmem, st, P, K);
         return mnv_launch_status(STEP ? "mnv_step(dense)" : "mnv_observe(dense)");
     }
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
