@@ -13,7 +13,7 @@
 //     as bf16 K-major core-matrix tiles (pre-packed by iqn_pack_tc, 73 KB);
 //   * A operands are produced in-kernel and written straight into the same UMMA canonical layout (no swizzle):
 //       A0 = cos(pi i tau)            (rotation recurrence from one sincospif per row)
-//       A1 = relu(D1 + b_c) * feat    A2 = relu(D2 + b_1)    A3 = relu(D3 + b_2)
+//       A1 = bf16(relu(D1 + b_c)) * bf16(feat)    A2 = relu(D2 + b_1)    A3 = relu(D3 + b_2)     (cvt.rn.relu.bf16x2 + mul.bf16x2)
 //   * one elected thread issues tcgen05.mma (M = 128, N = 208 / 64 / 64 / 16, K = 16 per instruction), accumulators in
 //     TMEM (208 + 64 + 64 + 16 columns), completion through tcgen05.commit -> mbarrier;
 //   * epilogues read TMEM with tcgen05.ld.32x32b (thread = row), apply bias / relu / the feature product, convert to
@@ -44,7 +44,7 @@ struct __align__(128) GroupSmem {
     // ONE operand region per group: A0 (cos features, 16 KB) is consumed by layer 1 before the first epilogue overwrites
     // the region with A1 (52 KB); A2 / A3 (16 KB each) are written after layers 2 / 3 have consumed A1 / A2.
     __nv_bfloat16 a1[kRows * kK1];
-    float feat[kEnvsPerTile * kFeat];
+    __nv_bfloat16 feat[kEnvsPerTile * kFeat];            // observation-encoder output, bf16 (it only ever multiplies a bf16 operand)
     float x[kEnvsPerTile * 28];
     float tau[kRows];
     unsigned long long bar;
@@ -137,6 +137,31 @@ __device__ __forceinline__ void store_chunk(__nv_bfloat16* base, int r, int kc, 
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
     u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8, K)) = u;
+}
+
+// relu + round to bf16 of two accumulator columns in ONE instruction (cvt.rn.relu.bf16x2.f32: upper half <- a, lower half <- b)
+__device__ __forceinline__ uint32_t relu_pack(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// one 8-column chunk of the next layer's A operand: relu(v) in bf16 (x feat in bf16 when f != nullptr), 16-byte store
+__device__ __forceinline__ void store_relu_chunk(__nv_bfloat16* base, int r, int kc, int K, const float* v, const __nv_bfloat16* f)
+{
+    uint4 u;
+    u.x = relu_pack(v[0], v[1]); u.y = relu_pack(v[2], v[3]); u.z = relu_pack(v[4], v[5]); u.w = relu_pack(v[6], v[7]);
+    if (f != nullptr) {
+        const uint4 fv = *reinterpret_cast<const uint4*>(f);           // 8 bf16 features, 16-byte aligned
+        u.x = mul_bf16x2(u.x, fv.x); u.y = mul_bf16x2(u.y, fv.y); u.z = mul_bf16x2(u.z, fv.z); u.w = mul_bf16x2(u.w, fv.w);
+    }
     *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8, K)) = u;
 }
 
@@ -233,7 +258,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
 #pragma unroll
                 for (int k = 0; k < 22; ++k) v = fmaf(s.enc[oSW + q * 22 + k], x[4 + k], v);
             }
-            gs.feat[idx] = v;
+            gs.feat[idx] = __float2bfloat16_rn(v);
         }
         // ---- A0 = cos(pi * i * tau), i = 0..63: thread (row, half) fills i in [32 half, 32 half + 32) by rotating
         //      (cos, sin)(i pi tau) with (cos, sin)(pi tau), starting from an exact sincospif at i = 32 half ----
@@ -270,7 +295,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
         tc_fence_after();
         {
             // this warp's 104 columns [104 half, 104 half + 104) = 3 x 32 + 8
-            const float* feat = gs.feat + (row / kTaus) * kFeat;
+            const __nv_bfloat16* feat = gs.feat + (row / kTaus) * kFeat;
             const int c0 = half * 104;
 #pragma unroll 1
             for (int blk = 0; blk < 3; ++blk) {
@@ -280,14 +305,8 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                 if (debug != nullptr && tile == 0)
                     for (int j = 0; j < 32; ++j) debug[row * kFeat + col + j] = v[j];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float u[8];
-                    const float4 f0 = *reinterpret_cast<const float4*>(feat + col + q * 8), f1 = *reinterpret_cast<const float4*>(feat + col + q * 8 + 4);
-                    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j], 0.f) * fv[j];   // model.py:177-180 (bias already in D1)
-                    store_chunk(gs.a1, row, (col >> 3) + q, kK1, u);
-                }
+                for (int q = 0; q < 4; ++q)                       // model.py:177-180 (bias already in D1): relu(D1) * feat, bf16 x bf16
+                    store_relu_chunk(gs.a1, row, (col >> 3) + q, kK1, v + q * 8, feat + col + q * 8);
             }
             {
                 float v[8];
@@ -295,9 +314,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                 tmem_ld8(tmem + lane_base + kD1 + col, v);
                 if (debug != nullptr && tile == 0)
                     for (int j = 0; j < 8; ++j) debug[row * kFeat + col + j] = v[j];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f) * feat[col + j];
-                store_chunk(gs.a1, row, col >> 3, kK1, v);
+                store_relu_chunk(gs.a1, row, col >> 3, kK1, v, feat + col);
             }
             if (half == 1) store_bias_step(gs.a1, row, kFeat / 8, kK1);
         }
@@ -321,12 +338,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
             if (debug != nullptr && tile == 0)
                 for (int j = 0; j < 32; ++j) debug[kRows * kFeat + row * kHid + col + j] = v[j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float u[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j], 0.f);
-                store_chunk(gs.a1, row, (col >> 3) + q, kK2, u);           // A2 over the (consumed) A1
-            }
+            for (int q = 0; q < 4; ++q) store_relu_chunk(gs.a1, row, (col >> 3) + q, kK2, v + q * 8, nullptr);   // A2 over the (consumed) A1
             if (half == 0) store_bias_step(gs.a1, row, kHid / 8, kK2);
         }
         fence_async_smem();
@@ -349,12 +361,7 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
             if (debug != nullptr && tile == 0)
                 for (int j = 0; j < 32; ++j) debug[kRows * (kFeat + kHid) + row * kHid + col + j] = v[j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float u[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = fmaxf(v[q * 8 + j], 0.f);
-                store_chunk(gs.a1, row, (col >> 3) + q, kK3, u);           // A3 over the (consumed) A2
-            }
+            for (int q = 0; q < 4; ++q) store_relu_chunk(gs.a1, row, (col >> 3) + q, kK3, v + q * 8, nullptr);   // A3 over the (consumed) A2
             if (half == 0) store_bias_step(gs.a1, row, kHid / 8, kK3);
         }
         fence_async_smem();

@@ -34,7 +34,7 @@ def emulate(P, x, taus, cvar=1.0):
     cos = np.cos(np.pi * np.arange(64)[None, None, :] * t[:, :, None].astype(np.float64)).astype(np.float32).reshape(B * K, 64)
     # the biases ride inside the GEMMs as one extra reduction column (bf16-rounded like the weights)
     d1 = bf(cos) @ bf(P["cos_embedding.weight"]).T + bf(P["cos_embedding.bias"])
-    h0 = np.maximum(d1, 0) * np.repeat(feat, K, axis=0)
+    h0 = bf(np.maximum(d1, 0)) * bf(np.repeat(feat, K, axis=0))       # relu -> bf16, bf16 features, bf16 product (mul.bf16x2)
     d2 = bf(h0) @ bf(P["hidden_layer.weight"]).T + bf(P["hidden_layer.bias"])
     d3 = bf(np.maximum(d2, 0)) @ bf(P["hidden_layer_2.weight"]).T + bf(P["hidden_layer_2.bias"])
     d4 = bf(np.maximum(d3, 0)) @ bf(P["output_layer.weight"]).T + bf(P["output_layer.bias"])
