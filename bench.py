@@ -80,6 +80,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep a private handle to the real stdout and point fd 1 at stderr, so that
+    library chatter (e.g. NCCL's version banner, printed with printf from C) cannot land in front of it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -129,7 +148,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -148,7 +167,6 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL's version banner goes to stderr)
         dist.init_process_group("nccl", device_id=dev)
     E, K, W = args.envs, args.steps, args.warmup
     W = max(W, 3)                                   # timing rules: at least 3 warm-up steps
@@ -295,7 +313,7 @@ def run_b200(args):
             line["dense"] = dense
         if iqn is not None:
             line["iqn"] = iqn
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -476,6 +494,7 @@ def main():
     ap.add_argument("--mix", type=int, default=200, help="auto-reset steps per env batch between the preload and the timed region")
     ap.add_argument("--preload", type=float, default=1.0, help="seconds of untimed identical load before the timed region (clock sampling)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         if args.steps > 50:
             args.steps = 50
