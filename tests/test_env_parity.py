@@ -129,7 +129,8 @@ def test_observe_masked_leaves_other_rows(golden_dir):
 
 @pytest.mark.parametrize("E,nc,no,n_beams,max_c,max_o", [
     (1, 4, 8, 11, 4, 8), (63, 4, 8, 11, 4, 8), (4097, 8, 10, 11, 8, 10), (65536, 4, 8, 11, 4, 8),
-    (3000, 0, 0, 11, 4, 8), (2048, 4, 16, 21, 8, 16), (16384, 4, 32, 64, 4, 32), (1023, 8, 20, 33, 8, 24), (5, 0, 3, 7, 1, 17)])
+    (3000, 0, 0, 11, 4, 8), (2048, 4, 16, 21, 8, 16), (16384, 4, 32, 64, 4, 32), (1023, 8, 20, 33, 8, 24), (5, 0, 3, 7, 1, 17),
+    (700, 8, 16, 128, 8, 16), (600, 8, 32, 128, 8, 32)])     # compiled capacities: 8 cores, 16 / 32 obstacles, 128 beams
 def test_step_vs_oracle_teacher_forced(E, nc, no, n_beams, max_c, max_o):
     """Seeded maps from the oracle's reset, random actions, every step compared from identical pre-states."""
     op = mo.default_params(n_beams)
