@@ -86,3 +86,14 @@ def test_product_never_imports_oracle():
                     text = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports oracle"
                     assert "marinenav_oracle" not in text, f"{f} references the oracle"
+
+
+def test_bench_algorithmic_bytes_match_survey_table():
+    """490 B per env-step at C2 (8 obstacles, 4 cores, 11 beams, fp64 tables), 1490 B at C5 (32 / 4 / 64)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.algorithmic_bytes_per_env_step(4, 8, 11, 8) == 490
+    assert bench.algorithmic_bytes_per_env_step(4, 32, 64, 8) == 1490
+    assert bench.algorithmic_bytes_per_env_step(4, 8, 11, 4) == 306
