@@ -188,7 +188,8 @@ class VecMarineNavEnv:
             hp = torch.zeros(n_patch, dtype=torch.uint8).pin_memory()
             views = lambda t: dict(count=t[:4].view(torch.int32), index=t[16:16 + 4 * cap].view(torch.int32),
                                    compact=t[16 + 4 * cap:].view(torch.float32).view(cap, D))
-            self._pinned = dict(action=torch.zeros(E, dtype=torch.int32).pin_memory(),
+            act = torch.zeros(E, dtype=torch.int32).pin_memory()
+            self._pinned = dict(action=act, action_np=act.numpy(),
                                 obs=torch.zeros(E, D, dtype=torch.float32).pin_memory(),
                                 rdi_pack=rdi, reward=rdi[o_r:o_r + 4 * E].view(torch.float32), done=rdi[o_d:o_d + E],
                                 info=rdi[o_i:o_i + E], patch_pack=hp, **views(hp))
@@ -234,7 +235,7 @@ class VecMarineNavEnv:
         (valid until the next call).  obs holds the first observation of the next episode for finished environments, like
         step().  graph=False runs the same operations eagerly on one stream (the parity reference of the graph path)."""
         pin = self._pin()
-        pin["action"].copy_(torch.as_tensor(actions, dtype=torch.int32))
+        np.copyto(pin["action_np"], np.asarray(actions), casting="unsafe")       # 9 us; torch's CPU copy_ costs 14 - 500 us here
         with torch.cuda.device(self.device):
             if not graph:
                 self.buf["action"].copy_(pin["action"], non_blocking=True)
