@@ -18,7 +18,7 @@ INFO_STRINGS = _lib.INFO_STRINGS
 
 class VecMarineNavEnv:
     def __init__(self, num_envs, seed=0, schedule=None, device="cuda:0", num_cores=8, num_obs=5, min_start_goal_dis=25.0,
-                 num_beams=11, max_cores=None, max_obstacles=None):
+                 num_beams=11, max_cores=None, max_obstacles=None, pdl_prefetch=True):
         if not torch.cuda.is_available():
             raise _lib.MarinenavError("VecMarineNavEnv needs a CUDA device (there is no CPU fallback)")
         _lib.load()
@@ -26,7 +26,8 @@ class VecMarineNavEnv:
         # launch before it on the stream still drains (include/marinenav_b200.h).  Its contract -- the launch right before
         # mnv_step does not write those tables -- holds for every sequence of this class: mnv_reset is always followed by
         # mnv_observe, table uploads are host copies, and tables_written() fences device-side edits (the facade's setters).
-        if os.environ.get("MNV_PDL") is None and _lib.get_option("pdl") == 0:
+        # pdl_prefetch=False (or MNV_PDL in the environment) leaves the process-wide switch alone.
+        if pdl_prefetch and os.environ.get("MNV_PDL") is None and _lib.get_option("pdl") == 0:
             _lib.set_option("pdl", 2)
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
