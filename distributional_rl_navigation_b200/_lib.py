@@ -52,7 +52,7 @@ _SIGNATURES = {
     "mnv_observe": (C.c_int, [_vp] * 7 + [_i64, _i32, _i32, C.POINTER(MnvParams), _i32, _vp]),
     "mnv_seed": (C.c_int, [_vp] * 3 + [_i64, _vp]),
     "mnv_reset": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, C.POINTER(MnvResetParams), _vp]),
-    "mnv_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mnv_scatter_rows_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "iqn_param_count": (C.c_int, []),
     "iqn_packed_count": (C.c_int, []),
     "iqn_pack": (C.c_int, [_vp, _vp, _vp]),

@@ -97,12 +97,11 @@ def reset(buf, rng_key, rng_pos, reset_params, mask=None):
     _lib.check(rc, "mnv_reset")
 
 
-def gather_rows(mask, rows, compact, index, count):
-    """Rows of `rows` (f32 [E, D]) where mask != 0 -> compact[:n], their env indices -> index[:n], n (total) -> count[0]."""
+def scatter_rows_host(mask, rows, host_rows):
+    """host_rows[e] <- rows[e] for every e with mask[e] != 0; host_rows is a PINNED CPU tensor (device-mapped under UVA)."""
     E, D = rows.shape
     _chk(mask, torch.uint8, (E,), "mask"); _chk(rows, torch.float32, (E, D), "rows")
-    cap = compact.shape[0]
-    _chk(compact, torch.float32, (cap, D), "compact"); _chk(index, torch.int32, (cap,), "index"); _chk(count, torch.int32, (1,), "count")
-    rc = _lib.load().mnv_gather_rows(_lib.ptr(mask), _lib.ptr(rows), E, D, cap, _lib.ptr(compact), _lib.ptr(index),
-                                     _lib.ptr(count), _stream())
-    _lib.check(rc, "mnv_gather_rows")
+    if not (host_rows.is_pinned() and host_rows.dtype == torch.float32 and host_rows.is_contiguous() and tuple(host_rows.shape) == (E, D)):
+        raise _lib.MarinenavError(f"host_rows: expected a pinned contiguous float32 CPU tensor {(E, D)}")
+    rc = _lib.load().mnv_scatter_rows_host(_lib.ptr(mask), _lib.ptr(rows), _lib.ptr(host_rows), E, D, _stream())
+    _lib.check(rc, "mnv_scatter_rows_host")

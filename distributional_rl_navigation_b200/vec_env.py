@@ -181,32 +181,24 @@ class VecMarineNavEnv:
     def _pin(self):
         if self._pinned is None:
             E, D = self.num_envs, self.obs_dim
-            cap = self.host_patch_capacity = max(1024, E // 16)          # re-observed rows shipped per step (else: full copy)
             o_r, o_d, o_i = self.buf["rdi_offsets"].tolist()
             rdi = torch.zeros(self.buf["rdi_pack"].numel(), dtype=torch.uint8).pin_memory()      # reward | done | info: one D2H
-            # count (16 B) | index i32 [cap] | compact f32 [cap, D]: one allocation on each side, one D2H
-            n_patch = 16 + 4 * cap + 4 * cap * D
-            hp = torch.zeros(n_patch, dtype=torch.uint8).pin_memory()
-            views = lambda t: dict(count=t[:4].view(torch.int32), index=t[16:16 + 4 * cap].view(torch.int32),
-                                   compact=t[16 + 4 * cap:].view(torch.float32).view(cap, D))
             act = torch.zeros(E, dtype=torch.int32).pin_memory()
             self._pinned = dict(action=act, action_np=act.numpy(),
                                 obs=torch.zeros(E, D, dtype=torch.float32).pin_memory(),
                                 rdi_pack=rdi, reward=rdi[o_r:o_r + 4 * E].view(torch.float32), done=rdi[o_d:o_d + E],
-                                info=rdi[o_i:o_i + E], patch_pack=hp, **views(hp))
-            with torch.cuda.device(self.device):
-                dp = torch.zeros(n_patch, dtype=torch.uint8, device=self.device)
-            self._dev_patch = dict(patch_pack=dp, **views(dp))
+                                info=rdi[o_i:o_i + E])
             self._host_graphs = {}
         return self._pinned
 
     def _capture_host_step(self, auto_reset):
         """One CUDA graph for the whole host-boundary step.  Stream A: H2D actions -> fused step -> (auto-reset: masked
-        reset -> masked re-observe -> compaction of the re-observed rows) ; stream B, forked right behind the step kernel:
-        D2H of the step's own observation block, reward, done, info (everything the host needs except the rows of the
-        environments that were reset).  A joins B and ships the compact row list.  The 7 MB D2H -- the longest item of the
-        step -- runs under the reset instead of after it, and the host pays one graph launch instead of ~12 launches."""
-        pin, b, dp = self._pin(), self.buf, self._dev_patch
+        reset -> masked re-observe); stream B, forked right behind the step kernel: D2H of the step's own observation block
+        and of reward | done | info (everything the host needs except the rows of the environments that were reset).  A
+        joins B and overwrites the rows of the re-observed environments directly in the pinned host array
+        (mnv_scatter_rows_host, zero-copy stores).  The 7 MB D2H -- the longest item of the step -- runs under the reset
+        instead of after it, the host pays one graph launch instead of ~12 launches and does no patching."""
+        pin, b = self._pin(), self.buf
         params = self.params()
         rp = self.reset_params() if auto_reset else None
         cur = torch.cuda.current_stream()
@@ -224,10 +216,9 @@ class VecMarineNavEnv:
                 if auto_reset:
                     env_ops.reset(b, self.rng_key, self.rng_pos, rp, mask=b["done"])
                     env_ops.observe(b, params, mask=b["done"], velocity_from_state=True)
-                    env_ops.gather_rows(b["done"], b["obs"], dp["compact"], dp["index"], dp["count"])
                 sa.wait_stream(sb)
                 if auto_reset:
-                    pin["patch_pack"].copy_(dp["patch_pack"], non_blocking=True)
+                    env_ops.scatter_rows_host(b["done"], b["obs"], pin["obs"])      # after the bulk copy has written those rows
         cur.wait_stream(sa)
         return g, (sa, sb)
 
@@ -255,14 +246,7 @@ class VecMarineNavEnv:
             entry[0].replay()
             self.total_timesteps += self.num_envs
             torch.cuda.current_stream().synchronize()
-            obs = pin["obs"].numpy()
-            if auto_reset:
-                n = int(pin["count"][0])
-                if n > self.host_patch_capacity:                  # rare: more episodes ended than the patch list holds
-                    pin["obs"].copy_(self.buf["obs"])
-                elif n > 0:
-                    obs[pin["index"].numpy()[:n]] = pin["compact"].numpy()[:n]
-        return obs, pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
+        return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
 
     def tables_written(self):
         """Call after writing buf['goal'|'cores'|'obstacles'] with a device-side kernel (e.g. indexed assignment) if a step
@@ -279,7 +263,8 @@ class VecMarineNavEnv:
 
     def d2h_bytes_per_step(self):
         self._pin()
-        return self.num_envs * self.obs_dim * 4 + self._pinned["rdi_pack"].numel() + self._pinned["patch_pack"].numel()
+        # bulk copies; the zero-copy rows of the re-observed environments (a few hundred x obs_dim x 4 bytes) come on top
+        return self.num_envs * self.obs_dim * 4 + self._pinned["rdi_pack"].numel()
 
     def close(self):
         pass

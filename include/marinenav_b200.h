@@ -125,12 +125,12 @@ int mnv_reset(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint8_t* d_mask,
               int64_t E, int32_t max_c, int32_t max_o, const mnv_reset_params* rp, void* stream);
 
 /* Host-boundary helper of the vectorised env (no counterpart in the reference, which steps ONE env and returns numpy):
- * compacts the rows d_rows[e][0:row_len] (f32, row-major, e.g. the observations) of every environment with d_mask[e] != 0
- * into d_compact[k][0:row_len], k < min(count, cap), writes their environment indices to d_index[k] (order between
- * warps is arbitrary, rows and indices agree) and the TOTAL number of selected environments to d_count (may exceed cap:
- * the caller then falls back to a full copy).  One memset node + one kernel on `stream`. */
-int mnv_gather_rows(const uint8_t* d_mask, const float* d_rows, int64_t E, int32_t row_len, int32_t cap,
-                    float* d_compact, int32_t* d_index, int32_t* d_count, void* stream);
+ * copies the rows d_rows[e][0:row_len] (f32, row-major, e.g. the observations) of every environment with d_mask[e] != 0
+ * to the same rows of h_rows_mapped, a pinned host array that is mapped into the device address space (cudaHostAlloc /
+ * torch pin_memory(); under UVA its host address is its device address).  Zero-copy stores: after the launch has completed
+ * (stream synchronisation) the host sees the rows.  One kernel on `stream`. */
+int mnv_scatter_rows_host(const uint8_t* d_mask, const float* d_rows, float* h_rows_mapped, int64_t E, int32_t row_len,
+                          void* stream);
 
 /* ======================================= IQN (thirdparty/IQN) ============================================
  * Parameters: ONE flat fp32 vector of iqn_param_count() = 35 785 floats = the 14 tensors of ObsEncoder.state_dict() in

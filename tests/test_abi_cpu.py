@@ -69,11 +69,11 @@ def test_kernel_options_roundtrip(lib):
     assert b"unknown key" in lib.mnv_last_error_string()
 
 
-def test_gather_rows_argument_errors(lib):
+def test_scatter_rows_host_argument_errors(lib):
     ok = C.c_void_p(4096)
-    assert lib.mnv_gather_rows(None, ok, 16, 26, 4, ok, ok, ok, None) == -1
-    assert lib.mnv_gather_rows(ok, ok, 0, 26, 4, ok, ok, ok, None) == -3
-    assert lib.mnv_gather_rows(ok, C.c_void_p(4100), 16, 26, 4, ok, ok, ok, None) == -2
+    assert lib.mnv_scatter_rows_host(None, ok, ok, 16, 26, None) == -1
+    assert lib.mnv_scatter_rows_host(ok, ok, ok, 0, 26, None) == -3
+    assert lib.mnv_scatter_rows_host(ok, C.c_void_p(4100), ok, 16, 26, None) == -2
 
 
 def test_product_never_imports_oracle():
