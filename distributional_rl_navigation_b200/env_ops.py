@@ -48,7 +48,11 @@ def step(buf, params, action=None, obs=None, trajectory=None):
     action = buf["action"] if action is None else action
     obs = buf["obs"] if obs is None else obs
     _chk(buf["state"], torch.float64, (4, E), "state"); _chk(buf["velocity"], torch.float64, (2, E), "velocity")
-    _chk(buf["goal"], torch.float64, (2, E), "goal"); _chk(action, torch.int32, (E,), "action")
+    _chk(buf["goal"], torch.float64, (2, E), "goal")
+    if action.is_cuda or not action.is_pinned():      # a PINNED host tensor is fine too: the kernel reads it zero-copy (UVA)
+        _chk(action, torch.int32, (E,), "action")
+    elif action.dtype != torch.int32 or tuple(action.shape) != (E,) or not action.is_contiguous():
+        raise _lib.MarinenavError("action: expected a contiguous int32 tensor of shape (E,)")
     _chk(buf["episode_step"], torch.int32, (E,), "episode_step")
     _chk(obs, torch.float32, (E, 4 + 2 * params.n_beams), "obs")
     if trajectory is not None:

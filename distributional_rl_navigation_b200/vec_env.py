@@ -192,7 +192,7 @@ class VecMarineNavEnv:
         return self._pinned
 
     def _capture_host_step(self, auto_reset):
-        """One CUDA graph for the whole host-boundary step.  Stream A: H2D actions -> fused step -> (auto-reset: masked
+        """One CUDA graph for the whole host-boundary step.  Stream A: fused step (actions read zero-copy from the pinned host buffer) -> (auto-reset: masked
         reset -> masked re-observe); stream B, forked right behind the step kernel: D2H of the step's own observation block
         and of reward | done | info (everything the host needs except the rows of the environments that were reset).  A
         joins B and overwrites the rows of the re-observed environments directly in the pinned host array
@@ -207,8 +207,7 @@ class VecMarineNavEnv:
         sa.wait_stream(cur)
         with torch.cuda.stream(sa):
             with torch.cuda.graph(g, stream=sa):
-                b["action"].copy_(pin["action"], non_blocking=True)
-                env_ops.step(b, params, action=b["action"], obs=b["next_obs"])
+                env_ops.step(b, params, action=pin["action"], obs=b["next_obs"])    # actions read zero-copy from the pinned buffer
                 sb.wait_stream(sa)
                 with torch.cuda.stream(sb):
                     pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["rdi_pack"].copy_(b["rdi_pack"], non_blocking=True)
