@@ -26,12 +26,26 @@ N_CORES, N_OBS, N_BEAMS = 4, 8, 11
 ENVS_PER_GPU = 65536
 N_BATCHES = 8
 NCU_DRAM_BYTES_PER_LAUNCH = 22.587e6     # measured, profiles/r1_step_kernel_v5_ncu_full.csv (algorithmic read volume: 22.5 MB)
+NCU_WARP_INST_PER_LAUNCH = 6.69e6        # smsp__inst_executed.sum of the same capture
+NCU_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                      "(profiles/r1_step_kernel_v5_ncu_full.csv); the 9.6 MB of writes were still in L2 when the profiled launch ended")
 
 
 def algorithmic_bytes_per_env_step(n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS, s=8):
     """SURVEY.md 8(d): read = s*(4 state + 2 goal + 3 n_o + 3 n_c) + 4 (timestep) + 4 (action);
     write = s*4 + 4 + 4*(4 + 2 n_b) + 4 (reward) + 2 (done, info).  fp64 tables -> s = 8 -> 490 B at C2."""
     return s * (4 + 2 + 3 * n_o + 3 * n_c) + 8 + (s * 4 + 4 + 4 * (4 + 2 * n_b) + 4 + 2)
+
+
+def bench_config(E, world):
+    """The workload description; BOTH arms (--impl b200 / reference) print exactly this dict as `config`."""
+    abytes = algorithmic_bytes_per_env_step()
+    return {"workload": "marinenav fused env step (MarineNavEnv.step), 65536 envs/GPU, 8 obstacles / 4 vortex cores / "
+                        "11 beams, random actions (BASELINE configs[1])",
+            "envs_per_gpu": E,
+            "l2": f"rotating {N_BATCHES} env batches ({N_BATCHES * E * abytes / 1e6:.0f} MB > 126 MB L2), one batch per step",
+            "auto_reset": "in e2e only; every batch is reset and mixed with auto-reset steps right before the timed region",
+            "parallelism": f"env-sharded x{world}, no collective in step"}
 
 
 def measured_peak_hbm():
@@ -121,30 +135,66 @@ def cpu_port_steps_per_s(n_envs, n_steps, n_threads, seed0=0):
     return n_envs * n_steps / dt, dt
 
 
+def cpu_baseline_leg(E, cores):
+    """`cpu_baseline` of the B200 arm (rank 0, N = 1): the reference's own Python step() on all host cores (one process per
+    core, staged in oracle/_ref) when available, with the C port beside it; bounded sample (~10-20 s of CPU work)."""
+    from oracle import ref_timing
+    port_v, port_dt = cpu_port_steps_per_s(E, 40, cores)
+    port1_v, _ = cpu_port_steps_per_s(E, 20, 1)
+    if not ref_timing.available():
+        return {"value": port_v, "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": port1_v,
+                "sample": f"{E} envs x 40 steps of the same workload, oracle/marinenav_oracle.c ({port_dt:.1f} s on {cores} threads); "
+                          "oracle/_ref (the staged Python reference) is absent"}
+    per = 1200
+    ref_v, ref_dt = ref_timing.env_steps_per_s(cores, per, n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS)
+    ref1_v, _ = ref_timing.env_steps_per_s(1, per, n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS)
+    return {"value": ref_v, "unit": UNIT, "cores": cores, "kind": "reference", "value_1_core": ref1_v,
+            "sample": f"{cores} processes x {per} MarineNavEnv.step calls (unmodified marinenav_env.py:199 staged in oracle/_ref, same map "
+                      f"rules / random actions, reset on done; {ref_dt:.1f} s), and 1 process alone",
+            "port": {"value": port_v, "value_1_thread": port1_v, "cores": cores,
+                     "sample": f"{E} envs x 40 steps, oracle/marinenav_oracle.c (C restatement, {port_dt:.1f} s on {cores} threads)"}}
+
+
+def params_pdl(p):
+    return bool(getattr(p, "pdl_prefetch", 0))
+
+
 def run_reference(args):
-    """--impl reference: the reference is pure Python and cannot travel to the GPU box, so this arm times the oracle
-    port (C restatement of MarineNavEnv.step, all host threads) on the same workload; each 'step' is a bounded sample."""
+    """--impl reference: the reference's OWN CPU implementation of the path on the box's host cores.  When oracle/_ref
+    (the staged, unmodified Python files: oracle/stage_ref.py) is present, P = cpu_count worker processes each step one
+    MarineNavEnv (marinenav_env.py:199) -- kind "reference"; otherwise the C restatement on all host threads -- kind "port".
+    Each timed step is a bounded sample of the 65 536-env workload (the Python reference needs ~10 s for one full step)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
+    from oracle import ref_timing
     cores = os.cpu_count() or 1
-    sample_envs = 16384
-    per_step = []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_port_steps_per_s(sample_envs, 1, cores, seed0=i)
-        if i >= args.warmup:
-            per_step.append((v, dt))
-    total = sum(sample_envs / v for v, _ in per_step)
-    value = sample_envs * len(per_step) / total
+    K, W = args.steps, args.warmup
+    port_v, _ = cpu_port_steps_per_s(ENVS_PER_GPU, 5, cores)                # the C port beside it, same envs per step as the GPU arm
+    if ref_timing.available():
+        per = 96                                                             # env steps per worker per timed step (~0.3 s)
+        durs = ref_timing.env_segments(cores, W + K, per, N_CORES, N_OBS, N_BEAMS)
+        seg = [max(d[i] for d in durs) for i in range(W, W + K)]             # a step ends when the slowest worker is done
+        total = sum(seg)
+        value = cores * per * K / total
+        kind, sample = "reference", (f"{cores} worker processes x {per} MarineNavEnv.step calls per timed step (unmodified "
+                                     f"marinenav_env.py / robot.py staged in oracle/_ref, reset on done); C port of the same "
+                                     f"path on {cores} threads at 65536 envs per step: {port_v:.3e} env-steps/s")
+    else:
+        seg = []
+        for i in range(W + K):
+            v, dt = cpu_port_steps_per_s(ENVS_PER_GPU, 1, cores, seed0=i)
+            if i >= W:
+                seg.append(dt)
+        total = sum(seg)
+        value = ENVS_PER_GPU * K / total
+        kind, sample = "port", f"{ENVS_PER_GPU} envs x 1 step per timed step, oracle/marinenav_oracle.c on {cores} threads (oracle/_ref absent)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "marinenav fused env step, 8 obstacles / 4 vortex cores / 11 beams (BASELINE configs[1])",
-                   "envs_per_step_sample": sample_envs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample_envs} envs x 1 step per timed step, oracle/marinenav_oracle.c on {cores} threads "
-                                   "(the Python reference itself: 330-385 steps/s/core, SURVEY.md section 6)"},
+        "config": bench_config(ENVS_PER_GPU, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "port_value": port_v},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,32 +245,38 @@ def run_b200(args):
     for i in range(W):
         one_step(i)
     barrier()
-    # The step kernel lasts ~10 us, less than a Python-side launch: capture CHUNK consecutive steps (CHUNK launches of
-    # mnv_step through the C-ABI on the capturing stream) in a CUDA graph and replay it, so the timed region is
-    # back-to-back kernels.  K = n_rep * CHUNK + rem; the remainder is launched eagerly.
-    chunk = min(K, 8 * N_BATCHES)
-    chunk -= chunk % N_BATCHES if chunk >= N_BATCHES else 0
+    # The step kernel lasts ~10 us, less than a Python-side launch, so the timed region consists of CUDA-graph replays ONLY:
+    # one graph holds REPS x K consecutive mnv_step launches (through the C-ABI on the capturing stream; REPS chosen so that
+    # a graph is >= 256 launches and a whole number of batch rotations), and it is replayed N_REPLAY times back to back with
+    # an event after every replay, so that the region lasts >= 25 ms.  ms_per_step = median replay / (REPS x K).
+    reps = max(1, -(-256 // K))
+    while (reps * K) % N_BATCHES != 0 and reps < 4096:
+        reps += 1
+    n_launch = reps * K
     graph = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         with torch.cuda.graph(graph, stream=side):
-            for i in range(chunk):
+            for i in range(n_launch):
                 one_step(W + i)
     torch.cuda.current_stream().wait_stream(side)
-    n_rep, rem = K // chunk, K % chunk
     stream = torch.cuda.current_stream()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph.replay(); torch.cuda.synchronize()
+    c0.record(stream); graph.replay(); c1.record(stream); torch.cuda.synchronize()
+    n_replay = int(min(400, max(5, -(-25.0 // c0.elapsed_time(c1)))))
 
-    def timed_region():
-        for _ in range(n_rep):
+    def timed_region(evs=None):
+        for r in range(n_replay):
             graph.replay()
-        for i in range(rem):
-            one_step(W + i)
+            if evs is not None:
+                evs[r + 1].record(stream)
 
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_replay + 1)]
     with ClockSampler(local_rank) as clk:
         # ~1 s of the same kernels right before the timed region so that nvidia-smi sees the clocks under THIS load
-        # (the timed region itself may last only milliseconds); clocks are sampled across both.
+        # (the timed region itself lasts tens of milliseconds); clocks are sampled across both.
         t_pre = time.perf_counter()
         while time.perf_counter() - t_pre < args.preload:
             timed_region()
@@ -228,7 +284,7 @@ def run_b200(args):
         # The untimed preload above ran tens of thousands of steps without resets, so the robots have long left their
         # maps.  Put every batch back into the stationary rollout distribution (fresh maps, then MIX auto-reset steps of the
         # random policy: episodes in every phase, finished ones re-drawn) right before the timed region; the timed region
-        # itself then steps each batch K / N_BATCHES times without resets.
+        # itself then steps each batch n_launch x n_replay / N_BATCHES times without resets.
         for bi, env in enumerate(batches):
             env.reset()
             for i in range(args.mix):
@@ -236,31 +292,60 @@ def run_b200(args):
         for i in range(N_BATCHES):                   # caches / instruction memory warm again after the reset kernels
             one_step(W + i)
         barrier()
-        ev0.record(stream)
-        timed_region()
-        ev1.record(stream)
+        evs[0].record(stream)
+        timed_region(evs)
         barrier()
-        ms_total = ev0.elapsed_time(ev1)
-    times = [ms_total]
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        per_replay = sorted(evs[r].elapsed_time(evs[r + 1]) for r in range(n_replay))
+        ms_region = evs[0].elapsed_time(evs[n_replay])
+    ms_median = per_replay[len(per_replay) // 2]
+    t = torch.tensor([ms_median / n_launch, ms_region / (n_launch * n_replay)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / K
+    ms_per_step, ms_per_step_mean = float(t[0].item()), float(t[1].item())
     value = world * E / (ms_per_step * 1e-3)
 
-    # ---- e2e: public API with HOST buffers (H2D actions, D2H obs/reward/done/info, auto-reset) every step ----
+    # ---- device-resident rollout step: fused step + masked reset + masked re-observe of the finished environments
+    #      (VecMarineNavEnv.step(auto_reset=True)), one batch, CUDA graph of 16 steps ----
     env0 = batches[0]
+    env0.reset()
+    for i in range(args.mix):
+        env0.step(actions[i % actions.shape[0]], auto_reset=True)
+    g_ar = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g_ar, stream=side):
+            for i in range(16):
+                env0.step(actions[i % actions.shape[0]], auto_reset=True)
+    torch.cuda.current_stream().wait_stream(side)
+    g_ar.replay(); torch.cuda.synchronize()
+    n_ar = 12
+    ar = [torch.cuda.Event(enable_timing=True) for _ in range(n_ar + 1)]
+    ar[0].record(stream)
+    for r in range(n_ar):
+        g_ar.replay(); ar[r + 1].record(stream)
+    barrier()
+    ar_ms = sorted(ar[r].elapsed_time(ar[r + 1]) / 16 for r in range(n_ar))[n_ar // 2]
+    ta = torch.tensor([ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+    ar_ms = float(ta.item())
+    finished_frac = float(env0.buf["done"].float().mean().item())
+
+    # ---- e2e: public API with HOST buffers (H2D actions, D2H obs/reward/done/info, auto-reset) every step: K steps per
+    #      repetition, repeated until >= ~0.1 s, median repetition ----
     host_actions = np.random.RandomState(7 + rank).randint(0, 9, size=(W + K, E)).astype(np.int32)
     for i in range(W):
         env0.step_host(host_actions[i])
     barrier()
-    t0 = time.perf_counter()
-    for i in range(W, W + K):
-        obs, rew, done, info = env0.step_host(host_actions[i])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    e2e_reps, e2e_times, t_all = 0, [], time.perf_counter()
+    while e2e_reps < 3 or (time.perf_counter() - t_all < 0.15 and e2e_reps < 200):
+        t0 = time.perf_counter()
+        for i in range(W, W + K):
+            obs, rew, done, info = env0.step_host(host_actions[i])
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+        e2e_reps += 1
+    te = torch.tensor([sorted(e2e_times)[len(e2e_times) // 2]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * K / float(te.item())
@@ -277,38 +362,40 @@ def run_b200(args):
         abytes = algorithmic_bytes_per_env_step()
         achieved = E * abytes / (ms_per_step * 1e-3) / 1e9
         cpu_cores = os.cpu_count() or 1
-        cpu_v, cpu_dt = cpu_port_steps_per_s(E, 40, cpu_cores) if world == 1 else (None, None)
-        cpu1_v, _ = cpu_port_steps_per_s(E, 20, 1) if world == 1 else (None, None)
+        cfg = bench_config(E, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "marinenav fused env step (mnv_step), 65536 envs/GPU, 8 obstacles / 4 vortex cores / "
-                                   "11 beams, random actions (BASELINE configs[1])",
-                       "envs_per_gpu": E, "l2": f"rotating {N_BATCHES} env batches ({N_BATCHES * E * abytes / 1e6:.0f} MB "
-                                                "> 126 MB L2), one batch per step",
-                       "auto_reset": "in e2e only; every batch is reset and mixed with %d auto-reset steps right before the timed region" % args.mix, "parallelism": f"env-sharded x{world}, no collective in step",
-                       "launch": f"CUDA graph of {chunk} mnv_step launches x {n_rep} replays + {rem} eager; launch mode pdl={_lib.get_option('pdl')} "
-                                 "(VecMarineNavEnv default 2: programmatic dependent launch, map tables fetched ahead of the grid dependency)",
-                       "timed_region_ms": round(times[0], 4)},
+            "config": cfg,
+            "timing": {"launch": f"timed region = {n_replay} replays of ONE CUDA graph of {n_launch} mnv_step launches ({reps} x steps={K}), "
+                                 f"no eager launches; an event after every replay; ms_per_step = median replay / {n_launch}; "
+                                 f"launch mode pdl={'2 (per call)' if params_pdl(params) else _lib.get_option('pdl')} "
+                                 "(programmatic dependent launch, map tables fetched ahead of the grid dependency)",
+                       "timed_region_ms": round(ms_region, 4), "ms_per_step_mean": ms_per_step_mean,
+                       "ms_per_step_min": per_replay[0] / n_launch, "ms_per_step_max": per_replay[-1] / n_launch,
+                       "mix_steps": args.mix},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E == ENVS_PER_GPU else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                           "(profiles/r1_step_kernel_v5_ncu_full.csv); the 9.6 MB of writes were still in L2 "
-                                           "when the profiled launch ended", "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
-                         "kernel": "mnv_env_kernel<4,8,true>"},
+                         "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
+                         "kernel": "mnv_env_kernel<4,8,true,true>",
+                         "issue_bound": {"warp_instructions_per_launch": NCU_WARP_INST_PER_LAUNCH,
+                                         "floor_us_at_1_ipc_per_scheduler": NCU_WARP_INST_PER_LAUNCH / (148 * 4) / 1.965e3,
+                                         "frac": NCU_WARP_INST_PER_LAUNCH / (148 * 4) / 1.965e3 / (ms_per_step * 1e3) if E == ENVS_PER_GPU else None,
+                                         "note": "second roofline (SURVEY 8d): warp instructions of one launch (ncu smsp__inst_executed.sum) "
+                                                 "/ (592 schedulers x 1.965 GHz) / measured time"}},
+            "device_step_auto_reset": {"ms_per_step": ar_ms, "env_steps_per_s": world * E / (ar_ms * 1e-3),
+                                       "finished_fraction_last_step": finished_frac,
+                                       "what": "VecMarineNavEnv.step(auto_reset=True) device-resident: mnv_step + obs copy + masked mnv_reset + "
+                                               "masked mnv_observe, CUDA graph of 16 steps, median of 12 replays"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env0.h2d_bytes_per_step() * world,
                     "d2h_bytes_per_step": env0.d2h_bytes_per_step() * world, "checksum": checksum,
-                    "api": "VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step)"},
-            "gpu_launches": K,
+                    "repetitions": e2e_reps, "api": env0.host_api_description()},
+            "gpu_launches": n_launch * n_replay,
             "clocks": clk.summary(),
         }
-        if cpu_v is not None:
-            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cpu_cores, "kind": "port",
-                                    "value_1_thread": cpu1_v,
-                                    "sample": f"{E} envs x 40 steps of the same workload, oracle/marinenav_oracle.c "
-                                              f"({cpu_dt:.1f} s on {cpu_cores} threads; the Python reference itself: "
-                                              "330-385 steps/s/core, SURVEY.md section 6)"}
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg(E, cpu_cores)
         if dense is not None:
             line["dense"] = dense
         if iqn is not None:
@@ -476,9 +563,21 @@ def iqn_bench(args, dev, world):
         t0 = time.perf_counter(); n = 0
         while time.perf_counter() - t0 < 5.0:
             io.loss_and_grad(P, P, xs, a_, r_, x2, d_, t1, t2); n += 1
-        out["cpu_baseline_updates_per_s"] = {"value": n / (time.perf_counter() - t0), "kind": "port", "cores": os.cpu_count(),
-                                             "sample": f"{n} updates of batch 1024, oracle/iqn_oracle.py (numpy/BLAS); the PyTorch "
-                                                       "reference: 242 updates/s at batch 32 on 1 thread (SURVEY.md section 6)"}
+        port_v = n / (time.perf_counter() - t0)
+        out["cpu_baseline_updates_per_s"] = {"value": port_v, "kind": "port", "cores": os.cpu_count(),
+                                             "sample": f"{n} updates of batch 1024, oracle/iqn_oracle.py (numpy/BLAS)"}
+        from oracle import ref_timing
+        if ref_timing.available():
+            # the reference's own IQNAgent.train (thirdparty/IQN/agent.py:269-304, PyTorch CPU), staged in oracle/_ref
+            r32, n32 = ref_timing.iqn_updates_per_s(32, threads=1, seconds=3.0)
+            r1k, n1k = ref_timing.iqn_updates_per_s(1024, threads=1, seconds=4.0)
+            r1k_all, n1k_all = ref_timing.iqn_updates_per_s(1024, threads=os.cpu_count() or 1, seconds=4.0)
+            out["cpu_baseline_updates_per_s"] = {
+                "value": max(r1k, r1k_all), "kind": "reference", "cores": os.cpu_count(),
+                "batch_1024_1_thread": r1k, "batch_1024_all_threads": r1k_all, "batch_32_1_thread": r32,
+                "sample": f"unmodified IQNAgent.train (PyTorch CPU): {n1k} / {n1k_all} updates of batch 1024 on 1 / all threads, {n32} updates of "
+                          "batch 32 (the reference's default) on 1 thread",
+                "port": {"value": port_v, "sample": f"{n} updates of batch 1024, oracle/iqn_oracle.py (numpy/BLAS)"}}
     return out
 
 

@@ -21,6 +21,7 @@ class MnvParams(C.Structure):
         ("sonar_range", C.c_double), ("sonar_angle", C.c_double), ("n_beams", C.c_int32),
         ("max_episode_steps", C.c_int32),
         ("set_boundary", C.c_int32), ("width", C.c_double), ("height", C.c_double),
+        ("pdl_prefetch", C.c_int32),
     ]
 
 

@@ -773,7 +773,7 @@ cudaError_t launch_one(Kern kern, unsigned grid, unsigned block, size_t smem, cu
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = mnv_option(MNV_OPT_PDL) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (mnv_option(MNV_OPT_PDL) || K.pdl_prefetch) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, P, K);
 }
 
@@ -831,7 +831,7 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
     K.n_beams = p->n_beams; K.max_ep_steps = p->max_episode_steps; K.set_boundary = p->set_boundary;
     K.max_c = max_c; K.max_o = max_o; K.obs_dim = 4 + 2 * p->n_beams; K.E = E;
     K.allow_tma = mnv_option(MNV_OPT_TMA) ? 1 : 0;
-    K.pdl_prefetch = mnv_option(MNV_OPT_PDL) >= 2 ? 1 : 0;
+    K.pdl_prefetch = (p->pdl_prefetch != 0 || mnv_option(MNV_OPT_PDL) >= 2) ? 1 : 0;
     // "tma" = 1 stages the obstacle rows with the TMA bulk-copy engine (UBLKCP) instead of per-thread cp.async (LDGSTS).
     // Measured A/B in one process (profiles/README.md): 25.03 us vs 24.18 us per step -> cp.async is the default.
     // Sonar.compute_phi / compute_beam_angles (robot.py:14-21)

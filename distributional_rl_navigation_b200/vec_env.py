@@ -22,13 +22,12 @@ class VecMarineNavEnv:
         if not torch.cuda.is_available():
             raise _lib.MarinenavError("VecMarineNavEnv needs a CUDA device (there is no CPU fallback)")
         _lib.load()
-        # Launch mode of the step kernel: "pdl" = 2 lets a step fetch the map tables (goal, cores, obstacles) while the
-        # launch before it on the stream still drains (include/marinenav_b200.h).  Its contract -- the launch right before
-        # mnv_step does not write those tables -- holds for every sequence of this class: mnv_reset is always followed by
-        # mnv_observe, table uploads are host copies, and tables_written() fences device-side edits (the facade's setters).
-        # pdl_prefetch=False (or MNV_PDL in the environment) leaves the process-wide switch alone.
-        if pdl_prefetch and os.environ.get("MNV_PDL") is None and _lib.get_option("pdl") == 0:
-            _lib.set_option("pdl", 2)
+        # Launch mode of THIS env's step launches (mnv_params.pdl_prefetch, per call -- no process-wide state is touched):
+        # a step fetches the map tables (goal, cores, obstacles) while the launch before it on the stream still drains
+        # (include/marinenav_b200.h).  Its contract -- the launch right before mnv_step does not write those tables -- holds
+        # for every sequence of this class: mnv_reset is always followed by mnv_observe, table uploads are host copies, and
+        # tables_written() fences device-side edits (the facade's setters).  MNV_PDL in the environment overrides (lab use).
+        self.pdl_prefetch = bool(pdl_prefetch) and os.environ.get("MNV_PDL") is None
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         self.sd = seed
@@ -92,7 +91,7 @@ class VecMarineNavEnv:
         """mnv_params of the current attribute values (cached: rebuilt only when an attribute changed)."""
         key = (self.num_beams, self.dt, self.N, tuple(float(v) for v in self.a), tuple(float(v) for v in self.w), self.max_speed,
                self.robot_r, self.r, self.goal_dis, self.timestep_penalty, self.collision_penalty, self.goal_reward,
-               self.sonar_range, self.sonar_angle, bool(self.set_boundary), self.width, self.height)
+               self.sonar_range, self.sonar_angle, bool(self.set_boundary), self.width, self.height, self.pdl_prefetch)
         if getattr(self, "_params_key", None) == key:
             return self._params_cache
         p = self._build_params()
@@ -110,6 +109,7 @@ class VecMarineNavEnv:
         p.timestep_penalty, p.collision_penalty, p.goal_reward = self.timestep_penalty, self.collision_penalty, self.goal_reward
         p.sonar_range, p.sonar_angle = self.sonar_range, self.sonar_angle
         p.set_boundary, p.width, p.height = int(self.set_boundary), self.width, self.height
+        p.pdl_prefetch = int(self.pdl_prefetch)
         return p
 
     def reset_params(self):
@@ -256,6 +256,9 @@ class VecMarineNavEnv:
         pin = self._pin()
         pin["obs"].copy_(self.reset())
         return pin["obs"].numpy()
+
+    def host_api_description(self):
+        return ("VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step)")
 
     def h2d_bytes_per_step(self):
         return self.num_envs * 4

@@ -55,6 +55,7 @@ typedef struct mnv_params {
     double sonar_range, sonar_angle; int32_t n_beams; /* Sonar.range, .angle, .num_beams */
     int32_t max_episode_steps;                        /* 1000, marinenav_env.py:244 */
     int32_t set_boundary; double width, height;       /* marinenav_env.py:73,40-41 */
+    int32_t pdl_prefetch;                             /* launch mode of THIS call, see below (0 = plain launch; default) */
 } mnv_params;
 
 /* Map-generation constants of MarineNavEnv.reset (marinenav_env.py:40-64,86-197). */
@@ -71,15 +72,18 @@ const char* mnv_last_error_string(void);
 void        mnv_default_params(mnv_params* p);
 void        mnv_default_reset_params(mnv_reset_params* p);
 
-/* Process-wide tuning switches of the kernels (results are identical for every setting; parity tests run all of them).
+/* Launch mode of mnv_step, PER CALL: mnv_params.pdl_prefetch != 0 launches the step with programmatic stream
+ * serialization and lets it fetch the map tables (d_goal, d_cores, d_obstacles) BEFORE griddepcontrol.wait, i.e. while the
+ * previous launch on the stream still runs (15.1 -> 12.9 us per 65 536-env step).  CONTRACT: the launch immediately before
+ * that mnv_step on the stream does not write those three tables (mnv_reset must be followed by mnv_observe or any other
+ * launch first; host -> device copies are fine).  Only a caller whose own launch sequences satisfy the contract sets the
+ * flag (VecMarineNavEnv does, for its own launches); the default 0 has no contract.
+ *
+ * Process-wide tuning switches of the kernels (lab use; results are identical for every setting; parity tests run all of them).
  *   "pdl" 0|1|2  1: launch mnv_step / mnv_observe with programmatic stream serialization: the next launch on the stream
  *              is scheduled while this one drains and blocks in griddepcontrol.wait before its first global access
- *              (measured 1 % slower than 0 on back-to-back steps, profiles/README.md).  2: additionally mnv_step fetches
- *              the map tables (d_goal, d_cores, d_obstacles) BEFORE that wait, i.e. while the previous launch still
- *              runs: 15.1 -> 12.9 us per 65 536-env step.  CONTRACT of 2: the launch immediately before mnv_step on the
- *              stream does not write those three tables (mnv_reset must be followed by mnv_observe or any other launch
- *              first; host -> device copies are fine).  Default 0; VecMarineNavEnv, whose sequences satisfy the
- *              contract, selects 2 unless MNV_PDL is set in the environment.
+ *              (measured 1 % slower than 0 on back-to-back steps, profiles/README.md).  2: every mnv_step of the process
+ *              behaves as if pdl_prefetch were set.  Default 0 (MNV_PDL in the environment gives the initial value).
  *   "tma" 0|1  stage the obstacle rows with the TMA bulk-copy engine (cp.async.bulk) instead of per-thread cp.async
  *              (default 0: measured slower, profiles/README.md)
  * Returns 0, or MNV_E_PARAM for an unknown key.  mnv_get_option returns the value or MNV_E_PARAM. */

@@ -20,7 +20,18 @@ import sys
 import types
 import warnings
 
-REF_ROOT = os.environ.get("MARINENAV_REF", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/stage_ref.py (travels to the GPU box)
+
+
+def _find_root():
+    cands = [os.environ.get("MARINENAV_REF"), "/root/reference", _STAGED]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "marinenav_env", "envs", "marinenav_env.py")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -60,13 +60,14 @@ def mnv_params_like(orc_p):
     return p
 
 
-def run_step_vectors(d, n_beams):
+def run_step_vectors(d, n_beams, pdl_prefetch=0):
     for boundary in (0, 1):
         sel = np.where(d["set_boundary"] == boundary)[0]
         if sel.size == 0:
             continue
         p = _lib.default_params(n_beams)
         p.set_boundary = boundary
+        p.pdl_prefetch = pdl_prefetch
         buf = to_buf(soa(d["state"][sel]), soa(d["velocity"][sel]), soa(d["goal"][sel]), soa(d["cores"][sel]),
                      soa(d["obstacles"][sel]), n_beams, d["action"][sel], d["episode_step"][sel])
         env_ops.step(buf, p)
@@ -98,6 +99,14 @@ def test_step_golden_vectors_every_kernel_option(golden_dir, opts):
     finally:
         for k, v in old.items():
             L.mnv_set_option(k.encode(), v)
+
+
+def test_step_golden_vectors_per_call_pdl_prefetch(golden_dir):
+    """mnv_params.pdl_prefetch (the per-call launch mode VecMarineNavEnv uses) changes no result and no process-wide switch."""
+    L = _lib.load()
+    before = L.mnv_get_option(b"pdl")
+    run_step_vectors(np.load(os.path.join(golden_dir, "step_vectors.npz")), 11, pdl_prefetch=1)
+    assert L.mnv_get_option(b"pdl") == before
 
 
 def test_step_dense_golden_vectors(golden_dir):
