@@ -26,6 +26,8 @@ FILES = [
     "thirdparty/IQN/agent.py",
     "thirdparty/IQN/model.py",
     "thirdparty/IQN/replay_buffer.py",
+    "train_IQN_model.py",                    # the caller that must run UNCHANGED on the drop-in packages (tests/test_dropin_driver.py)
+    "config/config_IQN.json",
     "pretrained_models/IQN/seed_3/network_params.pth",
     "pretrained_models/IQN/seed_3/constructor_params.json",
     "LICENSE",
