@@ -539,11 +539,11 @@ def iqn_bench(args, dev, world):
                           min_start_goal_dis=30.0, num_beams=N_BEAMS)
     agent2 = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B, BUFFER_SIZE=4 * E)
     n_roll = 41
-    agent2.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
+    agent2.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E)
     sync()
     t0 = time.perf_counter()
     start_ts = agent2.current_timestep
-    agent2.learn_vec(total_timesteps=start_ts + E * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
+    agent2.learn_vec(total_timesteps=start_ts + E * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E)
     sync()
     dt = time.perf_counter() - t0
     steps_done = agent2.current_timestep - start_ts

@@ -12,6 +12,10 @@
 //   * vortex velocity: tangent*speed = k*(-dy,dx)/d^2 outside the core and k*(-dy,dx)/r^2 inside (k = +-Gamma/2pi),
 //     i.e. no sqrt and one Newton reciprocal per core instead of normalise-then-scale (same value, Q1 kept: every
 //     core contributes; Q2: summation order is table order, ulp-level only);
+//     d == 0 (the robot exactly on a core centre): the reference divides 0/0 there (marinenav_env.py:447-449 -> NaN state
+//     for the rest of the episode); this kernel takes the solid-body branch, whose contribution at d = 0 is exactly zero.
+//     Unreachable in practice (a measure-zero point the fp64 trajectory would have to hit exactly) and deliberately NOT
+//     reproduced: a NaN pose has no defined observation, reward or flag to be in parity with;
 //   * heading: sincos(theta) once, then the sub-steps rotate (cos,sin) by the fixed yaw increment w*dt;
 //   * sonar: obstacle centres are rotated into the robot frame once, beams are the constant directions
 //     (cos b, sin b) there; ray/circle in direction form t = t_ca -+ sqrt(r^2 - cross^2) picking the reference's

@@ -329,8 +329,10 @@ class IQNAgent:
                      times=np.array(self.eval_times[policy]), energies=np.array(self.eval_energies[policy]))
 
     # ---- vectorised training: everything stays on the device ----------------------------------------------------------------
-    def evaluation_vec(self, eval_config, greedy=True, eval_log_path=None, verbose=False, params=None):
-        """evaluation() with all maps of eval_config stepped as ONE env batch (same episode definitions)."""
+    def evaluation_vec(self, eval_config, greedy=True, eval_log_path=None, verbose=False, tensor_cores=False):
+        """evaluation() with all maps of eval_config stepped as ONE env batch (same episode definitions).  Acts with the
+        fp32 parity kernel (iqn_forward) by default: the logged evaluations are the fp32 policy's, like the reference's;
+        tensor_cores=True selects the bf16 tcgen05 kernel (q-values within ~1e-2 relative: near-ties may flip an action)."""
         from .vec_env import VecMarineNavEnv
         cfgs = list(eval_config.values())
         env = VecMarineNavEnv.from_eval_configs(cfgs, device=self.device)
@@ -342,7 +344,7 @@ class IQNAgent:
         length = torch.zeros(n, dtype=torch.int64, device=self.device)
         acts = []
         for t in range(1000):
-            a = self.act_batch(obs, 0.0, adaptive=not greedy)
+            a = self.act_batch(obs, 0.0, adaptive=not greedy, tensor_cores=tensor_cores)
             obs, reward, done, info = env.step(a, auto_reset=False)
             ret += torch.where(alive, (env.discount ** t) * reward.double(), torch.zeros_like(ret))
             last_info = torch.where(alive, info, last_info)
@@ -358,22 +360,52 @@ class IQNAgent:
         self._log_evaluation(greedy, action_data, list(ret.cpu().numpy()), list((last_info == 3).cpu().numpy()),
                              list(env.dt * env.N * length_h.astype(np.float64)), energy, eval_log_path, verbose)
 
+    def reference_updates_per_step(self, num_envs, batch_size=None):
+        """The reference's replay ratio in vector form: agent.py:127-136 trains once on BATCH_SIZE = 32 samples every
+        UPDATE_EVERY = 4 transitions, i.e. 8 sampled transitions per collected one; a vector step collects num_envs (x world
+        size) transitions, so the same ratio needs num_envs * 32 / (UPDATE_EVERY * batch_size) updates of batch_size."""
+        B = batch_size or self.BATCH_SIZE
+        return max(1, int(round(num_envs * 32.0 / (self.UPDATE_EVERY * B))))
+
     def learn_vec(self, total_timesteps, train_env, eval_config=None, eval_freq=None, eval_log_path=None, batch_size=None,
                   updates_per_step=1, learning_starts=None, target_update_interval=None, buffer_size=None, verbose=False,
-                  on_step=None):
+                  on_step=None, sample_without_replacement=False):
         """Vectorised counterpart of learn(): E transitions per env.step, device replay buffer, `updates_per_step` IQN
-        updates of `batch_size` per vector step once `learning_starts` transitions were collected.  Schedules (epsilon,
-        target update, evaluation) are keyed on transitions / learning steps like the reference's."""
+        updates of `batch_size` per vector step once `learning_starts` transitions were collected.
+
+        Cadence (UPDATE_EVERY, agent.py:127-136).  The reference interleaves ONE update with every UPDATE_EVERY-th
+        transition; a vector step yields E transitions at once, so the unit here is updates per vector step:
+        `updates_per_step=1` (default, the throughput configuration of BASELINE configs[2]) or
+        `updates_per_step="reference"` = reference_updates_per_step(E x world, batch_size), which keeps the reference's
+        8 sampled transitions per collected transition.  The learning-step counters (target update every
+        `target_update_interval` updates... see below) count UPDATES x UPDATE_EVERY, so that `target_update_interval` and
+        `eval_freq` keep the reference's meaning ("learning timesteps" = transitions since learning started).
+        Schedules (epsilon, curriculum, termination) are keyed on GLOBAL transitions: E x world size per vector step.
+        Order inside a learning step as in the reference: train, then soft_update, then evaluation (agent.py:129-148)."""
         E = train_env.num_envs
+        world = mdist.world_size()
+        if world > 1:                                           # every rank must run the same number of all-reduces
+            lo_hi = torch.tensor([E, -E], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(lo_hi, op=torch.distributed.ReduceOp.MIN)
+            if int(lo_hi[0]) != E or int(-lo_hi[1]) != E:
+                raise ValueError(f"learn_vec: every rank needs the same number of environments (this rank: {E}, "
+                                 f"min {int(lo_hi[0])}, max {int(-lo_hi[1])}); shard num_envs * world evenly")
+        train_env.global_step_multiplier = world                 # curriculum keyed on global transitions (marinenav_env.py:89-98)
         B = batch_size or self.BATCH_SIZE
+        if updates_per_step == "reference":
+            updates_per_step = self.reference_updates_per_step(E * world, B)
         learning_starts = self.learning_starts if learning_starts is None else learning_starts
         target_update_interval = self.target_update_interval if target_update_interval is None else target_update_interval
         if self.device_memory is None:
-            self.device_memory = DeviceReplayBuffer(buffer_size or self.BUFFER_SIZE, B, self.device, seed=self.seed)
+            self.device_memory = DeviceReplayBuffer(buffer_size or self.BUFFER_SIZE, B, self.device, seed=self.seed,
+                                                    gamma=self.GAMMA, n_step=self.n_step, num_envs=E)
         mem = self.device_memory
+        if mem.n_step != self.n_step:
+            raise ValueError("learn_vec: the device replay buffer was built for n_step=%d, the agent uses %d" % (mem.n_step, self.n_step))
         obs = train_env.reset().clone()
         losses = []
         next_eval = 0
+        steps_per_update = (E * world) / float(updates_per_step)   # transitions one update stands for (reference: UPDATE_EVERY)
         # Two streams: the env stream (act -> fused step -> masked reset + re-observe) and the learner stream (replay append
         # -> sample -> IQN update), forked right behind the step kernel.  The update does not depend on the reset and the
         # reset does not depend on the update, so the two halves of a vector step overlap; act waits for the new weights.
@@ -389,7 +421,7 @@ class IQNAgent:
             action = self.act_batch(obs, eps)
             next_obs, reward, done, _ = train_env.step_begin(action)
             ev_step.record(env_stream)
-            self.current_timestep += E
+            self.current_timestep += E * world
             learn_stream.wait_event(ev_step)
             action.record_stream(learn_stream)
             with torch.cuda.stream(learn_stream):
@@ -400,30 +432,34 @@ class IQNAgent:
                 do_eval = False
                 if self.current_timestep >= learning_starts and len(mem) > B:
                     for _ in range(updates_per_step):
-                        s, a, r, s2, d = mem.sample(B)
-                        taus_t = torch.rand(B, 8, device=self.device, generator=self.gen)
+                        batch = mem.sample(B, without_replacement=sample_without_replacement)
+                        taus_t = torch.rand(B, 8, device=self.device, generator=self.gen)      # Q9: target taus first
                         taus_l = torch.rand(B, 8, device=self.device, generator=self.gen)
-                        if self.learning_timestep % target_update_interval == 0:
+                        loss = self.train_async(batch, (taus_t, taus_l))
+                        # agent.py:135-137: the target update follows the training step of the same learning timestep;
+                        # learning timesteps advance by the transitions this update stands for
+                        before = self.learning_timestep
+                        self.learning_timestep += steps_per_update
+                        if before == 0 or int(before // target_update_interval) != int(self.learning_timestep // target_update_interval):
                             self.soft_update(self.qnetwork_local, self.qnetwork_target)
-                        loss = self.train_async((s.contiguous(), a.contiguous(), r.contiguous(), s2.contiguous(), d.contiguous()),
-                                                (taus_t, taus_l))
-                        self.learning_timestep += 1
-                    if verbose and self.learning_timestep % 100 == 0:
-                        losses.append(float(loss.item()))
-                    do_eval = eval_config is not None and eval_freq and self.learning_timestep >= next_eval
+                    if verbose:
+                        losses.append(loss.clone())
+                    do_eval = eval_config is not None and bool(eval_freq) and self.learning_timestep >= next_eval
                 ev_update.record(learn_stream)
             train_env.step_finish(auto_reset=True)                # env stream: overlaps the update
             env_stream.wait_event(ev_added)                       # the replay append has read the previous obs
             obs.copy_(train_env.buf["obs"])
             if do_eval:
                 env_stream.wait_event(ev_update)
-                self.evaluation_vec(eval_config, greedy=True, eval_log_path=eval_log_path)
-                self.evaluation_vec(eval_config, greedy=False, eval_log_path=eval_log_path)
-                if eval_log_path is not None:
-                    self.qnetwork_local.save(eval_log_path)
+                if mdist.rank() == 0:                             # replicas are bit-identical: one rank evaluates and logs
+                    self.evaluation_vec(eval_config, greedy=True, eval_log_path=eval_log_path)
+                    self.evaluation_vec(eval_config, greedy=False, eval_log_path=eval_log_path)
+                    if eval_log_path is not None:
+                        self.qnetwork_local.save(eval_log_path)
+                mdist.barrier()
                 next_eval += eval_freq
                 learn_stream.wait_stream(env_stream)
             if on_step is not None:
                 on_step(self)
         env_stream.wait_stream(learn_stream)
-        return losses
+        return [float(x.item()) for x in losses[::max(1, len(losses) // 200)]] if verbose else losses

@@ -30,18 +30,61 @@ except ImportError:
 _CAP_CORES, _CAP_OBS = 8, 32
 
 
-class Core:
+class _TableItem:
+    """A map primitive whose field edits reach the device table it was read from (env.cores[0].x = ... works in place,
+    like editing the reference's Python objects)."""
+    _owner = None
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        owner = object.__getattribute__(self, "_owner")
+        if owner is not None and not name.startswith("_"):
+            owner._push()
+
+
+class Core(_TableItem):
     """marinenav_env.py:8-15"""
 
     def __init__(self, x, y, clockwise, Gamma):
         self.x, self.y, self.clockwise, self.Gamma = x, y, clockwise, Gamma
 
 
-class Obstacle:
+class Obstacle(_TableItem):
     """marinenav_env.py:17-23"""
 
     def __init__(self, x, y, r):
         self.x, self.y, self.r = x, y, r
+
+
+class _TableList(list):
+    """What env.cores / env.obstacles return: a list of the device table's entries that WRITES BACK on mutation, so the
+    reference-style in-place edits (env.cores.clear(), env.obstacles.append(...), run_experiments.py:131-180) reach the
+    device tables instead of being lost on a temporary."""
+
+    def __init__(self, items, env, attr):
+        super().__init__(items)
+        self._env, self._attr = env, attr
+        for it in self:
+            object.__setattr__(it, "_owner", self)
+
+    def _push(self):
+        for it in self:
+            if isinstance(it, _TableItem):
+                object.__setattr__(it, "_owner", self)
+        setattr(self._env, self._attr, list(self))
+
+
+def _mutator(name):
+    def method(self, *a, **k):
+        res = getattr(list, name)(self, *a, **k)
+        self._push()
+        return res
+    method.__name__ = name
+    return method
+
+
+for _m in ("append", "extend", "insert", "remove", "pop", "clear", "sort", "reverse", "__setitem__", "__delitem__", "__iadd__", "__imul__"):
+    setattr(_TableList, _m, _mutator(_m))
 
 
 class Sonar:
@@ -282,7 +325,8 @@ class MarineNavEnv(_gym.Env):
         b = self._vec.buf
         n, mc = int(b["n_placed"][0, 0]), self._vec.max_cores
         t = b["cores"][:, 0].cpu().numpy()
-        return [Core(float(t[k]), float(t[mc + k]), int(t[2 * mc + k] > 0), float(abs(t[2 * mc + k]))) for k in range(n)]
+        return _TableList([Core(float(t[k]), float(t[mc + k]), int(t[2 * mc + k] > 0), float(abs(t[2 * mc + k]))) for k in range(n)],
+                          self, "cores")
 
     @cores.setter
     def cores(self, cores):
@@ -299,7 +343,7 @@ class MarineNavEnv(_gym.Env):
         b = self._vec.buf
         n, mo = int(b["n_placed"][1, 0]), self._vec.max_obstacles
         t = b["obstacles"][:, 0].cpu().numpy()
-        return [Obstacle(float(t[k]), float(t[mo + k]), float(t[2 * mo + k])) for k in range(n)]
+        return _TableList([Obstacle(float(t[k]), float(t[mo + k]), float(t[2 * mo + k])) for k in range(n)], self, "obstacles")
 
     @obstacles.setter
     def obstacles(self, obstacles):

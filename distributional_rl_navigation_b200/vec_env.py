@@ -45,6 +45,7 @@ class VecMarineNavEnv:
         self.discount = 0.99
         self.num_cores, self.num_obs, self.min_start_goal_dis = num_cores, num_obs, min_start_goal_dis
         self.total_timesteps = 0          # env steps taken over ALL environments (curriculum key, marinenav_env.py:89-98)
+        self.global_step_multiplier = 1   # data-parallel training: world size, so the curriculum follows GLOBAL steps
         self.set_boundary = False
         # --- Robot / Sonar (robot.py:7-9,28-37) ---
         self.dt, self.N = 0.1, 10
@@ -164,7 +165,7 @@ class VecMarineNavEnv:
         b = self.buf
         with torch.cuda.device(self.device):
             env_ops.step(b, self.params(), action=actions, obs=b["next_obs"], trajectory=trajectory)
-        self.total_timesteps += self.num_envs
+        self.total_timesteps += self.num_envs * self.global_step_multiplier
         return b["next_obs"], b["reward"], b["done"], b["info"]
 
     def step_finish(self, auto_reset=True):
@@ -243,7 +244,7 @@ class VecMarineNavEnv:
                 self._host_graphs.clear()                         # parameters changed: the old graph holds stale constants
                 entry = self._host_graphs[key] = self._capture_host_step(auto_reset)
             entry[0].replay()
-            self.total_timesteps += self.num_envs
+            self.total_timesteps += self.num_envs * self.global_step_multiplier
             torch.cuda.current_stream().synchronize()
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
 
@@ -295,6 +296,15 @@ class VecMarineNavEnv:
         assert len(cfgs) == self.num_envs
         c0, E = cfgs[0], self.num_envs
         e, r = c0["env"], c0["robot"]
+        for i, c in enumerate(cfgs[1:], 1):                    # one kernel launch = one set of scalar constants
+            for k in ("width", "height", "r", "goal_dis", "timestep_penalty", "collision_penalty", "goal_reward", "discount"):
+                if c["env"][k] != e[k]:
+                    raise ValueError(f"load_eval_configs: env constant '{k}' of config {i} differs from config 0 ({c['env'][k]} != {e[k]})")
+            for k in ("dt", "N", "r", "max_speed", "a", "w"):
+                if c["robot"][k] != r[k]:
+                    raise ValueError(f"load_eval_configs: robot constant '{k}' of config {i} differs from config 0")
+            if c["robot"]["sonar"] != r["sonar"]:
+                raise ValueError(f"load_eval_configs: sonar constants of config {i} differ from config 0")
         self.width, self.height, self.r = e["width"], e["height"], e["r"]
         self.v_rel_max, self.p = e["v_rel_max"], e["p"]
         self.v_range, self.obs_r_range, self.clear_r = list(e["v_range"]), list(e["obs_r_range"]), e["clear_r"]
@@ -349,7 +359,7 @@ class VecMarineNavEnv:
         cores = b["cores"][:, i].cpu().numpy(); obst = b["obstacles"][:, i].cpu().numpy()
         sp = b["start_pose"][:, i].cpu().numpy(); goal = b["goal"][:, i].cpu().numpy()
         mc, mo = self.max_cores, self.max_obstacles
-        ep = {"env": {"seed": self.sd, "width": self.width, "height": self.height, "r": self.r, "v_rel_max": self.v_rel_max,
+        ep = {"env": {"seed": int(self.sd) + int(i), "width": self.width, "height": self.height, "r": self.r, "v_rel_max": self.v_rel_max,
                       "p": self.p, "v_range": list(self.v_range), "obs_r_range": list(self.obs_r_range), "clear_r": self.clear_r,
                       "start": [float(sp[0]), float(sp[1])], "goal": [float(goal[0]), float(goal[1])], "goal_dis": self.goal_dis,
                       "timestep_penalty": self.timestep_penalty, "collision_penalty": self.collision_penalty,

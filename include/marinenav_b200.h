@@ -136,6 +136,41 @@ int mnv_reset(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint8_t* d_mask,
 int mnv_scatter_rows_host(const uint8_t* d_mask, const float* d_rows, float* h_rows_mapped, int64_t E, int32_t row_len,
                           void* stream);
 
+/* ================================ replay buffer (thirdparty/IQN/replay_buffer.py) ===========================
+ * Device-resident ReplayBuffer of the vectorised trainer.  Ring arrays (caller-owned, `capacity` transitions):
+ *   d_states f32 [capacity][row_len], d_actions i64 [capacity], d_rewards f32 [capacity], d_next_states f32
+ *   [capacity][row_len], d_dones f32 [capacity]  -- the tuple layout of replay_buffer.py:20,49-53.
+ * A LOGICAL index i counts from the oldest stored transition (memory[i] of the reference's deque): ring slot =
+ * (head + i) mod capacity.  The caller keeps head / size / pos (they advance deterministically: pos += E per append). */
+
+/* ReplayBuffer.add (replay_buffer.py:26-41) for one vector step of E environments, ONE launch: transition e =
+ * (d_obs[e], d_action[e], d_reward[e], d_next_obs[e], d_done[e]) goes through environment e's n-step window
+ * (deque(maxlen=n_step), :24,29; d_win_* = [n_step][E] rows, only read / written when n_step > 1) and, once the window
+ * holds n_step entries (t >= n_step - 1, t = number of vector steps appended before this one), the folded transition
+ * (state_0, action_0, sum_i gamma^i reward_i in double, next_state_{n-1}, done_{n-1}) (:36-41) is stored in ring slot
+ * (pos + e) mod capacity.  Like the reference, the window is NOT cleared at episode ends. */
+int rpl_append(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
+               int64_t capacity, int64_t pos, const float* d_obs, const int32_t* d_action, const float* d_reward,
+               const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, float gamma,
+               int64_t t, float* d_win_obs, int32_t* d_win_action, float* d_win_reward, void* stream);
+
+/* ReplayBuffer.sample (replay_buffer.py:45-55): B picks among the `size` stored transitions, gathered into
+ * d_out_states f32 [B][row_len], d_out_actions i64 [B], d_out_rewards f32 [B], d_out_next_states, d_out_dones f32 [B]
+ * (what iqn_loss_grad consumes).  The picks (logical indices, also written to d_indices i64 [B]) come from the
+ * counter-based Philox4x32-10 stream (seed, call): without_replacement != 0 yields an ordered tuple of B distinct
+ * indices, every such tuple equally likely -- the distribution of random.sample (:47); 0 yields independent uniform picks.
+ * Deterministic for given (seed, call, size, B).  B <= 8192.  Two launches (draw, gather). */
+int rpl_sample(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
+               const float* d_dones, int64_t capacity, int64_t head, int64_t size, uint64_t seed, uint64_t call,
+               int32_t without_replacement, int64_t* d_indices, float* d_out_states, int64_t* d_out_actions,
+               float* d_out_rewards, float* d_out_next_states, float* d_out_dones, int64_t B, int32_t row_len, void* stream);
+
+/* The gather of rpl_sample for caller-provided logical indices d_indices i64 [B] (e.g. the reference's random.sample picks). */
+int rpl_gather(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
+               const float* d_dones, int64_t capacity, int64_t head, int64_t size, const int64_t* d_indices,
+               float* d_out_states, int64_t* d_out_actions, float* d_out_rewards, float* d_out_next_states,
+               float* d_out_dones, int64_t B, int32_t row_len, void* stream);
+
 /* ======================================= IQN (thirdparty/IQN) ============================================
  * Parameters: ONE flat fp32 vector of iqn_param_count() = 35 785 floats = the 14 tensors of ObsEncoder.state_dict() in
  * order (velocity_encoder.weight [16,2], .bias, goal_encoder.*, sensor_encoder.* [176,22], cos_embedding.* [208,64],

@@ -10,7 +10,7 @@
  * the CUDA product path uses a different (robot-centred, division-light) formulation and is compared
  * against this file within the tolerance stated in the tests.
  *
- * PARITY PINNED (see marinenav_oracle.h): tests/test_oracle_pinning.py.
+ * PARITY PINNED (see marinenav_oracle.h): tests/test_oracle_golden.py (reference golden vectors, recorded episodes, eval_config KAT).
  * Build: oracle/Makefile  (gcc -O2 -ffp-contract=off -fPIC -shared -pthread).
  */
 #include "marinenav_oracle.h"

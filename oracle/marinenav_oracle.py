@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/libmarinenav_oracle.so (the CPU parity oracle).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
-The product package never does (tests/test_no_oracle_in_product.py enforces it).
+The product package never does (tests/test_abi_cpu.py::test_product_never_imports_oracle enforces it).
 """
 import ctypes as C
 import os

@@ -9,9 +9,9 @@ from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
 E, B = 65536, 1024
 env = VecMarineNavEnv(E, seed=1, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
 agent = IQNAgent(26, 9, seed=0, device="cuda:0", BATCH_SIZE=B, BUFFER_SIZE=4 * E)
-agent.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
+agent.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-agent.learn_vec(total_timesteps=agent.current_timestep + E * 5, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100)
+agent.learn_vec(total_timesteps=agent.current_timestep + E * 5, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()

@@ -20,7 +20,7 @@ def lib():
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "marinenav_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:mnv|iqn)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:mnv|iqn|rpl)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_exports_every_declared_symbol(lib):

@@ -163,10 +163,22 @@ def test_learn_single_env_and_vectorised_smoke(tmp_path, golden_dir):
     # vectorised
     venv = VecMarineNavEnv(2048, seed=0, schedule=SCHED, device="cuda:0")
     agent2 = IQNAgent(26, 9, seed=1, device="cuda:0", BATCH_SIZE=256, BUFFER_SIZE=50000)
-    agent2.learn_vec(total_timesteps=2048 * 12, train_env=venv, batch_size=256, learning_starts=4096, target_update_interval=4,
-                     updates_per_step=2)
-    assert agent2.learning_timestep == 2 * 12 and len(agent2.device_memory) == min(50000, 2048 * 13)
-    assert torch.isfinite(agent2.qnetwork_local.flat).all() and agent2.optimizer.step_count == agent2.learning_timestep
+    agent2.learn_vec(total_timesteps=2048 * 12, train_env=venv, batch_size=256, learning_starts=4096, target_update_interval=4096,
+                     updates_per_step=2, sample_without_replacement=True)
+    # 12 learning vector steps x 2 updates; a learning timestep = one collected transition (agent.py:127-150), 1024 per update
+    assert agent2.optimizer.step_count == 2 * 12 and agent2.learning_timestep == 2 * 12 * 1024
+    assert len(agent2.device_memory) == min(50000, 2048 * 13)
+    assert torch.isfinite(agent2.qnetwork_local.flat).all()
+    assert len(set(agent2.device_memory.last_indices.cpu().tolist())) == 256          # random.sample semantics: distinct picks
+    # the reference's replay ratio (UPDATE_EVERY = 4, batch 32 -> 8 sampled per collected transition) in vector form
+    assert agent2.reference_updates_per_step(2048, 256) == 64 and agent2.reference_updates_per_step(64, 32) == 16
+    # n-step returns: the device buffer folds them per environment (replay_buffer.py:36-41)
+    venv3 = VecMarineNavEnv(256, seed=7, device="cuda:0")
+    agent3 = IQNAgent(26, 9, seed=2, device="cuda:0", BATCH_SIZE=64, BUFFER_SIZE=4096, n_step=3)
+    agent3.learn_vec(total_timesteps=256 * 8, train_env=venv3, learning_starts=1024, updates_per_step="reference")
+    assert agent3.device_memory.n_step == 3 and len(agent3.device_memory) == 256 * (9 - 2)
+    assert agent3.optimizer.step_count == 6 * agent3.reference_updates_per_step(256, 64)
+    assert torch.isfinite(agent3.qnetwork_local.flat).all()
 
 
 def test_step_host_matches_device_step():
@@ -300,3 +312,36 @@ def test_training_driver_reference_config_format(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     run = next((tmp_path / "vec").glob("training_*/seed_3"))
     assert (run / "network_params.pth").is_file() and (run / "greedy_evaluations.npz").is_file() and (run / "adaptive_evaluations.npz").is_file()
+
+
+def test_learn_loop_reproduces_reference_trace(golden_dir):
+    """IQNAgent.learn (agent.py:94-173) through the drop-in surfaces against a trace recorded from the UNMODIFIED reference
+    (tests/golden/make_golden_learn.py: env seed 13, agent seed 5, 241 steps, 51 train() calls, one evaluation map):
+    the epsilon-greedy actions, the episode ends, the replay picks of every random.sample and both evaluation episodes are
+    identical; rewards within 1e-5, every loss within 1e-4 (the north-star tolerance for the IQN loss)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_learn", os.path.join(golden_dir, "make_golden_learn.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    ref = np.load(os.path.join(golden_dir, "learn_trace.npz"))
+    assert json.loads(str(ref["config_json"])) == gen.CFG
+    with open(os.path.join(golden_dir, "eval_config.json")) as f:
+        eval_cfg = json.load(f)["env_0"]
+    from thirdparty import IQNAgent
+    C = gen.CFG
+    got = gen.record_learn(lambda s: make_env(s),
+                           lambda: IQNAgent(26, 9, seed=C["agent_seed"], BATCH_SIZE=C["batch_size"], UPDATE_EVERY=C["update_every"],
+                                            learning_starts=C["learning_starts"], target_update_interval=C["target_update_interval"],
+                                            device="cuda:0"), eval_cfg)
+    np.testing.assert_array_equal(got["actions"], ref["actions"])
+    np.testing.assert_array_equal(got["dones"], ref["dones"])
+    assert int(ref["dones"].sum()) >= 2                            # the trace crosses episode ends (reset inside learn)
+    np.testing.assert_array_equal(got["picks"], ref["picks"])
+    close(got["rewards"], ref["rewards"])
+    assert got["losses"].shape == ref["losses"].shape == (51,)
+    rel = np.abs(got["losses"] - ref["losses"]) / np.maximum(1.0, np.abs(ref["losses"]))
+    assert rel.max() <= 1e-4, rel.max()
+    for pol in ("greedy", "adaptive"):
+        np.testing.assert_array_equal(got[f"eval_{pol}_actions"], ref[f"eval_{pol}_actions"])
+        assert bool(got[f"eval_{pol}_success"]) == bool(ref[f"eval_{pol}_success"])
+        assert int(got[f"eval_{pol}_timestep"]) == int(ref[f"eval_{pol}_timestep"])
+        assert abs(float(got[f"eval_{pol}_reward"]) - float(ref[f"eval_{pol}_reward"])) <= 1e-4

@@ -51,6 +51,8 @@ def to_buf(state, velocity, goal, cores, obstacles, n_beams, action=None, episod
 def mnv_params_like(orc_p):
     p = _lib.default_params(orc_p.n_beams)
     for f, _ in _lib.MnvParams._fields_:
+        if not hasattr(orc_p, f):                              # launch-mode fields have no counterpart in the oracle
+            continue
         v = getattr(orc_p, f)
         if hasattr(v, "__len__"):
             for i in range(len(v)):
@@ -245,6 +247,36 @@ def test_reset_eval_config_kat(golden_dir):
             assert list(st[:2]) == c["env"]["start"]
 
 
+def test_reset_curriculum_streams_bit_exact_on_device(golden_dir):
+    """The reference's reset() streams with the training curriculum (train_IQN_model.py:86-90), recorded from the reference
+    in reset_vectors.npz `stream_*`: 8 seeds x 6 consecutive resets at total_timesteps 0 ... 2 999 999, i.e. all three
+    stages INCLUDING stages 1-2 with RANDOM start / goal at min_start_goal_dis 35 / 40 and 6-8 cores / 8-10 obstacles.
+    mnv_reset on the device, one stream per environment, must reproduce every map, start pose and goal bit for bit."""
+    d = np.load(os.path.join(golden_dir, "reset_vectors.npz"))
+    sched = dict(timesteps=[0, 1000000, 2000000], num_cores=[4, 6, 8], num_obstacles=[6, 8, 10], min_start_goal_dis=[30.0, 35.0, 40.0])
+    S = d["stream_state"].shape[0]
+    buf = env_ops.alloc_env_buffers(S, 8, 10, 11, DEV)
+    key = torch.zeros(S, 624, dtype=torch.int32, device=DEV); pos = torch.zeros(S, dtype=torch.int32, device=DEV)
+    env_ops.seed(key, pos, torch.arange(S, dtype=torch.int32, device=DEV))
+    p = _lib.default_params(11)
+    stages = set()
+    for k, tt in enumerate(d["stream_totals"]):
+        idx = int((np.array(sched["timesteps"]) - int(tt) <= 0).sum()) - 1            # marinenav_env.py:89-98
+        stages.add(idx)
+        rp = _lib.default_reset_params()
+        rp.num_cores, rp.num_obs, rp.min_start_goal_dis = sched["num_cores"][idx], sched["num_obstacles"][idx], sched["min_start_goal_dis"][idx]
+        env_ops.reset(buf, key, pos, rp)
+        env_ops.observe(buf, p, velocity_from_state=True)
+        np.testing.assert_array_equal(buf["state"].cpu().numpy().T, d["stream_state"][:, k])
+        np.testing.assert_array_equal(buf["goal"].cpu().numpy().T, d["stream_goal"][:, k])
+        np.testing.assert_array_equal(buf["cores"].cpu().numpy().T, d["stream_cores"][:, k])
+        np.testing.assert_array_equal(buf["obstacles"].cpu().numpy().T, d["stream_obstacles"][:, k])
+        np.testing.assert_array_equal(buf["n_placed"].cpu().numpy()[0], d["stream_n_cores"][:, k])
+        np.testing.assert_array_equal(buf["n_placed"].cpu().numpy()[1], d["stream_n_obs"][:, k])
+        close(buf["obs"].cpu().numpy(), d["stream_obs"][:, k])
+    assert stages == {0, 1, 2}
+
+
 def test_reset_masked_and_stream_continuation():
     """Masked reset only touches the selected environments and continues each stream like consecutive reset() calls."""
     E = 512
@@ -319,6 +351,13 @@ def test_recorded_episodes_full_replay(golden_dir, name):
     ok_err = err[~bad]
     print(f"{name}: {E} episodes, {int(L.sum())} steps, flag flips {n_bad}, return err max {ok_err.max():.3e}, "
           f"frac > 1e-3: {(ok_err > 1e-3).mean():.2e}")
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):                                  # keep the observed counts (copied to profiles/ per round)
+        with open(os.path.join(out_dir, "free_run_replay_counts.txt"), "a") as f:
+            f.write(f"{name}: episodes {E} steps {int(L.sum())} flag_flips {n_bad} return_err_max {ok_err.max():.3e} "
+                    f"frac_err_gt_1e-3 {(ok_err > 1e-3).mean():.3e} frac_err_gt_1e-2 {(ok_err > 1e-2).mean():.3e}\n")
     np.testing.assert_allclose(0.1 * 10 * lengths, d["times"], rtol=0, atol=1e-9)
-    assert n_bad <= 27, n_bad                                   # <= 0.3 % of episodes (the chaotic ones; the CPU oracle: 0)
+    # observed (profiles/r2_free_run_replay_counts.txt): greedy 0, adaptive 13, dqn 0 flips of 9 000 -- the band is
+    # 1.5x the worst observed count (chaotic vortex-trapped episodes; the CPU oracle, same operation order as the reference: 0)
+    assert n_bad <= 20, n_bad
     assert (ok_err > 1e-2).mean() <= 2e-3
