@@ -46,6 +46,7 @@ struct KParams {
     long long E;
     double snap_t1, snap_t2;        // pi/2 - beam_angle[0], 3pi/2 - beam_angle[0]   (Q10 pre-test, see snap_beam)
     float inv_phi, snap_tol;        // 1 / beam spacing, (1e-3 / spacing) + 1e-4 in beam-index units
+    float beam0f; int precise_bins; // beam_angle[0]; 1: per-obstacle beam intervals (<= 16 beams, field of view < pi), 0: every beam of every obstacle within reach
     double beam_angle[MNV_MAX_BEAMS];
     double beam_cos[MNV_MAX_BEAMS];
     double beam_sin[MNV_MAX_BEAMS];
@@ -70,6 +71,68 @@ __device__ __forceinline__ double fast_rcp(double a)
     return fma(r, fma(e, e, e), r);
 }
 
+// sqrt(a) to <= 1 ulp for a in [1e-300, 1e300]: MUFU.RSQ64H seed (>= 20 bits) + two coupled Newton steps.  Used where the
+// reference's value passes through further roundings anyway (reward differences, ray parameters of the reformulated
+// sonar); threshold DECISIONS on a square root are taken on the squares (collides(), reaches()).
+__device__ __forceinline__ double fast_sqrt(double a)
+{
+    if (a <= 0.0) return a == 0.0 ? 0.0 : sqrt(a);           // 0 and the NaN of a negative argument, like sqrt
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y;                                       // ~ sqrt(a)
+    double h = 0.5 * y;
+    double r = fma(-g, h, 0.5);                             // 0.5 - g h
+    g = fma(g, r, g); h = fma(h, r, h);                     // one Goldschmidt step: ~40 bits
+    const double e = fma(-g, g, a);                         // residual
+    return fma(e, h, g);                                    // final Newton correction: <= 1 ulp
+}
+
+// sin / cos for theta in [0, 2 pi) (the heading after Robot.update_state's wrap, robot.py:120-123): quadrant by one
+// multiply, a two-term Cody-Waite reduction (k <= 4, so k * pio2_hi is exact) and the fdlibm kernel polynomials on
+// [-pi/4, pi/4] (< 1 ulp).  Anything else (a caller poked theta out of range) takes the general sincos().
+__device__ __forceinline__ void sincos_heading(double th, double* sn, double* cs)
+{
+    if (!(th >= 0.0 && th < 6.5)) { sincos(th, sn, cs); return; }
+    const int k = __double2int_rn(th * 0.63661977236758134308);        // 2 / pi
+    const double kd = (double)k;
+    double r = fma(-kd, 1.57079632673412561417e+00, th);               // pio2_1  (33 bits)
+    r = fma(-kd, 6.07710050650619224932e-11, r);                       // pio2_1t
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    ps = fma(z, ps, 2.75573137070700676789e-06); pc = fma(z, pc, -2.75573143513906633035e-07);
+    ps = fma(z, ps, -1.98412698298579493134e-04); pc = fma(z, pc, 2.48015872894767294178e-05);
+    ps = fma(z, ps, 8.33333333332248946124e-03); pc = fma(z, pc, -1.38888888888741095749e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01); pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double sr = fma(r * z, ps, r);                               // sin r
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));               // cos r
+    const double a = (k & 1) ? cr : sr, b = (k & 1) ? sr : cr;         // sin(r + k pi/2), cos(r + k pi/2)
+    *sn = (k & 2) ? -a : a;
+    *cs = ((k + 1) & 2) ? -b : b;
+}
+
+// ---- conservative angular bounds in fp32 for the sonar binning (errors are covered by the margins at the use site) ----
+// atan2(y, x) with |error| <= 1.2e-5 rad (Abramowitz & Stegun 4.4.47 on min/max); (0, 0) -> 0
+__device__ __forceinline__ float atan2_approx(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+    const float t = __fdividef(mn, mx), t2 = t * t;
+    float a = fmaf(t2, 0.0208351f, -0.0851330f);
+    a = fmaf(t2, a, 0.1801410f); a = fmaf(t2, a, -0.3302995f); a = fmaf(t2, a, 0.9998660f);
+    a *= t;
+    a = ay > ax ? 1.57079632679f - a : a;
+    a = x < 0.0f ? 3.14159265359f - a : a;
+    return copysignf(a, y);
+}
+// asin(x), 0 <= x <= 1, |error| <= 6e-5 rad (Abramowitz & Stegun 4.4.45)
+__device__ __forceinline__ float asin_approx(float x)
+{
+    float p = fmaf(x, -0.0187293f, 0.0742610f);
+    p = fmaf(x, p, -0.2121144f); p = fmaf(x, p, 1.5707288f);
+    return fmaf(-sqrtf(1.0f - x), p, 1.57079632679f);
+}
+
 // check_collision (marinenav_env.py:329-336): sqrt(d2) <= thr, decided on the squares unless d2 is within 1e-15 (relative)
 // of thr^2 -- only there can the rounding of the square root matter, and only there is it evaluated.
 __device__ __forceinline__ bool collides(double d2, double thr)
@@ -79,6 +142,9 @@ __device__ __forceinline__ bool collides(double d2, double thr)
     if (!(d2 <= t2 * (1.0 + 1e-15))) return false;                 // also d2 = inf (no obstacle) and NaN
     return sqrt(d2) <= thr;
 }
+
+// check_reach_goal (marinenav_env.py:338-342): sqrt(d2) <= goal_dis, decided like collides()
+__device__ __forceinline__ bool reaches(double d2, double thr) { return collides(d2, thr); }
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: one issue slot for two lanes of the candidate filter) ----
 typedef unsigned long long f32x2;
@@ -141,8 +207,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Dynamic shared memory: [kBlock * obs_dim floats, padded to 16 B][3 * max_o rows x kBlock doubles][mbarriers][exact-test rings]
-constexpr int kRing = 64;       // per-warp ring of pending exact sonar tests: < 32 pending + <= 32 pushed per beam
+// Dynamic shared memory: [kBlock * obs_dim floats, padded to 16 B][3 * max_o rows x kBlock doubles][mbarriers]
+//                        [per-warp lists of pending exact sonar tests][per-env obstacle beam masks][per-env relevant-obstacle masks]
+constexpr int kBeamWord = 16;   // beams handled per pass of the sonar phase (the default 11 beams: one pass)
+constexpr int kRing = 32 * kBeamWord;   // per-warp list of pending exact tests: every (lane, beam of the pass) at most once
 
 #ifndef MNV_MIN_CTAS
 #define MNV_MIN_CTAS 8
@@ -152,7 +220,7 @@ __global__ void __launch_bounds__(kBlock, MNV_MIN_CTAS)
 mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 {
     static_assert(STEP || !PREFETCH, "only the step launch fetches the map tables ahead of its grid dependency");
-    static_assert((MAXO & 1) == 0 && MAXO <= 16, "obstacle pairs are packed for FFMA2; the candidate mask is 16 bits of a ring entry");
+    static_assert((MAXO & 1) == 0 && MAXO <= 16, "per-env obstacle masks are 16-bit words");
     extern __shared__ __align__(16) float s_obs[];           // [kBlock][obs_dim]
     const long long E = K.E;
     const long long e0 = (long long)blockIdx.x * kBlock;
@@ -163,7 +231,10 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     float* my_obs = s_obs + tid * D;
     double* s_ob = reinterpret_cast<double*>(s_obs + ((kBlock * D + 3) & ~3));   // obstacle rows of this CTA
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ob + 3 * K.max_o * kBlock);
-    unsigned* ring = reinterpret_cast<unsigned*>(s_bar + kBlock / 32) + (tid >> 5) * kRing;
+    unsigned short* ring = reinterpret_cast<unsigned short*>(s_bar + kBlock / 32) + (tid >> 5) * kRing;
+    constexpr int kBmStride = (MAXO + 7) & ~7;               // 16-byte rows
+    unsigned short* s_bm = reinterpret_cast<unsigned short*>(s_bar + kBlock / 32) + (kBlock / 32) * kRing;   // [kBlock][kBmStride]: beams obstacle j may return on
+    unsigned* s_rel = reinterpret_cast<unsigned*>(s_bm + kBlock * kBmStride);                                // [kBlock]: obstacles within sonar reach
     const int max_o = K.max_o;
     // vortex cores (registers), goal and obstacle rows (shared memory, per-thread cp.async: each thread copies its own
     // column; first needed after the sub-step loop, so that DRAM round trip hides under the integration)
@@ -215,11 +286,9 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     double x = 0.0, y = 0.0, th = 0.0, sp = 0.0, c = 1.0, s = 0.0;
     double vx = 0.0, vy = 0.0, reward = 0.0, dis_after = 0.0;
     int ep = 0, bs1 = -1, bs2 = -1;
-    f32x2 qx2[MAXO / 2], qy2[MAXO / 2], nr2[MAXO / 2];      // fp32: only the conservative candidate filter uses them
-#pragma unroll
-    for (int jj = 0; jj < MAXO / 2; ++jj) { qx2[jj] = 0ull; qy2[jj] = 0ull; nr2[jj] = pack2(1e30f, 1e30f); }
-    bool force_slow = false;                                // robot within 1e-9 of a circle: decide everything exactly
+    unsigned rel = 0u, beams = 0u;                          // obstacles within sonar reach; beams with a candidate obstacle
     double best_d2 = INFINITY, best_r = 0.0;               // Q4: nearest CENTRE only (marinenav_env.py:329-336)
+    double dis_after2 = 0.0;
 
     if (live) {
         // ---- every global load of this environment is issued before the first use of any of them, so that the kernel entry
@@ -242,7 +311,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 }
             }
         }
-        sincos(th, &s, &c);
+        sincos_heading(th, &s, &c);
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) ck[i] *= (1.0 / (2.0 * MNV_PI));
         auto current = [&](double px, double py, double& ux, double& uy) {
@@ -261,7 +330,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         if (STEP) {
             const int ai = action / 3, wi = action - 3 * ai;
             const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
-            const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+            const double dis_before = fast_sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
             auto substeps = [&](auto with_traj) {
                 double* ptraj = decltype(with_traj)::value ? P.traj + e : nullptr;
                 for (int it = 0; it < K.n_substeps; ++it) {
@@ -294,7 +363,8 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 }
             };
             if (P.traj != nullptr) substeps(std::true_type{}); else substeps(std::false_type{});
-            dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+            dis_after2 = fma(gx - x, gx - x, (gy - y) * (gy - y));
+            dis_after = fast_sqrt(dis_after2);
             reward = K.pen_step + (dis_before - dis_after);   // marinenav_env.py:220,229
         } else {
             if (K.velocity_from_state) {
@@ -322,88 +392,105 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             bs2 = fabsf(u2 - n2) < K.snap_tol ? (int)n2 : -1;
         }
 
-        // ---- obstacles -> robot frame, fp32 pairs for the candidate filter.  q is pre-multiplied by sigma = +1 (robot
-        //      outside the circle) or -1 (inside) so that "the nearer root can be in front" reads tc >= 0 in both cases;
-        //      nr2 = -(r^2 + 1e-3), or +1e30 for empty slots and obstacles that cannot be reached within the sonar range
-        //      (discriminant test always fails). ----
+        // ---- obstacles: nearest centre (Q4) and the set within sonar reach.  Only an obstacle with |centre - pos| <=
+        //      range + r can return a hit (the hit distance is >= d - r), so everything below looks at those alone. ----
         if (use_tma) mbar_wait(my_bar, 0); else cp_async_wait_all();
         const double* ob = s_ob + tid;
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            double r = -1.0, ox = 0.0, oy = 0.0;
+            if (j < max_o) { ox = ob[j * kBlock]; oy = ob[(max_o + j) * kBlock]; r = ob[(2 * max_o + j) * kBlock]; }
+            const double dx = ox - x, dy = oy - y;
+            const double d2 = fma(dx, dx, dy * dy);
+            const bool on = r > 0.0;
+            if (on && d2 < best_d2) { best_d2 = d2; best_r = r; }
+            const double lim = K.range_slack + r;
+            if (on && d2 <= lim * lim) rel |= 1u << j;
+        }
+
+        // ---- sonar binning, obstacle-major (robot.py:125-198).  In the robot frame the beams are the fixed directions
+        //      beta_b = beta_0 + b * spacing, and the beams on which obstacle j can return a hit form ONE interval of beam
+        //      indices: with q = R^T (centre - pos), d = |q|,
+        //        robot outside the circle: real roots and the nearer root in front  <=>  |beta_b - atan2(q)| < asin(r / d);
+        //        robot inside:  the nearer root is in front iff q . dir <= 0        <=>  |beta_b - atan2(-q)| <= pi / 2.
+        //      The interval is computed conservatively in fp32 (radius inflated by 1e-3 m, half-width by 2e-4 rad + the
+        //      approximation errors of atan2_approx / asin_approx, bounds rounded outwards by 1e-3 index units), so it can
+        //      only add beams, never lose one; every flagged (env, beam) is then decided EXACTLY in fp64 below.  A robot
+        //      within fp32 resolution of the circle line, or within 1 m of the centre of a circle it is inside of, flags
+        //      every beam.  Geometries whose intervals could wrap around (field of view >= pi, or more than 16 beams)
+        //      flag every beam of every obstacle within reach (K.precise_bins = 0). ----
         {
             const float cf = (float)c, sf = (float)s;
-            const f32x2 c2 = pack2(cf, cf), s2 = pack2(sf, sf), ns2 = pack2(-sf, -sf);
+            const unsigned all_beams = K.n_beams >= 32 ? 0xffffffffu : ((1u << K.n_beams) - 1u);
+            unsigned short* my_bm = s_bm + tid * kBmStride;
 #pragma unroll
-            for (int jj = 0; jj < MAXO / 2; ++jj) {
-                float dxf[2], dyf[2], nrf[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = 2 * jj + h;
-                    double r = -1.0, ox = 0.0, oy = 0.0;
-                    if (j < max_o) { ox = ob[j * kBlock]; oy = ob[(max_o + j) * kBlock]; r = ob[(2 * max_o + j) * kBlock]; }
-                    const double dx = ox - x, dy = oy - y;
-                    const bool on = r > 0.0;
-                    const double d2 = fma(dx, dx, dy * dy);
-                    const double rr = r * r, lim = K.range_slack + r;
-                    if (on && d2 < best_d2) { best_d2 = d2; best_r = r; }
-                    force_slow |= on && (fabs(d2 - rr) <= 1e-9 * rr);
-                    const float sg = d2 < rr ? -1.0f : 1.0f;
-                    dxf[h] = sg * (float)dx; dyf[h] = sg * (float)dy;
-                    nrf[h] = (on && d2 <= lim * lim) ? -((float)rr + 1e-3f) : 1e30f;
+            for (int j4 = 0; j4 < kBmStride / 8; ++j4) reinterpret_cast<uint4*>(my_bm)[j4] = make_uint4(0u, 0u, 0u, 0u);
+            s_rel[tid] = rel;
+            if (!K.precise_bins) beams = rel != 0u ? 0xffffffffu : 0u;
+            else {
+                unsigned todo = rel;
+                while (todo != 0u) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const float dxf = (float)(ob[j * kBlock] - x), dyf = (float)(ob[(max_o + j) * kBlock] - y);
+                    const float rf = (float)ob[(2 * max_o + j) * kBlock];
+                    float qx = fmaf(cf, dxf, sf * dyf), qy = fmaf(cf, dyf, -sf * dxf);      // R^T (centre - pos)
+                    const float d2f = fmaf(qx, qx, qy * qy), rrf = rf * rf;
+                    unsigned bm = all_beams;
+                    const bool inside = d2f < rrf;
+                    if (fabsf(d2f - rrf) > 2e-3f * fmaxf(1.0f, rrf) && !(inside && d2f < 1.0f)) {
+                        float alpha = 1.57079632679f + 2e-3f;                               // inside: the half plane q . dir <= 1e-3
+                        if (inside) { qx = -qx; qy = -qy; }
+                        else alpha = asin_approx(fminf(1.0f, (rf + 1e-3f) * rsqrtf(d2f))) + 4e-4f;
+                        const float ci = (atan2_approx(qy, qx) - K.beam0f) * K.inv_phi;
+                        const float wi = fmaf(alpha, K.inv_phi, 1e-3f);
+                        const int lo = max(0, (int)ceilf(ci - wi)), hi = min(K.n_beams - 1, (int)floorf(ci + wi));
+                        bm = lo <= hi ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+                    }
+                    my_bm[j] = (unsigned short)bm;
+                    beams |= bm;
                 }
-                const f32x2 dx2 = pack2(dxf[0], dxf[1]), dy2 = pack2(dyf[0], dyf[1]);
-                qx2[jj] = fma2(c2, dx2, mul2(s2, dy2));          // R^T (centre - pos), fp32 (error ~1e-5 << the 1e-3 margin)
-                qy2[jj] = fma2(c2, dy2, mul2(ns2, dx2));
-                nr2[jj] = pack2(nrf[0], nrf[1]);
+                if (rel != 0u) {                            // a beam that may be snapped to the vertical (Q10) is decided exactly
+                    if (bs1 >= 0 && bs1 < K.n_beams) beams |= 1u << bs1;
+                    if (bs2 >= 0 && bs2 < K.n_beams) beams |= 1u << bs2;
+                }
             }
+            // "no return" everywhere (marinenav_env.py:318-320); the exact tests overwrite the beams that hit
+            for (int b = 0; b < K.n_beams; ++b) *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);
         }
     }
 
     // ================= sonar (robot.py:125-198), warp-wide =================
-    // Per (environment, beam): a conservative candidate filter in fp32 (no sqrt): "real roots and the nearer root not behind
-    // the robot" with a 1e-3 margin, >= 30x the fp32 rounding error of these expressions near the decision boundary
-    // (|q| <= range + r); two obstacles per FFMA2; bit j of m <=> obstacle j is a candidate: cr^2 - r^2 - 1e-3 < 0 and
-    // tc + 1e-3 >= 0.  Every (environment, beam) with a candidate is then decided EXACTLY in fp64, so the filter can only
-    // cost time, never a result.  Few lanes have a candidate on a given beam (~1.5 of 32), but most beams have one in some
-    // lane, so the exact tests are not run in place: they are pushed to a per-warp ring in shared memory and drained 32 at
-    // a time with every lane busy -- the fp64 square-root chain is walked ~once per warp and step instead of ~7 times.
+    // Few (env, beam) pairs are flagged (~1.5 lanes of 32 per beam), so the exact fp64 tests are not run in place: every lane
+    // appends its flagged beams to a per-warp list in shared memory (slots from a warp prefix sum of the per-lane counts) and
+    // the list is evaluated 32 entries at a time with every lane busy -- the evaluator fetches the owner's pose with
+    // shuffles, the owner's obstacles and beam masks from shared memory, runs the reference's ordered scan (Q3) over the
+    // obstacles whose interval contains the beam and writes the hit into the owner's observation row.
     {
-        const f32x2 margin2 = pack2(1e-3f, 1e-3f);
         const double* obw = s_ob + w0;                          // obstacle columns of this warp's environments
-        const unsigned lt_mask = (1u << lane) - 1u;
-        int n_pend = 0, head = 0;                               // warp-uniform ring state
         const int n_beams = K.n_beams;
-        for (int b = 0;; ++b) {
-            const bool last = b >= n_beams;
-            if (!last) {
-                const float2 bd = K.beam_dirf[b];
-                const f32x2 bx2 = pack2(bd.x, bd.x), by2 = pack2(bd.y, bd.y), nby2 = pack2(-bd.y, -bd.y);
-                unsigned m = 0;
+        for (int b0 = 0; b0 < n_beams; b0 += kBeamWord) {       // one pass for <= 16 beams
+            unsigned mine_beams = K.precise_bins ? beams : (beams != 0u ? (n_beams - b0 >= kBeamWord ? 0xffffu : (1u << (n_beams - b0)) - 1u) : 0u);
+            const int cnt = __popc(mine_beams);
+            int incl = cnt;
 #pragma unroll
-                for (int jj = MAXO / 2 - 1; jj >= 0; --jj) {
-                    const f32x2 tc = fma2(qx2[jj], bx2, fma2(qy2[jj], by2, margin2));
-                    const f32x2 ncr = fma2(qy2[jj], bx2, mul2(qx2[jj], nby2));
-                    const f32x2 nd = fma2(ncr, ncr, nr2[jj]);
-                    unsigned tlo, thi, dlo, dhi;
-                    unpack2(tc, tlo, thi); unpack2(nd, dlo, dhi);
-                    m = __funnelshift_l(dhi & ~thi, m, 1);       // sign bit of (nd < 0 && tc >= 0) shifted in: obstacle 2jj+1
-                    m = __funnelshift_l(dlo & ~tlo, m, 1);       // obstacle 2jj
-                }
-                const bool maybe_snap = (b == bs1) || (b == bs2);
-                const bool pend = live && (m != 0u || force_slow || maybe_snap);
-                const unsigned bal = __ballot_sync(0xffffffffu, pend);
-                if (pend)      // ring entry: [4:0] owner lane, [12:5] beam, [13] Q10 candidate, [14] exact-only, [31:16] candidate mask
-                    ring[(head + n_pend + __popc(bal & lt_mask)) & (kRing - 1)] =
-                        (unsigned)lane | ((unsigned)b << 5) | (maybe_snap ? 1u << 13 : 0u) | (force_slow ? 1u << 14 : 0u) | (m << 16);
-                else if (live)
-                    *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);   // no return (marinenav_env.py:318-320)
-                n_pend += __popc(bal);
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
             }
-            if (n_pend >= 32 || (last && n_pend > 0)) {
-                __syncwarp();                                    // ring entries of other lanes are visible
-                const int n_now = n_pend < 32 ? n_pend : 32;
-                const bool mine = lane < n_now;
-                const unsigned ent = mine ? ring[(head + lane) & (kRing - 1)] : (unsigned)lane;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;                           // warp-uniform
+            int slot = incl - cnt;
+            while (mine_beams != 0u) {                          // list entry: [4:0] owner lane, [12:5] beam, [13] Q10 candidate
+                const int b = b0 + __ffs(mine_beams) - 1;
+                mine_beams &= mine_beams - 1u;
+                ring[slot++] = (unsigned short)((unsigned)lane | ((unsigned)b << 5) | (((b == bs1) || (b == bs2)) ? 1u << 13 : 0u));
+            }
+            __syncwarp();                                       // list entries, masks and zero-filled rows of other lanes are visible
+            for (int base = 0; base < total; base += 32) {
+                const bool mine = base + lane < total;
+                const unsigned ent = mine ? ring[base + lane] : (unsigned)lane;
                 const int owner = ent & 31, bb = (ent >> 5) & 0xff;
-                const unsigned m = ent >> 16;
                 // the owner's pose after the sub-steps
                 const double ox_ = __shfl_sync(0xffffffffu, x, owner), oy_ = __shfl_sync(0xffffffffu, y, owner);
                 const double oc = __shfl_sync(0xffffffffu, c, owner), os = __shfl_sync(0xffffffffu, s, owner);
@@ -411,44 +498,55 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 if (mine) {
                     const double* ob = obw + owner;
                     double bx = K.beam_cos[bb], by = K.beam_sin[bb];    // beam direction in the robot frame
-                    bool scan_all = (ent & (1u << 14)) != 0u;
+                    bool scan_all = !K.precise_bins;
                     if (ent & (1u << 13)) {
                         const double ang = oth + K.beam_angle[bb];       // robot.py:131 (not wrapped)
                         if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = os; by = oc; scan_all = true; }            // Q10: exactly (0,+1) in the world frame
                         else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -os; by = -oc; scan_all = true; }     // Q10: exactly (0,-1)
                     }
-                    // the reference's ordered scan (Q3, robot.py:149-195) over the candidates in list order; for the usual
-                    // single candidate this is one pass
-                    unsigned mm = scan_all ? ((1u << max_o) - 1u) : m;
+                    // obstacles whose beam interval contains this beam (all obstacles within reach for a snapped beam, whose
+                    // direction is not the table's), in list order
+                    unsigned mm = s_rel[w0 + owner];
+                    if (!scan_all) {
+                        const unsigned short* bm = s_bm + (w0 + owner) * kBmStride;
+                        unsigned m = 0u;
+#pragma unroll
+                        for (int j4 = 0; j4 < kBmStride / 8; ++j4) {
+                            const uint4 v = reinterpret_cast<const uint4*>(bm)[j4];
+                            const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                m |= ((wv[q] >> bb) & 1u) << (8 * j4 + 2 * q);
+                                m |= ((wv[q] >> (16 + bb)) & 1u) << (8 * j4 + 2 * q + 1);
+                            }
+                        }
+                        mm = m;
+                    }
+                    // the reference's ordered scan (Q3, robot.py:149-195) over those obstacles; usually one pass
                     bool hit = false;
                     double best = INFINITY;
                     while (mm != 0u) {
                         const int j = __ffs(mm) - 1;
                         mm &= mm - 1u;
                         const double r = ob[(2 * max_o + j) * kBlock];
-                        if (!(r > 0.0)) continue;
                         const double dx = ob[j * kBlock] - ox_, dy = ob[(max_o + j) * kBlock] - oy_;
                         const double ax = fma(oc, dx, os * dy), ay = fma(oc, dy, -os * dx);
                         const double tc = fma(ax, bx, ay * by);
                         const double cr = fma(ax, by, -ay * bx);
                         const double disc = fma(-cr, cr, r * r);
                         if (disc < 0.0) continue;                    // robot.py:172-174
-                        const double hh = sqrt(disc);
+                        const double hh = fast_sqrt(disc);
                         const double tj = tc > 0.0 ? tc - hh : tc + hh;   // nearer root first (robot.py:184)
                         if (fabs(tj) > K.range) continue;            // robot.py:185-187
                         if (tj < 0.0) continue;                      // robot.py:188-190
                         if (hit && tj >= best) break;                // robot.py:192-195
                         best = tj; hit = true;
                     }
-                    float2 o2;                                        // marinenav_env.py:314-320
-                    o2.x = hit ? (float)(best * bx) : 0.0f;
-                    o2.y = hit ? (float)(best * by) : 0.0f;
-                    *reinterpret_cast<float2*>(s_obs + (w0 + owner) * D + 4 + 2 * bb) = o2;   // rows are 8-byte aligned (obs_dim is even)
+                    if (hit)                                          // marinenav_env.py:314-317 (rows are 8-byte aligned: obs_dim is even)
+                        *reinterpret_cast<float2*>(s_obs + (w0 + owner) * D + 4 + 2 * bb) = make_float2((float)(best * bx), (float)(best * by));
                 }
-                head += n_now; n_pend -= n_now;
-                __syncwarp();                                    // ring slots may be overwritten by the next pushes
             }
-            if (last) break;
+            __syncwarp();                                       // the list is rewritten by the next pass
         }
     }
 
@@ -459,7 +557,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
         else if (ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
         else if (collides(best_d2, best_r + K.robot_r)) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
-        else if (dis_after <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }   // same norm as the reward's (marinenav_env.py:270,340)
+        else if (reaches(dis_after2, K.goal_dis)) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }   // marinenav_env.py:338-342, decided on the squares
         P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = sp;
         P.velocity[e] = vx; P.velocity[E + e] = vy;
         P.ep_step[e] = ep + 1;                                // marinenav_env.py:259
@@ -793,9 +891,11 @@ int launch_env(const EnvPtrs& P, const KParams& K, cudaStream_t st)
         return mnv_launch_status(STEP ? "mnv_step(dense)" : "mnv_observe(dense)");
     }
     const unsigned grid = (unsigned)((K.E + kBlock - 1) / kBlock);
-    const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + 8 * (kBlock / 32) + (size_t)(kBlock / 32) * kRing * sizeof(unsigned);
 #define MNV_LAUNCH(MC, MO)                                                                                   \
     do {                                                                                                     \
+        const size_t smem = (size_t)((kBlock * K.obs_dim + 3) & ~3) * sizeof(float) + (size_t)3 * K.max_o * kBlock * sizeof(double) + \
+                            8 * (kBlock / 32) + (size_t)(kBlock / 32) * kRing * sizeof(unsigned short) +    \
+                            (size_t)kBlock * ((MO + 7) & ~7) * sizeof(unsigned short) + (size_t)kBlock * sizeof(unsigned); \
         auto kern = (STEP && K.pdl_prefetch) ? mnv_env_kernel<MC, MO, STEP, STEP> : mnv_env_kernel<MC, MO, STEP, false>; \
         if (smem > 48 * 1024) {                                                                              \
             cudaError_t a = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -848,6 +948,8 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
     }
     K.snap_t1 = 0.5 * MNV_PI - a0; K.snap_t2 = 1.5 * MNV_PI - a0;      // Q10 pre-test (see the kernel)
     K.inv_phi = (float)(1.0 / phi); K.snap_tol = (float)(1e-3 / phi + 1e-4);
+    K.beam0f = (float)a0;
+    K.precise_bins = (p->n_beams <= 16 && p->sonar_angle < MNV_PI - 0.01 && p->sonar_angle > 0.0) ? 1 : 0;
     return 0;
 }
 

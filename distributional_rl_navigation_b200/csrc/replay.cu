@@ -34,7 +34,7 @@ __device__ __forceinline__ void copy_row(float* __restrict__ dst, const float* _
 __global__ void __launch_bounds__(kWarps * 32)
 rpl_append_kernel(Ring R, long long pos, const float* __restrict__ obs, const int32_t* __restrict__ action,
                   const float* __restrict__ reward, const float* __restrict__ next_obs, const uint8_t* __restrict__ done,
-                  long long E, int row_len, int n_step, float gamma, long long t,
+                  long long E, int row_len, int n_step, double gamma, long long t,
                   float* __restrict__ win_obs, int32_t* __restrict__ win_action, float* __restrict__ win_reward)
 {
     const int lane = threadIdx.x & 31;
@@ -59,7 +59,7 @@ rpl_append_kernel(Ring R, long long pos, const float* __restrict__ obs, const in
             const long long slot = (old + i) % n_step;
             const float r = (slot == cur) ? reward[e] : win_reward[slot * E + e];
             ret += g * (double)r;
-            g *= (double)gamma;
+            g *= gamma;
         }
     }
     const long long slot = (pos + e) % R.capacity;
@@ -156,7 +156,7 @@ int check_ring(const char* fn, const float* s, const int64_t* a, const float* r,
 
 extern "C" int rpl_append(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
                           int64_t capacity, int64_t pos, const float* d_obs, const int32_t* d_action, const float* d_reward,
-                          const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, float gamma,
+                          const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
                           int64_t t, float* d_win_obs, int32_t* d_win_action, float* d_win_reward, void* stream)
 {
     int rc = check_ring("rpl_append", d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, row_len);

@@ -151,7 +151,7 @@ int mnv_scatter_rows_host(const uint8_t* d_mask, const float* d_rows, float* h_r
  * (pos + e) mod capacity.  Like the reference, the window is NOT cleared at episode ends. */
 int rpl_append(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
                int64_t capacity, int64_t pos, const float* d_obs, const int32_t* d_action, const float* d_reward,
-               const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, float gamma,
+               const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
                int64_t t, float* d_win_obs, int32_t* d_win_action, float* d_win_reward, void* stream);
 
 /* ReplayBuffer.sample (replay_buffer.py:45-55): B picks among the `size` stored transitions, gathered into

@@ -96,7 +96,10 @@ def test_unmodified_driver_trains_end_to_end(tmp_path, golden_dir):
               "adaptive_evaluations.npz", "network_params.pth", "constructor_params.json"):
         assert (d / f).is_file(), f
     with open(d / "eval_config.json") as f, open(os.path.join(golden_dir, "eval_config.json")) as g:
-        assert json.load(f) == json.load(g)
+        mine, shipped = json.load(f), json.load(g)
+    for c in mine.values():                 # episode_data() of the current reference also records the (empty) trajectory
+        assert c["robot"].pop("trajectory") == []     # (marinenav_env.py:620); the shipped file predates that key
+    assert mine == shipped
     ev = np.load(d / "greedy_evaluations.npz", allow_pickle=True)
     assert ev["timesteps"].tolist() == [10000] and ev["actions"].shape[:2] == (1, 30) and ev["rewards"].shape == (1, 30)
     assert "++++++++ Evaluation info (adaptive IQN) ++++++++" in r.stdout and "======== training info ========" in r.stdout
