@@ -4,6 +4,17 @@
 // (key u32 [E][624]: one contiguous 2.5 KB record per environment, staged through shared memory; pos i32 [E]).  The draw
 // order and the arithmetic (separately rounded * and +, IEEE sqrt and /) follow the reference exactly, so environment e
 // reproduces MarineNavEnv(seed=s_e).reset() bit-for-bit: this file MUST be compiled with -fmad=false.
+//
+// SPECULATIVE REJECTION SAMPLING.  The reference's three sampling loops (start/goal :114-127, cores :130-143, obstacles
+// :158-169) draw a FIXED number of stream words per candidate (8 / 8 / 6) whether or not the candidate is accepted, so
+// candidate k of a loop is a pure function of the stream words [pos + k w, pos + (k + 1) w).  The warp therefore evaluates
+// up to 32 consecutive candidates at once, one per lane: draws, map-bound / clearance tests and the tests against
+// everything accepted before the batch run in parallel; only the dependence on candidates accepted INSIDE the batch is
+// resolved in order (first surviving lane is accepted, later lanes test against it, repeat).  The stream position then
+// advances by exactly the candidates the sequential loop would have consumed.  A batch never reads past the end of the
+// current MT19937 block; the one candidate that straddles a regeneration is evaluated on its own.  Same candidates, same
+// arithmetic per candidate, same accept decisions -> bit-identical maps, ~12 dependent rounds instead of ~30 serial
+// candidates with several square-root chains each.
 // A persistent grid of warps scans the done flags in contiguous chunks, so a masked launch with a few finished
 // environments costs one flag scan plus ~one reset latency.
 #include <math.h>
@@ -61,14 +72,23 @@ struct Mt {
         y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
         return y;
     }
-    // RandomState.random_sample: 53-bit double
-    __device__ double sample()
+    __device__ static uint32_t temper(uint32_t y)
     {
-        const uint32_t a = next32() >> 5, b = next32() >> 6;
-        return (a * 67108864.0 + b) / 9007199254740992.0;
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
     }
+    // RandomState.random_sample from two consecutive outputs: (a * 2^26 + b) / 2^53 -- the division by a power of two is
+    // exact, so multiplying by 2^-53 gives the identical double
+    __device__ static double to_sample(uint32_t t0, uint32_t t1)
+    {
+        const uint32_t a = t0 >> 5, b = t1 >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    __device__ double sample() { const uint32_t t0 = next32(), t1 = next32(); return to_sample(t0, t1); }
     // RandomState.uniform(lo, hi) = lo + (hi - lo) * U
-    __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * sample(); }
+    __device__ static double uni(double lo, double hi, double u) { return lo + (hi - lo) * u; }
+    // sample j of the candidate that starts `word` words after the current position (no regeneration: caller stays in the block)
+    __device__ double peek(int word, int j) const { return to_sample(temper(mt[pos + word + 2 * j]), temper(mt[pos + word + 2 * j + 1])); }
 };
 
 __global__ void __launch_bounds__(kBlock) mnv_seed_kernel(uint32_t* key, int32_t* pos, const uint32_t* seeds, long long E)
@@ -143,98 +163,159 @@ mnv_reset_kernel(const ResetPtrs P, const mnv_reset_params R, long long E, int m
                 // NaN start in the parameter block = "keep the per-environment start / goal already in the tables"
                 sx = P.start_pose[e]; sy = P.start_pose[E + e]; gx = P.goal[e]; gy = P.goal[E + e];
             }
+            // One batch of candidates: lane k < n holds candidate k of the loop, u[] = its uniform samples in draw order.
+            // n = how many whole candidates the current MT19937 block still holds (<= 32, <= iterations left); when the next
+            // candidate straddles a regeneration it is drawn word by word (all lanes, uniform) and forms a batch of one whose
+            // words are already consumed (returns true).
+            auto draw_batch = [&](int words, int iterations_left, int& n, double (&u)[4]) -> bool {
+                if (rd.pos >= kMtN) rd.regenerate();                         // block exhausted: the next one (warp-uniform)
+                n = (kMtN - rd.pos) / words;
+                n = n < 32 ? n : 32;
+                n = n < iterations_left ? n : iterations_left;
+                if (n == 0) {
+                    for (int j = 0; j < words / 2; ++j) u[j] = rd.sample();
+                    n = 1;
+                    return true;
+                }
+                if (lane < n)
+                    for (int j = 0; j < words / 2; ++j) u[j] = rd.peek(lane * words, j);
+                return false;
+            };
+
             if (R.reset_start_and_goal) {                                    // marinenav_env.py:112-127
+                // the loop keeps the farthest pair seen and stops at the first candidate farther apart than
+                // min_start_goal_dis (every earlier one was not) or after 500 candidates
                 int iteration = 500; double max_dist = 0.0;
-                for (;;) {
-                    const double s0 = rd.uniform(2.0, R.width - 2.0), s1 = rd.uniform(2.0, R.height - 2.0);
-                    const double g0 = rd.uniform(2.0, R.width - 2.0), g1 = rd.uniform(2.0, R.height - 2.0);
-                    iteration -= 1;
-                    const double d = dist2d(g0, g1, s0, s1);
-                    if (d > max_dist) { max_dist = d; sx = s0; sy = s1; gx = g0; gy = g1; }
-                    if (max_dist > R.min_start_goal_dis || iteration == 0) break;
+                while (iteration > 0) {
+                    int n; double u[4];
+                    const bool consumed = draw_batch(8, iteration, n, u);
+                    double s0 = 0, s1 = 0, g0 = 0, g1 = 0, d = -1.0;
+                    if (lane < n) {
+                        s0 = Mt::uni(2.0, R.width - 2.0, u[0]); s1 = Mt::uni(2.0, R.height - 2.0, u[1]);
+                        g0 = Mt::uni(2.0, R.width - 2.0, u[2]); g1 = Mt::uni(2.0, R.height - 2.0, u[3]);
+                        d = dist2d(g0, g1, s0, s1);
+                    }
+                    // the loop ends at the first candidate k whose running maximum max(max_dist, d_0 .. d_k) exceeds
+                    // min_start_goal_dis; m = candidates consumed
+                    unsigned far = __ballot_sync(0xffffffffu, lane < n && d > R.min_start_goal_dis);
+                    if (max_dist > R.min_start_goal_dis) far |= 1u;          // (only reachable with a negative threshold)
+                    const int m = far != 0u ? __ffs(far) : n;
+                    // running maximum over the consumed candidates: the FIRST one holding the largest distance, if it
+                    // exceeds the carried maximum (strict >, like the reference's update)
+                    double best = lane < m ? d : -1.0; int who = lane;
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double od = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int ow = __shfl_xor_sync(0xffffffffu, who, off);
+                        if (od > best || (od == best && ow < who)) { best = od; who = ow; }
+                    }
+                    if (best > max_dist) {
+                        max_dist = best;
+                        sx = __shfl_sync(0xffffffffu, s0, who); sy = __shfl_sync(0xffffffffu, s1, who);
+                        gx = __shfl_sync(0xffffffffu, g0, who); gy = __shfl_sync(0xffffffffu, g1, who);
+                    }
+                    if (!consumed) rd.pos += m * 8;
+                    iteration -= m;
+                    if (far != 0u) break;
                 }
             }
 
             int nc = 0;
-            int num_cores = R.num_cores;
-            if (num_cores > 0) {                                             // marinenav_env.py:130-143
-                int iteration = 500;
-                for (;;) {
-                    const double x = rd.uniform(0.0, R.width), y = rd.uniform(0.0, R.height);
-                    const int clockwise = rd.sample() > 0.5 ? 1 : 0;         // binomial(1, 0.5): inversion, one draw
-                    const double v_edge = rd.uniform(R.v_range[0], R.v_range[1]);
-                    const double Gamma = kTwoPi * R.core_r * v_edge;
-                    iteration -= 1;
-                    // check_core, marinenav_env.py:344-383 (the y test uses width, sic)
-                    bool ok = !(x - R.core_r < 0.0 || x + R.core_r > R.width) && !(y - R.core_r < 0.0 || y + R.core_r > R.width);
-                    ok = ok && !(dist2d(x, y, sx, sy) < R.core_r + R.clear_r) && !(dist2d(x, y, gx, gy) < R.core_r + R.clear_r);
-                    // pairwise constraints against the accepted cores: lane i checks core i (same arithmetic per pair as the
-                    // reference's loop, marinenav_env.py:361-381), the verdict is a warp vote
-                    {
-                        bool fail = false;
-                        if (ok && lane < nc) {
-                            const int i = lane;
-                            const double dx = S.cx[i] - x, dy = S.cy[i] - y;
-                            const double dis = sqrt(dx * dx + dy * dy);
-                            if (S.ccw[i] == clockwise) {
-                                const double bi = S.cG[i] / (kTwoPi * R.v_rel_max), bj = Gamma / (kTwoPi * R.v_rel_max);
-                                if (dis < bi + bj) fail = true;
-                            } else {
-                                const double Gl = S.cG[i] > Gamma ? S.cG[i] : Gamma, Gs = S.cG[i] < Gamma ? S.cG[i] : Gamma;
-                                const double v1 = Gl / (kTwoPi * (dis - 2 * R.core_r));      // Q7: negative when dis < 2r -> accepted
-                                const double v2 = Gs / (kTwoPi * R.core_r);
-                                if (v1 > R.p * v2) fail = true;
-                            }
-                        }
-                        ok = ok && !__any_sync(0xffffffffu, fail);
+            if (R.num_cores > 0) {                                           // marinenav_env.py:130-143
+                int iteration = 500, need = R.num_cores;
+                // check_core's pairwise rule (marinenav_env.py:361-381): existing core i against the new core (x, y, cw, Gamma)
+                auto core_conflict = [&](int i, double x, double y, int clockwise, double Gamma) -> bool {
+                    const double dx = S.cx[i] - x, dy = S.cy[i] - y;
+                    const double dis = sqrt(dx * dx + dy * dy);
+                    if (S.ccw[i] == clockwise) {
+                        const double bi = S.cG[i] / (kTwoPi * R.v_rel_max), bj = Gamma / (kTwoPi * R.v_rel_max);
+                        return dis < bi + bj;
                     }
-                    if (ok) {
-                        __syncwarp();
-                        if (lane == 0) { S.cx[nc] = x; S.cy[nc] = y; S.cG[nc] = Gamma; S.ccw[nc] = clockwise; }
-                        __syncwarp();
-                        ++nc; num_cores -= 1;
+                    const double Gl = S.cG[i] > Gamma ? S.cG[i] : Gamma, Gs = S.cG[i] < Gamma ? S.cG[i] : Gamma;
+                    const double v1 = Gl / (kTwoPi * (dis - 2 * R.core_r));          // Q7: negative when dis < 2r -> accepted
+                    const double v2 = Gs / (kTwoPi * R.core_r);
+                    return v1 > R.p * v2;
+                };
+                while (iteration > 0 && need > 0) {
+                    int n; double u[4];
+                    const bool consumed = draw_batch(8, iteration, n, u);
+                    double x = 0, y = 0, Gamma = 0; int clockwise = 0;
+                    bool alive = lane < n;
+                    if (alive) {
+                        x = Mt::uni(0.0, R.width, u[0]); y = Mt::uni(0.0, R.height, u[1]);
+                        clockwise = u[2] > 0.5 ? 1 : 0;                      // binomial(1, 0.5): inversion, one draw
+                        const double v_edge = Mt::uni(R.v_range[0], R.v_range[1], u[3]);
+                        Gamma = kTwoPi * R.core_r * v_edge;
+                        // check_core, marinenav_env.py:344-383 (the y test uses width, sic)
+                        alive = !(x - R.core_r < 0.0 || x + R.core_r > R.width) && !(y - R.core_r < 0.0 || y + R.core_r > R.width);
+                        alive = alive && !(dist2d(x, y, sx, sy) < R.core_r + R.clear_r) && !(dist2d(x, y, gx, gy) < R.core_r + R.clear_r);
+                        for (int i = 0; alive && i < nc; ++i) alive = !core_conflict(i, x, y, clockwise, Gamma);   // cores of earlier batches
                     }
-                    if (iteration == 0 || num_cores == 0) break;
+                    int m = n;
+                    for (;;) {                                               // resolve the batch in candidate order
+                        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                        if (bal == 0u) break;
+                        const int f = __ffs(bal) - 1;                        // the next candidate the sequential loop accepts
+                        const double ax = __shfl_sync(0xffffffffu, x, f), ay = __shfl_sync(0xffffffffu, y, f);
+                        const double aG = __shfl_sync(0xffffffffu, Gamma, f);
+                        const int acw = __shfl_sync(0xffffffffu, clockwise, f);
+                        __syncwarp();
+                        if (lane == 0) { S.cx[nc] = ax; S.cy[nc] = ay; S.cG[nc] = aG; S.ccw[nc] = acw; }
+                        __syncwarp();
+                        ++nc; --need;
+                        if (need == 0) { m = f + 1; break; }
+                        alive = alive && lane > f && !core_conflict(nc - 1, x, y, clockwise, Gamma);
+                    }
+                    if (!consumed) rd.pos += m * 8;
+                    iteration -= m;
                 }
             }
 
             int no = 0;
-            int num_obs = R.num_obs;
-            if (num_obs > 0) {                                               // marinenav_env.py:158-169
-                int iteration = 500;
-                for (;;) {
-                    const double x = rd.uniform(5.0, R.width - 5.0), y = rd.uniform(5.0, R.height - 5.0);
-                    const double r = rd.uniform(R.obs_r_range[0], R.obs_r_range[1]);
-                    iteration -= 1;
-                    // check_obstacle, marinenav_env.py:385-420
-                    bool ok = !(x - r < 0.0 || x + r > R.width) && !(y - r < 0.0 || y + r > R.height);
-                    ok = ok && !(dist2d(x, y, sx, sy) < r + R.clear_r) && !(dist2d(x, y, gx, gy) < r + R.clear_r);
-                    {   // lane i checks vortex core i and obstacle i (marinenav_env.py:402-418), warp vote
-                        bool fail = false;
-                        if (ok && lane < nc) {
-                            const double dx = S.cx[lane] - x, dy = S.cy[lane] - y;
-                            if (sqrt(dx * dx + dy * dy) <= R.core_r + r) fail = true;
+            if (R.num_obs > 0) {                                             // marinenav_env.py:158-169
+                int iteration = 500, need = R.num_obs;
+                while (iteration > 0 && need > 0) {
+                    int n; double u[4];
+                    const bool consumed = draw_batch(6, iteration, n, u);
+                    double x = 0, y = 0, r = 0;
+                    bool alive = lane < n;
+                    if (alive) {
+                        x = Mt::uni(5.0, R.width - 5.0, u[0]); y = Mt::uni(5.0, R.height - 5.0, u[1]);
+                        r = Mt::uni(R.obs_r_range[0], R.obs_r_range[1], u[2]);
+                        // check_obstacle, marinenav_env.py:385-420
+                        alive = !(x - r < 0.0 || x + r > R.width) && !(y - r < 0.0 || y + r > R.height);
+                        alive = alive && !(dist2d(x, y, sx, sy) < r + R.clear_r) && !(dist2d(x, y, gx, gy) < r + R.clear_r);
+                        for (int i = 0; alive && i < nc; ++i) {              // every vortex core (marinenav_env.py:402-408)
+                            const double dx = S.cx[i] - x, dy = S.cy[i] - y;
+                            alive = !(sqrt(dx * dx + dy * dy) <= R.core_r + r);
                         }
-                        if (ok && lane < no) {
-                            const double dx = S.ox[lane] - x, dy = S.oy[lane] - y;
-                            if (sqrt(dx * dx + dy * dy) <= S.orr[lane] + r) fail = true;
+                        for (int i = 0; alive && i < no; ++i) {              // obstacles of earlier batches (:410-418)
+                            const double dx = S.ox[i] - x, dy = S.oy[i] - y;
+                            alive = !(sqrt(dx * dx + dy * dy) <= S.orr[i] + r);
                         }
-                        ok = ok && !__any_sync(0xffffffffu, fail);
                     }
-                    if (ok) {
+                    int m = n;
+                    for (;;) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                        if (bal == 0u) break;
+                        const int f = __ffs(bal) - 1;
+                        const double ax = __shfl_sync(0xffffffffu, x, f), ay = __shfl_sync(0xffffffffu, y, f), ar = __shfl_sync(0xffffffffu, r, f);
                         __syncwarp();
-                        if (lane == 0) { S.ox[no] = x; S.oy[no] = y; S.orr[no] = r; }
+                        if (lane == 0) { S.ox[no] = ax; S.oy[no] = ay; S.orr[no] = ar; }
                         __syncwarp();
-                        ++no; num_obs -= 1;
+                        ++no; --need;
+                        if (need == 0) { m = f + 1; break; }
+                        const double dx = ax - x, dy = ay - y;               // existing obstacle (ax, ay, ar) against the candidate
+                        alive = alive && lane > f && !(sqrt(dx * dx + dy * dy) <= ar + r);
                     }
-                    if (iteration == 0 || num_obs == 0) break;
+                    if (!consumed) rd.pos += m * 6;
+                    iteration -= m;
                 }
             }
 
             double th0 = R.init_theta, sp0 = R.init_speed;                    // reset_robot, marinenav_env.py:188-197
             if (R.random_reset_state) {
-                th0 = rd.uniform(0.0, kTwoPi);
-                sp0 = rd.uniform(0.0, R.max_speed);
+                th0 = Mt::uni(0.0, kTwoPi, rd.sample());
+                sp0 = Mt::uni(0.0, R.max_speed, rd.sample());
             }
             __syncwarp();
             for (int i = lane; i < kMtN; i += 32) P.key[e * kMtN + i] = S.mt[i];

@@ -174,6 +174,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -239,6 +244,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
     // vortex cores (registers), goal and obstacle rows (shared memory, per-thread cp.async: each thread copies its own
     // column; first needed after the sub-step loop, so that DRAM round trip hides under the integration)
     double cx[MAXC], cy[MAXC], ck[MAXC], gx = 0.0, gy = 0.0;
+    const bool coop = (e0 + w0 + 32 <= E) && ((E & 1) == 0) && (STEP || P.mask == nullptr);   // warp-uniform
     auto load_tables = [&]() {
         gx = P.goal[e]; gy = P.goal[E + e];
         const double* pc = P.cores + e;
@@ -249,14 +255,22 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             else { cx[i] = 0.0; cy[i] = 0.0; ck[i] = 0.0; }
             pc += E;
         }
-        const double* po = P.obst + e;
-        for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
+        if (coop) {
+            // a full warp: row r of the warp's 32 environments is 256 contiguous, 16-byte aligned bytes -> 16 lanes x 16 B, two
+            // rows per trip (half the cp.async instructions of the per-thread copy; the data is shared after a __syncwarp)
+            const double* pw = P.obst + (e0 + w0) + (lane & 15) * 2;
+            double* ps = s_ob + w0 + (lane & 15) * 2;
+            for (int row = lane >> 4; row < 3 * max_o; row += 2) cp_async16(ps + row * kBlock, pw + (long long)row * E);
+        } else {
+            const double* po = P.obst + e;
+            for (int row = 0; row < 3 * max_o; ++row, po += E) cp_async8(s_ob + row * kBlock + tid, po);
+        }
         cp_async_commit();
     };
     // "pdl" = 2: the map tables (goal, cores, obstacles) are not written by the launch right before this one (the caller's
     // contract; true for step -> step and for step after anything but mnv_reset / a table upload), so they are fetched
     // while that launch still drains; everything else waits for it.
-    if (PREFETCH && e < E) load_tables();
+    if (PREFETCH && e < E) load_tables();                     // (PREFETCH implies STEP: a full warp is all live)
     pdl_wait();                                               // everything below reads what earlier launches wrote
     pdl_launch_dependents();                                  // the next launch may be scheduled while this one runs (it waits like this one)
     const bool live = (e < E) && (STEP || P.mask == nullptr || P.mask[e] != 0);
@@ -331,6 +345,8 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             const int ai = action / 3, wi = action - 3 * ai;
             const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
             const double dis_before = fast_sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+            const bool wdt_neg = wdt < 0.0;
+            const double wrap_adj = wdt_neg ? 2.0 * MNV_PI : -2.0 * MNV_PI;
             auto substeps = [&](auto with_traj) {
                 double* ptraj = decltype(with_traj)::value ? P.traj + e : nullptr;
                 for (int it = 0; it < K.n_substeps; ++it) {
@@ -344,16 +360,21 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                     sp = sp < 0.0 ? 0.0 : sp;                     // robot.py:114 (np.clip)
                     sp = sp > K.max_speed ? K.max_speed : sp;
                     th = __dadd_rn(th, wdt);                      // robot.py:117
-                    // robot.py:120-123: the two while loops; |w dt| << 2 pi, so one conditional add / subtract each is
-                    // the whole loop unless theta came in far outside [0, 2 pi) (then the loops below finish the job
-                    // with the reference's own sequence of additions)
-                    th = th < 0.0 ? __dadd_rn(th, 2.0 * MNV_PI) : th;
-                    th = th >= 2.0 * MNV_PI ? __dsub_rn(th, 2.0 * MNV_PI) : th;
-                    if (th < 0.0 || th >= 2.0 * MNV_PI) {
+                    // robot.py:120-123, the two while loops.  theta was in [0, 2 pi) and |w dt| << 2 pi, so at most ONE
+                    // correction is due and the sign of the yaw increment says which: + 2 pi if w dt < 0 and theta < 0,
+                    // - 2 pi if w dt > 0 and theta >= 2 pi.  Anything that does not land strictly inside (0, 2 pi) -- a
+                    // theta that came in out of range, or a sum that rounded onto 0 / 2 pi -- runs the reference's own
+                    // loops on the uncorrected sum (|theta - pi| < pi has no false negatives).
+                    {
+                        const double th_c = __dadd_rn(th, wrap_adj);
+                        const double th_f = (wdt_neg ? th < 0.0 : th >= 2.0 * MNV_PI) ? th_c : th;
+                        if (fabs(th_f - MNV_PI) < MNV_PI) th = th_f;
+                        else {
 #pragma unroll 1
-                        while (th < 0.0) th += 2.0 * MNV_PI;
+                            while (th < 0.0) th += 2.0 * MNV_PI;
 #pragma unroll 1
-                        while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                            while (th >= 2.0 * MNV_PI) th -= 2.0 * MNV_PI;
+                        }
                     }
                     const double c2 = fma(c, cw, -s * sw), s2 = fma(s, cw, c * sw);
                     c = c2; s = s2;
@@ -395,6 +416,7 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         // ---- obstacles: nearest centre (Q4) and the set within sonar reach.  Only an obstacle with |centre - pos| <=
         //      range + r can return a hit (the hit distance is >= d - r), so everything below looks at those alone. ----
         if (use_tma) mbar_wait(my_bar, 0); else cp_async_wait_all();
+        if (coop) __syncwarp();                               // rows were copied by other lanes of this (fully live) warp
         const double* ob = s_ob + tid;
 #pragma unroll
         for (int j = 0; j < MAXO; ++j) {
@@ -425,7 +447,8 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             unsigned short* my_bm = s_bm + tid * kBmStride;
 #pragma unroll
             for (int j4 = 0; j4 < kBmStride / 8; ++j4) reinterpret_cast<uint4*>(my_bm)[j4] = make_uint4(0u, 0u, 0u, 0u);
-            s_rel[tid] = rel;
+            const unsigned sb1 = (bs1 >= 0 && bs1 < K.n_beams) ? (unsigned)(bs1 + 1) : 0u, sb2 = (bs2 >= 0 && bs2 < K.n_beams) ? (unsigned)(bs2 + 1) : 0u;
+            s_rel[tid] = rel | (sb1 << 16) | (sb2 << 24);   // [15:0] obstacles within reach, [23:16] / [31:24] Q10 candidate beams + 1
             if (!K.precise_bins) beams = rel != 0u ? 0xffffffffu : 0u;
             else {
                 unsigned todo = rel;
@@ -451,11 +474,12 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                     beams |= bm;
                 }
                 if (rel != 0u) {                            // a beam that may be snapped to the vertical (Q10) is decided exactly
-                    if (bs1 >= 0 && bs1 < K.n_beams) beams |= 1u << bs1;
-                    if (bs2 >= 0 && bs2 < K.n_beams) beams |= 1u << bs2;
+                    if (sb1) beams |= 1u << (sb1 - 1u);
+                    if (sb2) beams |= 1u << (sb2 - 1u);
                 }
             }
             // "no return" everywhere (marinenav_env.py:318-320); the exact tests overwrite the beams that hit
+#pragma unroll 4
             for (int b = 0; b < K.n_beams; ++b) *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);
         }
     }
@@ -481,10 +505,11 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (total == 0) continue;                           // warp-uniform
             int slot = incl - cnt;
-            while (mine_beams != 0u) {                          // list entry: [4:0] owner lane, [12:5] beam, [13] Q10 candidate
-                const int b = b0 + __ffs(mine_beams) - 1;
+            const unsigned ent0 = (unsigned)lane | ((unsigned)b0 << 5);
+            while (mine_beams != 0u) {                          // list entry: [4:0] owner lane, [12:5] beam
+                const int bl = __ffs(mine_beams) - 1;
                 mine_beams &= mine_beams - 1u;
-                ring[slot++] = (unsigned short)((unsigned)lane | ((unsigned)b << 5) | (((b == bs1) || (b == bs2)) ? 1u << 13 : 0u));
+                ring[slot++] = (unsigned short)(ent0 + ((unsigned)bl << 5));
             }
             __syncwarp();                                       // list entries, masks and zero-filled rows of other lanes are visible
             for (int base = 0; base < total; base += 32) {
@@ -499,14 +524,15 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                     const double* ob = obw + owner;
                     double bx = K.beam_cos[bb], by = K.beam_sin[bb];    // beam direction in the robot frame
                     bool scan_all = !K.precise_bins;
-                    if (ent & (1u << 13)) {
+                    const unsigned orel = s_rel[w0 + owner];
+                    if (bb + 1 == (int)((orel >> 16) & 0xffu) || bb + 1 == (int)(orel >> 24)) {
                         const double ang = oth + K.beam_angle[bb];       // robot.py:131 (not wrapped)
                         if (fabs(ang - 0.5 * MNV_PI) < 1e-03) { bx = os; by = oc; scan_all = true; }            // Q10: exactly (0,+1) in the world frame
                         else if (fabs(ang - 1.5 * MNV_PI) < 1e-03) { bx = -os; by = -oc; scan_all = true; }     // Q10: exactly (0,-1)
                     }
                     // obstacles whose beam interval contains this beam (all obstacles within reach for a snapped beam, whose
                     // direction is not the table's), in list order
-                    unsigned mm = s_rel[w0 + owner];
+                    unsigned mm = orel & 0xffffu;
                     if (!scan_all) {
                         const unsigned short* bm = s_bm + (w0 + owner) * kBmStride;
                         unsigned m = 0u;
@@ -580,9 +606,12 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         return;
     }
     const int n4 = n >> 2;
-#pragma unroll 2
-    for (int i = lane; i < n4; i += 32)
-        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    const float4* src4 = reinterpret_cast<const float4*>(src) + lane;
+    float4* dst4 = reinterpret_cast<float4*>(dst) + lane;
+    const int full = n4 >> 5;                                      // whole 32-lane trips (6 for 32 rows of 26 floats)
+#pragma unroll 6
+    for (int k = 0; k < full; ++k) dst4[k * 32] = src4[k * 32];
+    if ((full << 5) + lane < n4) dst4[full * 32] = src4[full * 32];
     for (int i = (n4 << 2) + lane; i < n; i += 32) dst[i] = src[i];
 }
 
