@@ -15,8 +15,9 @@
 // current MT19937 block; the one candidate that straddles a regeneration is evaluated on its own.  Same candidates, same
 // arithmetic per candidate, same accept decisions -> bit-identical maps, ~12 dependent rounds instead of ~30 serial
 // candidates with several square-root chains each.
-// A persistent grid of warps scans the done flags in contiguous chunks, so a masked launch with a few finished
-// environments costs one flag scan plus ~one reset latency.
+// A persistent grid scans the done flags; each CTA spreads the finished environments of its range over its warps
+// through a shared-memory list, so a masked launch with a few finished environments costs one flag scan plus ~one
+// reset latency.
 #include <math.h>
 
 #include "mnv_common.cuh"
@@ -137,22 +138,30 @@ mnv_reset_kernel(const ResetPtrs P, const mnv_reset_params R, long long E, int m
     __shared__ WarpScratch s_ws[kWarpsPerCta];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpScratch& S = s_ws[w];
-    // contiguous chunk of environments per warp: a warp whose chunk has no finished environment only scans its flags
-    const long long n_warps = (long long)gridDim.x * kWarpsPerCta;
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + w;
-    const long long chunk = (E + n_warps - 1) / n_warps;
-    const long long lo = gw * chunk, hi = (lo + chunk < E) ? lo + chunk : E;
+    // Work distribution: the CTA owns a contiguous range of environments and walks it in tiles of kBlock.  Per tile every
+    // thread tests ONE flag and the finished environments go to a shared-memory list (slot = position among the tile's
+    // finished environments: ballot + per-warp prefix, no atomics, deterministic); after a barrier the CTA's warps take the
+    // list entries round robin, one environment per warp at a time.  A reset is a ~8 us dependent chain, so what matters is
+    // that no warp gets two while another has none: with 1 % of 65 536 environments finished a CTA's 222 environments
+    // hold ~2 resets for its 8 warps (a contiguous chunk per WARP left the unluckiest warp with 3-4).
+    __shared__ int s_list[kBlock];
+    __shared__ int s_warp_cnt[kWarpsPerCta];
+    const long long per_cta = (E + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per_cta, hi = (lo + per_cta < E) ? lo + per_cta : E;
 
-    for (long long base = lo; base < hi; base += 32) {
-        unsigned todo = 0xffffffffu;
-        if (P.mask != nullptr) {
-            const long long i = base + lane;
-            todo = __ballot_sync(0xffffffffu, i < hi && P.mask[i] != 0);
-        } else if (hi - base < 32) todo = (1u << (int)(hi - base)) - 1u;
-        while (todo) {
-            const int bit = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const long long e = base + bit;
+    for (long long tile = lo; tile < hi; tile += kBlock) {
+        const long long i = tile + threadIdx.x;
+        const bool fin = i < hi && (P.mask == nullptr || P.mask[i] != 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, fin);
+        if (lane == 0) s_warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, n_fin = 0;
+#pragma unroll
+        for (int k = 0; k < kWarpsPerCta; ++k) { const int c = s_warp_cnt[k]; before += k < w ? c : 0; n_fin += c; }
+        if (fin) s_list[before + __popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
+        __syncthreads();
+        for (int q = w; q < n_fin; q += kWarpsPerCta) {
+            const long long e = tile + s_list[q];
 
             for (int i = lane; i < kMtN; i += 32) S.mt[i] = P.key[e * kMtN + i];
             __syncwarp();
@@ -343,6 +352,7 @@ mnv_reset_kernel(const ResetPtrs P, const mnv_reset_params R, long long E, int m
             }
             __syncwarp();
         }
+        __syncthreads();                                    // the list is rebuilt by the next tile
     }
 }
 
