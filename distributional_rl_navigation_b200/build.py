@@ -13,6 +13,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 SO = os.path.join(LIBDIR, "libmarinenav_b200.so")
 OBJDIR = os.path.join(PKG, "build")
+HOST_SRC = os.path.join(PKG, "csrc_host", "mnv_host.c")
+HOST_SO = os.path.join(LIBDIR, "libmnv_host.so")      # native host-side helper of step_host (plain C, pthreads)
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -52,6 +54,12 @@ def build(force=False, verbose=False):
             rebuilt = True
     if rebuilt or force or _stale(SO, objs):
         cmd = [_nvcc()] + ARCH + ["-shared", "-o", SO] + objs
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    if force or _stale(HOST_SO, [HOST_SRC, os.path.join(ROOT, "include", "mnv_host.h")]):
+        cmd = [shutil.which("gcc") or "gcc", "-O3", "-Wall", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"),
+               "-o", HOST_SO, HOST_SRC]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -25,11 +25,18 @@ def _chk(t, dtype, shape, name):
 def alloc_env_buffers(E, max_c, max_o, n_beams, device):
     """All per-environment arrays of one env batch (layout: include/marinenav_b200.h)."""
     f64 = dict(dtype=torch.float64, device=device)
-    # reward | done | info share ONE allocation (16-byte aligned segments) so that the host boundary ships them with one copy
+    # reward | done | info | compact observation packet (head, hit count, hit list: mnv_pack_obs) share ONE allocation
+    # (16-byte aligned segments) so that the host boundary ships everything with one copy
     seg = lambda n: (n + 15) // 16 * 16
     o_done, o_info, n_pack = seg(4 * E), seg(4 * E) + seg(E), seg(4 * E) + 2 * seg(E)
-    pack = torch.zeros(n_pack, dtype=torch.uint8, device=device)
+    hit_cap = max(1024, E * n_beams // 8)                      # list capacity: 12.5 % of the beam slots (a rollout fills ~4 %)
+    o_head, o_cnt, o_hits = n_pack, n_pack + 16 * E, n_pack + 16 * E + 16
+    whole = torch.zeros(o_hits + 12 * hit_cap, dtype=torch.uint8, device=device)
+    pack = whole[:n_pack]
     return dict(
+        host_packet=whole, packet_offsets=dict(done=o_done, info=o_info, head=o_head, count=o_cnt, hits=o_hits, hit_cap=hit_cap),
+        packet_head=whole[o_head:o_cnt].view(torch.float32).view(E, 4), packet_count=whole[o_cnt:o_hits].view(torch.int32),
+        packet_hits=whole[o_hits:].view(torch.int32).view(hit_cap, 3),
         rdi_pack=pack, rdi_offsets=torch.tensor([0, o_done, o_info]),
         state=torch.zeros(4, E, **f64), velocity=torch.zeros(2, E, **f64), goal=torch.zeros(2, E, **f64),
         cores=torch.zeros(3 * max_c, E, **f64), obstacles=torch.zeros(3 * max_o, E, **f64),
@@ -99,6 +106,15 @@ def reset(buf, rng_key, rng_pos, reset_params, mask=None):
                                _lib.ptr(buf["start_pose"]), _lib.ptr(buf["episode_step"]), _lib.ptr(buf["n_placed"]),
                                E, max_c, max_o, C.byref(reset_params), _stream())
     _lib.check(rc, "mnv_reset")
+
+
+def pack_obs(obs, head, count, hits):
+    """Compact packet of an observation block (mnv_pack_obs): head f32 [E, 4], count i32 [4], hits i32 [cap, 3]."""
+    E, D = obs.shape
+    _chk(obs, torch.float32, (E, D), "obs"); _chk(head, torch.float32, (E, 4), "head")
+    _chk(count, torch.int32, (4,), "count"); _chk(hits, torch.int32, (hits.shape[0], 3), "hits")
+    rc = _lib.load().mnv_pack_obs(_lib.ptr(obs), E, D, _lib.ptr(head), _lib.ptr(count), _lib.ptr(hits), hits.shape[0], _stream())
+    _lib.check(rc, "mnv_pack_obs")
 
 
 def scatter_rows_host(mask, rows, host_rows):

@@ -181,51 +181,76 @@ class VecMarineNavEnv:
     # ---- host-buffer surface (numpy in / numpy out, pinned staging) ------------------------------------------------
     def _pin(self):
         if self._pinned is None:
+            from . import _hostlib
             E, D = self.num_envs, self.obs_dim
+            off = self.buf["packet_offsets"]
             o_r, o_d, o_i = self.buf["rdi_offsets"].tolist()
-            rdi = torch.zeros(self.buf["rdi_pack"].numel(), dtype=torch.uint8).pin_memory()      # reward | done | info: one D2H
+            # first tier of the packet copy: reward | done | info | head | count | hits of 6.25 % of the beam slots
+            tier1 = min(off["hit_cap"], max(512, E * self.num_beams // 16))
+            pk = torch.zeros(self.buf["host_packet"].numel(), dtype=torch.uint8).pin_memory()
             act = torch.zeros(E, dtype=torch.int32).pin_memory()
+            rdi = pk[:self.buf["rdi_pack"].numel()]
             self._pinned = dict(action=act, action_np=act.numpy(),
                                 obs=torch.zeros(E, D, dtype=torch.float32).pin_memory(),
+                                packet=pk, tier1_bytes=off["hits"] + 12 * tier1, tier1=tier1,
+                                head=pk[off["head"]:off["count"]], count=pk[off["count"]:off["hits"]].view(torch.int32),
+                                count_np=pk[off["count"]:off["hits"]].view(torch.int32).numpy(),
+                                hits=pk[off["hits"]:],
                                 rdi_pack=rdi, reward=rdi[o_r:o_r + 4 * E].view(torch.float32), done=rdi[o_d:o_d + E],
                                 info=rdi[o_i:o_i + E])
             self._host_graphs = {}
+            self._expander = _hostlib.Expander(E, D)
+            self._host_dirty = False                  # True: the pinned dense block was written outside the expander
         return self._pinned
 
     def _capture_host_step(self, auto_reset):
-        """One CUDA graph for the whole host-boundary step.  Stream A: fused step (actions read zero-copy from the pinned host buffer) -> (auto-reset: masked
-        reset -> masked re-observe); stream B, forked right behind the step kernel: D2H of the step's own observation block
-        and of reward | done | info (everything the host needs except the rows of the environments that were reset).  A
-        joins B and overwrites the rows of the re-observed environments directly in the pinned host array
-        (mnv_scatter_rows_host, zero-copy stores).  The 7 MB D2H -- the longest item of the step -- runs under the reset
-        instead of after it, the host pays one graph launch instead of ~12 launches and does no patching."""
+        """One CUDA graph for the whole host-boundary step.  Stream A: fused step (actions read zero-copy from the pinned host
+        buffer) -> (auto-reset: masked reset -> masked re-observe); stream B, forked right behind the step kernel: the
+        step's own observation block goes through mnv_pack_obs (head of every row + the list of sonar returns, ~4 % of the
+        beam slots) and ships together with reward | done | info in ONE device -> host copy of ~2 MB instead of the dense
+        7.2 MB.  A joins B and overwrites the rows of the re-observed environments directly in the pinned dense array
+        (mnv_scatter_rows_host, zero-copy stores); after the graph the native expander (libmnv_host.so) brings the dense
+        array up to date from the packet, skipping those rows.  The copy runs under the reset, the host pays one graph
+        launch and touches only the slots that change."""
         pin, b = self._pin(), self.buf
         params = self.params()
         rp = self.reset_params() if auto_reset else None
         cur = torch.cuda.current_stream()
         sa, sb = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
         g = torch.cuda.CUDAGraph()
+        n1 = pin["tier1_bytes"]
         sa.wait_stream(cur)
         with torch.cuda.stream(sa):
             with torch.cuda.graph(g, stream=sa):
                 env_ops.step(b, params, action=pin["action"], obs=b["next_obs"])    # actions read zero-copy from the pinned buffer
                 sb.wait_stream(sa)
                 with torch.cuda.stream(sb):
-                    pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["rdi_pack"].copy_(b["rdi_pack"], non_blocking=True)
+                    env_ops.pack_obs(b["next_obs"], b["packet_head"], b["packet_count"], b["packet_hits"])
+                    pin["packet"][:n1].copy_(b["host_packet"][:n1], non_blocking=True)
                 b["obs"].copy_(b["next_obs"])
                 if auto_reset:
                     env_ops.reset(b, self.rng_key, self.rng_pos, rp, mask=b["done"])
                     env_ops.observe(b, params, mask=b["done"], velocity_from_state=True)
                 sa.wait_stream(sb)
                 if auto_reset:
-                    env_ops.scatter_rows_host(b["done"], b["obs"], pin["obs"])      # after the bulk copy has written those rows
+                    env_ops.scatter_rows_host(b["done"], b["obs"], pin["obs"])      # dense rows of the re-observed environments
         cur.wait_stream(sa)
         return g, (sa, sb)
 
+    def _refresh_host_dense(self):
+        """Dense device -> host copy of the current observation block + rebuild of the expander's bookkeeping (the slow
+        path: first use after a dense write, hit-list overflow)."""
+        pin = self._pin()
+        pin["obs"].copy_(self.buf["obs"])
+        torch.cuda.current_stream(self.device).synchronize()
+        self._expander.rescan(pin["obs"].data_ptr())
+        self._host_dirty = False
+
     def step_host(self, actions, auto_reset=True, graph=True):
         """numpy int actions [E] -> (obs f32 [E,D], reward f32 [E], done bool [E], info u8 [E]) numpy views of pinned buffers
-        (valid until the next call).  obs holds the first observation of the next episode for finished environments, like
-        step().  graph=False runs the same operations eagerly on one stream (the parity reference of the graph path)."""
+        (valid until the next call; read-only: the observation array is updated in place from step to step).  obs holds the
+        first observation of the next episode for finished environments, like step().  graph=False runs the same operations
+        eagerly on one stream with a dense copy (the parity reference of the graph path)."""
         pin = self._pin()
         np.copyto(pin["action_np"], np.asarray(actions), casting="unsafe")       # 9 us; torch's CPU copy_ costs 14 - 500 us here
         with torch.cuda.device(self.device):
@@ -234,6 +259,7 @@ class VecMarineNavEnv:
                 obs, reward, done, info = self.step(self.buf["action"], auto_reset=auto_reset)
                 pin["obs"].copy_(obs, non_blocking=True); pin["rdi_pack"].copy_(self.buf["rdi_pack"], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
+                self._host_dirty = True
                 return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
             self.params()
             if auto_reset:
@@ -243,9 +269,22 @@ class VecMarineNavEnv:
             if entry is None:
                 self._host_graphs.clear()                         # parameters changed: the old graph holds stale constants
                 entry = self._host_graphs[key] = self._capture_host_step(auto_reset)
+            if self._host_dirty:
+                self._expander.rescan(pin["obs"].data_ptr())
+                self._host_dirty = False
             entry[0].replay()
             self.total_timesteps += self.num_envs * self.global_step_multiplier
             torch.cuda.current_stream().synchronize()
+            n_hits = int(pin["count_np"][0])
+            if n_hits > self.buf["packet_offsets"]["hit_cap"]:
+                self._refresh_host_dense()                        # more returns than the list holds: dense block this once
+            else:
+                if n_hits > pin["tier1"]:                         # the rest of the list (rare: > 6.25 % of the beam slots)
+                    lo, hi = pin["tier1_bytes"], self.buf["packet_offsets"]["hits"] + 12 * n_hits
+                    pin["packet"][lo:hi].copy_(self.buf["host_packet"][lo:hi], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                self._expander.expand(pin["obs"].data_ptr(), pin["head"].data_ptr(), pin["done"].data_ptr() if auto_reset else None,
+                                      pin["hits"].data_ptr(), n_hits)
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
 
     def tables_written(self):
@@ -255,19 +294,24 @@ class VecMarineNavEnv:
 
     def reset_host(self):
         pin = self._pin()
-        pin["obs"].copy_(self.reset())
+        self.reset()
+        with torch.cuda.device(self.device):
+            self._refresh_host_dense()
         return pin["obs"].numpy()
 
     def host_api_description(self):
-        return ("VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step)")
+        return ("VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step; the "
+                "observation block travels as head + list of sonar returns (mnv_pack_obs) and is expanded into the dense numpy "
+                f"array by libmnv_host.so on {self._expander.n_threads if self._pinned else '?'} host threads)")
 
     def h2d_bytes_per_step(self):
         return self.num_envs * 4
 
     def d2h_bytes_per_step(self):
         self._pin()
-        # bulk copies; the zero-copy rows of the re-observed environments (a few hundred x obs_dim x 4 bytes) come on top
-        return self.num_envs * self.obs_dim * 4 + self._pinned["rdi_pack"].numel()
+        # the packet copy (reward | done | info | head | count | first tier of the hit list); the zero-copy rows of the
+        # re-observed environments (a few hundred x obs_dim x 4 bytes) come on top
+        return self._pinned["tier1_bytes"]
 
     def close(self):
         pass

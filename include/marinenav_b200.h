@@ -136,6 +136,16 @@ int mnv_reset(uint32_t* d_rng_key, int32_t* d_rng_pos, const uint8_t* d_mask,
 int mnv_scatter_rows_host(const uint8_t* d_mask, const float* d_rows, float* h_rows_mapped, int64_t E, int32_t row_len,
                           void* stream);
 
+/* Host-boundary helper: compact transport of the observation block d_obs f32 [E][obs_dim] (obs_dim = 4 + 2 * n_beams).  A beam
+ * without a return is exactly (0, 0) (marinenav_env.py:318-320) and few beams carry one, so the kernel writes
+ *   d_head  f32 [E][4]            the 4 head values of every row
+ *   d_count u32 [4]               d_count[0] = number of beams with a return (may exceed `capacity`: the list is then truncated)
+ *   d_hits  u32 [capacity][3]     (env << 8 | beam, bits of x, bits of y) per return, in no particular order
+ * for ONE device -> host copy; libmnv_host.so (include/mnv_host.h) expands it into the dense block on the host.  E < 2^24,
+ * n_beams <= 256.  One memset node + one kernel on `stream`. */
+int mnv_pack_obs(const float* d_obs, int64_t E, int32_t obs_dim, float* d_head, uint32_t* d_count, uint32_t* d_hits,
+                 int64_t capacity, void* stream);
+
 /* ================================ replay buffer (thirdparty/IQN/replay_buffer.py) ===========================
  * Device-resident ReplayBuffer of the vectorised trainer.  Ring arrays (caller-owned, `capacity` transitions):
  *   d_states f32 [capacity][row_len], d_actions i64 [capacity], d_rewards f32 [capacity], d_next_states f32

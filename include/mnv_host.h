@@ -1,0 +1,33 @@
+/*
+ * mnv_host.h -- C-ABI of libmnv_host.so, the native HOST-side helper of VecMarineNavEnv.step_host (plain C, pthreads; no
+ * CUDA).  It expands the compact observation packet produced on the device by mnv_pack_obs (marinenav_b200.h) into the dense
+ * row-major f32 [E][obs_dim] observation block (row layout of MarineNavEnv.get_observation, marinenav_env.py:273-326).
+ */
+#ifndef MNV_HOST_H
+#define MNV_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mnvh_pool mnvh_pool;
+
+/* n_threads workers (the caller is one of them) for E environments with obs_dim = 4 + 2 * n_beams floats per row.
+ * cpu_first >= 0 pins worker t to CPU cpu_first + t; < 0 leaves the placement to the OS.  NULL on bad arguments. */
+mnvh_pool* mnvh_create(int n_threads, int64_t E, int obs_dim, int cpu_first);
+void       mnvh_destroy(mnvh_pool* p);
+int        mnvh_threads(const mnvh_pool* p);
+
+/* obs holds a complete dense block (after a reset / a dense refresh): rebuild the bookkeeping of non-zero beam slots. */
+void mnvh_rescan(mnvh_pool* p, float* obs);
+
+/* One packet -> obs, in place: head f32 [E][4]; hits u32 [n_hits][3] = (env << 8 | beam, bits of x, bits of y);
+ * skip u8 [E] (may be NULL): rows the caller has already written (left alone, then re-scanned). */
+void mnvh_expand(mnvh_pool* p, float* obs, const float* head, const uint8_t* skip, const uint32_t* hits, uint32_t n_hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
