@@ -21,7 +21,7 @@ def load():
         L.mnvh_destroy.restype, L.mnvh_destroy.argtypes = None, [C.c_void_p]
         L.mnvh_threads.restype, L.mnvh_threads.argtypes = C.c_int, [C.c_void_p]
         L.mnvh_rescan.restype, L.mnvh_rescan.argtypes = None, [C.c_void_p, C.c_void_p]
-        L.mnvh_expand.restype, L.mnvh_expand.argtypes = None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.mnvh_expand.restype, L.mnvh_expand.argtypes = None, [C.c_void_p] * 7
         _lib = L
     return _lib
 
@@ -29,19 +29,20 @@ def load():
 def default_threads_and_first_cpu():
     """Workers for this process and the first CPU to pin them to: the CPUs this process may run on are split evenly among
     the ranks of the node (LOCAL_RANK / LOCAL_WORLD_SIZE from torchrun), so that the expanders of different ranks never
-    share a core; at most 8 workers per rank.  MNV_HOST_THREADS overrides the count; no pinning unless the CPU set is a
-    contiguous range."""
+    share a core; at most 8 workers per rank.  MNV_HOST_THREADS overrides the count; MNV_HOST_PIN=1 pins worker t to the
+    t-th CPU of this rank's share (only when the CPU set is a contiguous range)."""
     cpus = sorted(os.sched_getaffinity(0))
     lw, lr = int(os.environ.get("LOCAL_WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     share = max(1, len(cpus) // max(1, lw))
     n = int(os.environ.get("MNV_HOST_THREADS", "0")) or max(1, min(8, share))
     contiguous = cpus == list(range(cpus[0], cpus[0] + len(cpus)))
-    first = cpus[0] + lr * share if (contiguous and n <= share) else -1
+    pin = os.environ.get("MNV_HOST_PIN", "0") == "1"           # off by default: measured slower on a shared VM (profiles/README.md)
+    first = cpus[0] + lr * share if (pin and contiguous and n <= share) else -1
     return n, first
 
 
 class Expander:
-    """One pool per VecMarineNavEnv: expand(obs_np, head_np, skip_np | None, hits_np, n_hits) updates obs_np in place."""
+    """One pool per VecMarineNavEnv: expand(obs, head, skip | None, mask, dir, vals) (raw addresses) updates obs in place."""
 
     def __init__(self, E, obs_dim, n_threads=None, cpu_first=None):
         n, first = default_threads_and_first_cpu()
@@ -56,8 +57,8 @@ class Expander:
     def rescan(self, obs_ptr):
         self._L.mnvh_rescan(self._p, obs_ptr)
 
-    def expand(self, obs_ptr, head_ptr, skip_ptr, hits_ptr, n_hits):
-        self._L.mnvh_expand(self._p, obs_ptr, head_ptr, skip_ptr, hits_ptr, int(n_hits))
+    def expand(self, obs_ptr, head_ptr, skip_ptr, mask_ptr, dir_ptr, vals_ptr):
+        self._L.mnvh_expand(self._p, obs_ptr, head_ptr, skip_ptr, mask_ptr, dir_ptr, vals_ptr)
 
     def close(self):
         if self._p:

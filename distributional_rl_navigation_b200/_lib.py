@@ -54,7 +54,7 @@ _SIGNATURES = {
     "mnv_seed": (C.c_int, [_vp] * 3 + [_i64, _vp]),
     "mnv_reset": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, C.POINTER(MnvResetParams), _vp]),
     "mnv_scatter_rows_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
-    "mnv_pack_obs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "mnv_pack_obs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rpl_append": (C.c_int, [_vp] * 5 + [_i64, _i64] + [_vp] * 5 + [_i64, _i32, _i32, C.c_double, _i64] + [_vp] * 4),
     "rpl_sample": (C.c_int, [_vp] * 5 + [_i64, _i64, _i64, C.c_uint64, C.c_uint64, _i32] + [_vp] * 6 + [_i64, _i32, _vp]),
     "rpl_gather": (C.c_int, [_vp] * 5 + [_i64, _i64, _i64] + [_vp] * 6 + [_i64, _i32, _vp]),

@@ -30,13 +30,21 @@ def alloc_env_buffers(E, max_c, max_o, n_beams, device):
     seg = lambda n: (n + 15) // 16 * 16
     o_done, o_info, n_pack = seg(4 * E), seg(4 * E) + seg(E), seg(4 * E) + 2 * seg(E)
     hit_cap = max(1024, E * n_beams // 8)                      # list capacity: 12.5 % of the beam slots (a rollout fills ~4 %)
-    o_head, o_cnt, o_hits = n_pack, n_pack + 16 * E, n_pack + 16 * E + 16
-    whole = torch.zeros(o_hits + 12 * hit_cap, dtype=torch.uint8, device=device)
+    W, G = (n_beams + 31) // 32, (E + 31) // 32
+    o_head = n_pack
+    o_mask = o_head + 16 * E
+    o_dir = o_mask + seg(4 * W * E)
+    o_cnt = o_dir + seg(4 * G)
+    o_vals = o_cnt + 16
+    whole = torch.zeros(o_vals + 8 * hit_cap, dtype=torch.uint8, device=device)
     pack = whole[:n_pack]
     return dict(
-        host_packet=whole, packet_offsets=dict(done=o_done, info=o_info, head=o_head, count=o_cnt, hits=o_hits, hit_cap=hit_cap),
-        packet_head=whole[o_head:o_cnt].view(torch.float32).view(E, 4), packet_count=whole[o_cnt:o_hits].view(torch.int32),
-        packet_hits=whole[o_hits:].view(torch.int32).view(hit_cap, 3),
+        host_packet=whole, packet_offsets=dict(done=o_done, info=o_info, head=o_head, mask=o_mask, dir=o_dir, count=o_cnt, vals=o_vals,
+                                               hit_cap=hit_cap),
+        packet_head=whole[o_head:o_mask].view(torch.float32).view(E, 4),
+        packet_mask=whole[o_mask:o_mask + 4 * W * E].view(torch.int32).view(E, W),
+        packet_dir=whole[o_dir:o_dir + 4 * G].view(torch.int32), packet_count=whole[o_cnt:o_vals].view(torch.int32),
+        packet_vals=whole[o_vals:].view(torch.float32).view(hit_cap, 2),
         rdi_pack=pack, rdi_offsets=torch.tensor([0, o_done, o_info]),
         state=torch.zeros(4, E, **f64), velocity=torch.zeros(2, E, **f64), goal=torch.zeros(2, E, **f64),
         cores=torch.zeros(3 * max_c, E, **f64), obstacles=torch.zeros(3 * max_o, E, **f64),
@@ -108,12 +116,15 @@ def reset(buf, rng_key, rng_pos, reset_params, mask=None):
     _lib.check(rc, "mnv_reset")
 
 
-def pack_obs(obs, head, count, hits):
-    """Compact packet of an observation block (mnv_pack_obs): head f32 [E, 4], count i32 [4], hits i32 [cap, 3]."""
+def pack_obs(obs, head, mask, dir_, count, vals):
+    """Compact packet of an observation block (mnv_pack_obs): head f32 [E, 4], mask i32 [E, W], dir i32 [ceil(E / 32)],
+    count i32 [4], vals f32 [cap, 2]."""
     E, D = obs.shape
-    _chk(obs, torch.float32, (E, D), "obs"); _chk(head, torch.float32, (E, 4), "head")
-    _chk(count, torch.int32, (4,), "count"); _chk(hits, torch.int32, (hits.shape[0], 3), "hits")
-    rc = _lib.load().mnv_pack_obs(_lib.ptr(obs), E, D, _lib.ptr(head), _lib.ptr(count), _lib.ptr(hits), hits.shape[0], _stream())
+    W, G = ((D - 4) // 2 + 31) // 32, (E + 31) // 32
+    _chk(obs, torch.float32, (E, D), "obs"); _chk(head, torch.float32, (E, 4), "head"); _chk(mask, torch.int32, (E, W), "mask")
+    _chk(dir_, torch.int32, (G,), "dir"); _chk(count, torch.int32, (4,), "count"); _chk(vals, torch.float32, (vals.shape[0], 2), "vals")
+    rc = _lib.load().mnv_pack_obs(_lib.ptr(obs), E, D, _lib.ptr(head), _lib.ptr(mask), _lib.ptr(dir_), _lib.ptr(count), _lib.ptr(vals),
+                                  vals.shape[0], _stream())
     _lib.check(rc, "mnv_pack_obs")
 
 

@@ -192,10 +192,9 @@ class VecMarineNavEnv:
             rdi = pk[:self.buf["rdi_pack"].numel()]
             self._pinned = dict(action=act, action_np=act.numpy(),
                                 obs=torch.zeros(E, D, dtype=torch.float32).pin_memory(),
-                                packet=pk, tier1_bytes=off["hits"] + 12 * tier1, tier1=tier1,
-                                head=pk[off["head"]:off["count"]], count=pk[off["count"]:off["hits"]].view(torch.int32),
-                                count_np=pk[off["count"]:off["hits"]].view(torch.int32).numpy(),
-                                hits=pk[off["hits"]:],
+                                packet=pk, tier1_bytes=off["vals"] + 8 * tier1, tier1=tier1,
+                                head=pk[off["head"]:off["mask"]], mask=pk[off["mask"]:off["dir"]], dir=pk[off["dir"]:off["count"]],
+                                count_np=pk[off["count"]:off["vals"]].view(torch.int32).numpy(), vals=pk[off["vals"]:],
                                 rdi_pack=rdi, reward=rdi[o_r:o_r + 4 * E].view(torch.float32), done=rdi[o_d:o_d + E],
                                 info=rdi[o_i:o_i + E])
             self._host_graphs = {}
@@ -225,7 +224,7 @@ class VecMarineNavEnv:
                 env_ops.step(b, params, action=pin["action"], obs=b["next_obs"])    # actions read zero-copy from the pinned buffer
                 sb.wait_stream(sa)
                 with torch.cuda.stream(sb):
-                    env_ops.pack_obs(b["next_obs"], b["packet_head"], b["packet_count"], b["packet_hits"])
+                    env_ops.pack_obs(b["next_obs"], b["packet_head"], b["packet_mask"], b["packet_dir"], b["packet_count"], b["packet_vals"])
                     pin["packet"][:n1].copy_(b["host_packet"][:n1], non_blocking=True)
                 b["obs"].copy_(b["next_obs"])
                 if auto_reset:
@@ -280,11 +279,11 @@ class VecMarineNavEnv:
                 self._refresh_host_dense()                        # more returns than the list holds: dense block this once
             else:
                 if n_hits > pin["tier1"]:                         # the rest of the list (rare: > 6.25 % of the beam slots)
-                    lo, hi = pin["tier1_bytes"], self.buf["packet_offsets"]["hits"] + 12 * n_hits
+                    lo, hi = pin["tier1_bytes"], self.buf["packet_offsets"]["vals"] + 8 * n_hits
                     pin["packet"][lo:hi].copy_(self.buf["host_packet"][lo:hi], non_blocking=True)
                     torch.cuda.current_stream().synchronize()
                 self._expander.expand(pin["obs"].data_ptr(), pin["head"].data_ptr(), pin["done"].data_ptr() if auto_reset else None,
-                                      pin["hits"].data_ptr(), n_hits)
+                                      pin["mask"].data_ptr(), pin["dir"].data_ptr(), pin["vals"].data_ptr())
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
 
     def tables_written(self):

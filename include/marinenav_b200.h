@@ -138,13 +138,15 @@ int mnv_scatter_rows_host(const uint8_t* d_mask, const float* d_rows, float* h_r
 
 /* Host-boundary helper: compact transport of the observation block d_obs f32 [E][obs_dim] (obs_dim = 4 + 2 * n_beams).  A beam
  * without a return is exactly (0, 0) (marinenav_env.py:318-320) and few beams carry one, so the kernel writes
- *   d_head  f32 [E][4]            the 4 head values of every row
- *   d_count u32 [4]               d_count[0] = number of beams with a return (may exceed `capacity`: the list is then truncated)
- *   d_hits  u32 [capacity][3]     (env << 8 | beam, bits of x, bits of y) per return, in no particular order
- * for ONE device -> host copy; libmnv_host.so (include/mnv_host.h) expands it into the dense block on the host.  E < 2^24,
- * n_beams <= 256.  One memset node + one kernel on `stream`. */
-int mnv_pack_obs(const float* d_obs, int64_t E, int32_t obs_dim, float* d_head, uint32_t* d_count, uint32_t* d_hits,
-                 int64_t capacity, void* stream);
+ *   d_head  f32 [E][4]              the 4 head values of every row
+ *   d_mask  u32 [E][W]              W = ceil(n_beams / 32); bit b of environment e: beam b has a return
+ *   d_dir   u32 [ceil(E / 32)]      where the returns of environments 32 g .. 32 g + 31 start in d_vals
+ *   d_count u32 [4]                 d_count[0] = number of returns (may exceed `capacity`: the tail is then not written)
+ *   d_vals  f32 [capacity][2]       (x, y) of a group's returns, environment by environment, beam by beam
+ * for ONE device -> host copy; libmnv_host.so (include/mnv_host.h) expands it into the dense block on the host.
+ * One memset node + one kernel on `stream`. */
+int mnv_pack_obs(const float* d_obs, int64_t E, int32_t obs_dim, float* d_head, uint32_t* d_mask, uint32_t* d_dir,
+                 uint32_t* d_count, float* d_vals, int64_t capacity, void* stream);
 
 /* ================================ replay buffer (thirdparty/IQN/replay_buffer.py) ===========================
  * Device-resident ReplayBuffer of the vectorised trainer.  Ring arrays (caller-owned, `capacity` transitions):

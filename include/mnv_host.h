@@ -23,9 +23,11 @@ int        mnvh_threads(const mnvh_pool* p);
 /* obs holds a complete dense block (after a reset / a dense refresh): rebuild the bookkeeping of non-zero beam slots. */
 void mnvh_rescan(mnvh_pool* p, float* obs);
 
-/* One packet -> obs, in place: head f32 [E][4]; hits u32 [n_hits][3] = (env << 8 | beam, bits of x, bits of y);
+/* One packet of mnv_pack_obs -> obs, in place: head f32 [E][4]; mask u32 [E][ceil(n_beams / 32)] (bit b: beam b has a
+ * return); dir u32 [ceil(E / 32)] (where the returns of environments 32 g .. 32 g + 31 start in vals); vals f32 [.][2];
  * skip u8 [E] (may be NULL): rows the caller has already written (left alone, then re-scanned). */
-void mnvh_expand(mnvh_pool* p, float* obs, const float* head, const uint8_t* skip, const uint32_t* hits, uint32_t n_hits);
+void mnvh_expand(mnvh_pool* p, float* obs, const float* head, const uint8_t* skip, const uint32_t* mask, const uint32_t* dir,
+                 const float* vals);
 
 #ifdef __cplusplus
 }

@@ -348,29 +348,37 @@ def test_learn_loop_reproduces_reference_trace(golden_dir):
 
 
 def test_pack_obs_matches_numpy():
-    """mnv_pack_obs: head of every row + one (env << 8 | beam, x, y) entry per beam with a return; the count keeps counting
-    past the list capacity (the caller's overflow signal)."""
+    """mnv_pack_obs: head of every row, beam masks, and per group of 32 environments the (x, y) of its returns in
+    (environment, beam) order starting at dir[g]; the count keeps counting past the capacity (the overflow signal)."""
     from distributional_rl_navigation_b200 import env_ops
     rs = np.random.RandomState(0)
     for E, nb, p_hit, cap in ((1000, 11, 0.05, 4096), (4097, 64, 0.5, 200000), (33, 11, 1.0, 100), (64, 11, 0.0, 64)):
-        D = 4 + 2 * nb
+        D, W, G = 4 + 2 * nb, (nb + 31) // 32, (E + 31) // 32
         obs = np.zeros((E, D), np.float32)
         obs[:, :4] = rs.randn(E, 4)
         hit = rs.rand(E, nb) < p_hit
         pts = (rs.randn(E, nb, 2) * 4).astype(np.float32); pts[~hit] = 0.0
         obs[:, 4:] = pts.reshape(E, -1)
-        head = torch.zeros(E, 4, device="cuda"); count = torch.zeros(4, dtype=torch.int32, device="cuda")
-        hits = torch.zeros(cap, 3, dtype=torch.int32, device="cuda")
-        env_ops.pack_obs(torch.from_numpy(obs).cuda(), head, count, hits)
+        dev = dict(device="cuda")
+        head = torch.zeros(E, 4, **dev); count = torch.zeros(4, dtype=torch.int32, **dev)
+        mask = torch.zeros(E, W, dtype=torch.int32, **dev); dir_ = torch.zeros(G, dtype=torch.int32, **dev)
+        vals = torch.zeros(cap, 2, **dev)
+        env_ops.pack_obs(torch.from_numpy(obs).cuda(), head, mask, dir_, count, vals)
         n = int(count[0])
         assert n == int(hit.sum())
         assert np.array_equal(head.cpu().numpy(), obs[:, :4])
-        got = hits.cpu().numpy().view(np.uint32)[:min(n, cap)]
-        e, b = (got[:, 0] >> 8).astype(np.int64), (got[:, 0] & 255).astype(np.int64)
-        assert hit[e, b].all() and len(set(zip(e.tolist(), b.tolist()))) == len(e)          # distinct, all real returns
-        assert np.array_equal(got[:, 1:].view(np.float32), pts[e, b])
-        if n <= cap:
-            assert len(e) == n                                                              # ... and all of them
+        m = mask.cpu().numpy().view(np.uint32)
+        for b in range(nb):
+            assert np.array_equal((m[:, b // 32] >> np.uint32(b % 32)) & 1, hit[:, b].astype(np.uint32))
+        d, v = dir_.cpu().numpy().view(np.uint32), vals.cpu().numpy()
+        starts = sorted(int(x) for g, x in enumerate(d) if hit[32 * g:32 * g + 32].any())
+        sizes = sorted(int(hit[32 * g:32 * g + 32].sum()) for g in range(G) if hit[32 * g:32 * g + 32].any())
+        assert len(set(starts)) == len(starts) and sum(sizes) == n                    # disjoint runs that tile [0, n)
+        for g in range(G):
+            blk = pts[32 * g:32 * g + 32][hit[32 * g:32 * g + 32]]
+            lo = int(d[g])
+            k = max(0, min(len(blk), cap - lo))
+            assert np.array_equal(v[lo:lo + k], blk[:k])
 
 
 def test_step_host_hit_list_tiers_and_overflow():
@@ -385,9 +393,9 @@ def test_step_host_hit_list_tiers_and_overflow():
         a.reset(); b.reset()
         if cap is not None:
             a.buf["packet_offsets"]["hit_cap"] = cap
-            a.buf["packet_hits"] = a.buf["packet_hits"][:cap]
+            a.buf["packet_vals"] = a.buf["packet_vals"][:cap]
         pin = a._pin()
-        pin["tier1"], pin["tier1_bytes"] = tier1, a.buf["packet_offsets"]["hits"] + 12 * tier1
+        pin["tier1"], pin["tier1_bytes"] = tier1, a.buf["packet_offsets"]["vals"] + 8 * tier1
         seen_hits = 0
         for t in range(25):
             act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)

@@ -26,16 +26,25 @@ def dense_block(rs, E, nb, p_hit):
 
 
 def pack(obs, rs):
-    """What mnv_pack_obs writes: head, and (env << 8 | beam, x bits, y bits) per beam with a return, in any order."""
+    """What mnv_pack_obs writes: head, the beam masks, and per group of 32 environments a contiguous run of (x, y) values
+    (environment by environment, beam by beam) that starts at dir[g]; the groups' runs sit in the list in any order."""
     E, D = obs.shape
-    pts = obs[:, 4:].reshape(E, -1, 2)
-    e, b = np.nonzero((pts[..., 0] != 0) | (pts[..., 1] != 0))
-    order = rs.permutation(len(e))
-    e, b = e[order], b[order]
-    hits = np.zeros((len(e), 3), np.uint32)
-    hits[:, 0] = (e.astype(np.uint32) << 8) | b.astype(np.uint32)
-    hits[:, 1:] = pts[e, b].view(np.uint32)
-    return np.ascontiguousarray(obs[:, :4]), hits
+    nb = (D - 4) // 2
+    W, G = (nb + 31) // 32, (E + 31) // 32
+    pts = obs[:, 4:].reshape(E, nb, 2)
+    hit = (pts[..., 0] != 0) | (pts[..., 1] != 0)
+    mask = np.zeros((E, W), np.uint32)
+    for b in range(nb):
+        mask[:, b // 32] |= (hit[:, b].astype(np.uint32) << np.uint32(b % 32))
+    dir_ = np.zeros(G, np.uint32)
+    vals = np.zeros((int(hit.sum()) + 1, 2), np.float32)
+    pos = 0
+    for g in rs.permutation(G):
+        dir_[g] = pos
+        blk = pts[32 * g:32 * g + 32][hit[32 * g:32 * g + 32]]
+        vals[pos:pos + len(blk)] = blk
+        pos += len(blk)
+    return np.ascontiguousarray(obs[:, :4]), mask, dir_, vals
 
 
 def ptr(a):
@@ -46,20 +55,20 @@ def ptr(a):
 def test_expand_follows_dense_blocks(E, nb, threads):
     rs = np.random.RandomState(E + threads)
     ex = _hostlib.Expander(E, 4 + 2 * nb, n_threads=threads, cpu_first=-1)
-    assert ex.n_threads == min(threads, E)
+    assert ex.n_threads == min(threads, (E + 31) // 32)
     truth = dense_block(rs, E, nb, 0.3)
     out = truth.copy()
     ex.rescan(ptr(out))                                         # a dense refresh (what reset_host does)
     for step in range(12):
         nxt = dense_block(rs, E, nb, [0.04, 0.5, 0.0, 1.0][step % 4])
-        head, hits = pack(nxt, rs)
+        head, mask, dir_, vals = pack(nxt, rs)
         skip = None
         if step % 3 == 1:                                       # auto-reset rows: the "GPU" has written them already
             skip = (rs.rand(E) < 0.1).astype(np.uint8)
             fresh = dense_block(rs, E, nb, 0.2)
             nxt[skip != 0] = fresh[skip != 0]
             out[skip != 0] = fresh[skip != 0]
-        ex.expand(ptr(out), ptr(head), None if skip is None else ptr(skip), ptr(hits), len(hits))
+        ex.expand(ptr(out), ptr(head), None if skip is None else ptr(skip), ptr(mask), ptr(dir_), ptr(vals))
         np.testing.assert_array_equal(out, nxt)
     ex.close()
 
@@ -72,5 +81,8 @@ def test_default_thread_split_by_local_rank(monkeypatch):
     n, first = _hostlib.default_threads_and_first_cpu()
     assert 1 <= n <= max(1, min(8, n_cpu // 2))
     cpus = sorted(os.sched_getaffinity(0))
+    assert first == -1                                          # no pinning unless MNV_HOST_PIN=1
+    monkeypatch.setenv("MNV_HOST_PIN", "1")
+    n, first = _hostlib.default_threads_and_first_cpu()
     if cpus == list(range(cpus[0], cpus[0] + n_cpu)) and n <= n_cpu // 2:
         assert first == cpus[0] + max(1, n_cpu // 2)
