@@ -18,7 +18,7 @@ INFO_STRINGS = _lib.INFO_STRINGS
 
 class VecMarineNavEnv:
     def __init__(self, num_envs, seed=0, schedule=None, device="cuda:0", num_cores=8, num_obs=5, min_start_goal_dis=25.0,
-                 num_beams=11, max_cores=None, max_obstacles=None, pdl_prefetch=True):
+                 num_beams=11, max_cores=None, max_obstacles=None, pdl_prefetch=True, host_transport="auto"):
         if not torch.cuda.is_available():
             raise _lib.MarinenavError("VecMarineNavEnv needs a CUDA device (there is no CPU fallback)")
         _lib.load()
@@ -28,6 +28,20 @@ class VecMarineNavEnv:
         # for every sequence of this class: mnv_reset is always followed by mnv_observe, table uploads are host copies, and
         # tables_written() fences device-side edits (the facade's setters).  MNV_PDL in the environment overrides (lab use).
         self.pdl_prefetch = bool(pdl_prefetch) and os.environ.get("MNV_PDL") is None
+        # How step_host ships the observation block to the host (same results either way):
+        #   "dense"    one 6.8 MB device -> host copy of the f32 [E, obs_dim] block (the DMA engine writes the rows): fastest
+        #              when this process has the PCIe link and the host memory system to itself (measured 200 us per
+        #              65 536-env step vs 223 us compact on the 16-vCPU single-GPU box);
+        #   "compact"  ~2 MB packet (head + list of sonar returns, mnv_pack_obs) expanded by host threads (libmnv_host.so):
+        #              4x fewer bytes over PCIe, which is what binds when the GPUs of a node share the host (8 ranks dense:
+        #              547 us per step);
+        #   "auto"     compact iff several ranks share this node (LOCAL_WORLD_SIZE > 1).  MNV_HOST_TRANSPORT overrides.
+        t = os.environ.get("MNV_HOST_TRANSPORT", host_transport)
+        if t == "auto":
+            t = "compact" if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1 else "dense"
+        if t not in ("dense", "compact"):
+            raise ValueError(f"host_transport must be 'auto', 'dense' or 'compact' (got {t!r})")
+        self.host_transport = t
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         self.sd = seed
@@ -224,8 +238,11 @@ class VecMarineNavEnv:
                 env_ops.step(b, params, action=pin["action"], obs=b["next_obs"])    # actions read zero-copy from the pinned buffer
                 sb.wait_stream(sa)
                 with torch.cuda.stream(sb):
-                    env_ops.pack_obs(b["next_obs"], b["packet_head"], b["packet_mask"], b["packet_dir"], b["packet_count"], b["packet_vals"])
-                    pin["packet"][:n1].copy_(b["host_packet"][:n1], non_blocking=True)
+                    if self.host_transport == "compact":
+                        env_ops.pack_obs(b["next_obs"], b["packet_head"], b["packet_mask"], b["packet_dir"], b["packet_count"], b["packet_vals"])
+                        pin["packet"][:n1].copy_(b["host_packet"][:n1], non_blocking=True)
+                    else:
+                        pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["rdi_pack"].copy_(b["rdi_pack"], non_blocking=True)
                 b["obs"].copy_(b["next_obs"])
                 if auto_reset:
                     env_ops.reset(b, self.rng_key, self.rng_pos, rp, mask=b["done"])
@@ -263,17 +280,21 @@ class VecMarineNavEnv:
             self.params()
             if auto_reset:
                 self.reset_params()
-            key = (self._params_key, self._reset_key if auto_reset else None, bool(auto_reset))
+            key = (self._params_key, self._reset_key if auto_reset else None, bool(auto_reset), self.host_transport)
             entry = self._host_graphs.get(key)
             if entry is None:
                 self._host_graphs.clear()                         # parameters changed: the old graph holds stale constants
                 entry = self._host_graphs[key] = self._capture_host_step(auto_reset)
-            if self._host_dirty:
+            compact = self.host_transport == "compact"
+            if compact and self._host_dirty:
                 self._expander.rescan(pin["obs"].data_ptr())
                 self._host_dirty = False
             entry[0].replay()
             self.total_timesteps += self.num_envs * self.global_step_multiplier
             torch.cuda.current_stream().synchronize()
+            if not compact:
+                self._host_dirty = True
+                return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
             n_hits = int(pin["count_np"][0])
             if n_hits > self.buf["packet_offsets"]["hit_cap"]:
                 self._refresh_host_dense()                        # more returns than the list holds: dense block this once
@@ -299,9 +320,11 @@ class VecMarineNavEnv:
         return pin["obs"].numpy()
 
     def host_api_description(self):
-        return ("VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step; the "
-                "observation block travels as head + list of sonar returns (mnv_pack_obs) and is expanded into the dense numpy "
-                f"array by libmnv_host.so on {self._expander.n_threads if self._pinned else '?'} host threads)")
+        how = ("the observation block travels as head + list of sonar returns (mnv_pack_obs) and is expanded into the dense numpy "
+               f"array by libmnv_host.so on {self._expander.n_threads if self._pinned else '?'} host threads") \
+            if self.host_transport == "compact" else "dense device -> host copy of the observation block under the masked reset"
+        return ("VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step; "
+                f"host_transport={self.host_transport}: {how})")
 
     def h2d_bytes_per_step(self):
         return self.num_envs * 4
@@ -310,7 +333,9 @@ class VecMarineNavEnv:
         self._pin()
         # the packet copy (reward | done | info | head | count | first tier of the hit list); the zero-copy rows of the
         # re-observed environments (a few hundred x obs_dim x 4 bytes) come on top
-        return self._pinned["tier1_bytes"]
+        if self.host_transport == "compact":
+            return self._pinned["tier1_bytes"]
+        return self.num_envs * self.obs_dim * 4 + self._pinned["rdi_pack"].numel()
 
     def close(self):
         pass

@@ -181,11 +181,12 @@ def test_learn_single_env_and_vectorised_smoke(tmp_path, golden_dir):
     assert torch.isfinite(agent3.qnetwork_local.flat).all()
 
 
-def test_step_host_matches_device_step():
+@pytest.mark.parametrize("transport", ["dense", "compact"])
+def test_step_host_matches_device_step(transport):
     """The overlapped host-buffer path returns exactly what the plain device path computes (incl. auto-reset rows)."""
     from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
     E = 3000
-    a = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+    a = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0, host_transport=transport)
     b = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
     o_a, o_b = a.reset_host().copy(), b.reset().cpu().numpy()
     assert np.array_equal(o_a, o_b)
@@ -203,12 +204,14 @@ def test_step_host_matches_device_step():
     assert n_done > 0
 
 
-def test_step_host_graph_equals_eager_and_survives_patch_overflow():
-    """graph=True (two-stream CUDA graph, re-observed rows written zero-copy into the pinned array) == graph=False (eager,
-    one stream), also when every episode ends in the same step and after a parameter edit (re-capture)."""
+@pytest.mark.parametrize("transport", ["dense", "compact"])
+def test_step_host_graph_equals_eager_and_survives_patch_overflow(transport):
+    """graph=True (two-stream CUDA graph, re-observed rows written zero-copy into the pinned array; dense block or compact
+    packet + native host expander) == graph=False (eager, one stream), also when every episode ends in the same step and
+    after a parameter edit (re-capture)."""
     from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
     E = 2500
-    a = VecMarineNavEnv(E, seed=5, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+    a = VecMarineNavEnv(E, seed=5, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0, host_transport=transport)
     b = VecMarineNavEnv(E, seed=5, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
     a.reset(); b.reset()
     rng = np.random.RandomState(3)
@@ -388,7 +391,7 @@ def test_step_host_hit_list_tiers_and_overflow():
     E = 1500
     rng = np.random.RandomState(11)
     for tier1, cap in ((4, None), (4, 16)):
-        a = VecMarineNavEnv(E, seed=9, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+        a = VecMarineNavEnv(E, seed=9, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0, host_transport="compact")
         b = VecMarineNavEnv(E, seed=9, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
         a.reset(); b.reset()
         if cap is not None:
