@@ -550,7 +550,8 @@ def iqn_bench(args, dev, world):
         out[f"act_{name}_ms_per_env_batch"] = act_ms
         out[f"act_{name}_acts_per_s"] = world * E * 1e3 / act_ms
         out[f"act_{name}_tflops"] = IQN_ACT_FLOP_PER_ENV * E / (act_ms * 1e-3) / 1e12
-    out["act_config"] = f"{E} envs x K=32 taus: torch.rand taus + iqn_act_tc (tcgen05, bf16 operands) / iqn_forward (fp32) + eps-greedy"
+    out["act_config"] = (f"{E} envs x K=32 taus, eps-greedy: tc = iqn_act_tc_sample (encoder pre-pass + tcgen05 kernel, bf16 operands, taus / "
+                         "coin / random action from the in-kernel Philox stream); fp32 = torch.rand taus + iqn_forward + eager eps-greedy")
 
     # rollout + learn (BASELINE configs[2]): act -> env step (+auto-reset) -> replay append -> 1 update of 1024 per vector step
     env = VecMarineNavEnv(E, seed=12345 + E * (int(os.environ.get("RANK", 0))), device=dev, num_cores=N_CORES, num_obs=N_OBS,

@@ -67,7 +67,9 @@ _SIGNATURES = {
     "iqn_clip_adam": (C.c_int, [_vp] * 6 + [C.c_float] * 6 + [_i64, _vp, _vp]),
     "iqn_packed_tc_bytes": (C.c_int, []),
     "iqn_pack_tc": (C.c_int, [_vp, _vp, _vp]),
-    "iqn_act_tc": (C.c_int, [_vp] * 5 + [C.c_float] + [_vp] * 3 + [_i64, _i32, _vp]),
+    "iqn_act_scratch_bytes": (C.c_int64, [_i64]),
+    "iqn_act_tc": (C.c_int, [_vp] * 5 + [C.c_float] + [_vp] * 4 + [_i64, _i32, _vp]),
+    "iqn_act_tc_sample": (C.c_int, [_vp] * 3 + [_i32, _vp, C.c_float, C.c_float, C.c_uint64, C.c_uint64] + [_vp] * 4 + [_i64, _vp]),
 }
 
 _lib = None

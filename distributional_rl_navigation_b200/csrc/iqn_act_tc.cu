@@ -7,12 +7,18 @@
 // (132 GFLOP per vector step).  Only the argmax of the mean is consumed, so operands are bf16 with fp32 accumulation
 // (the fp32 FFMA kernel in iqn.cu stays the parity path for training and for act_eval's quantile outputs).
 //
+// A pre-pass (iqn_encode_kernel) computes what depends on the environment alone: the three observation encoders
+// (fp32 FFMA, 208 features, stored as bf16 -- they only ever multiply a bf16 operand) and, for the adaptive policy, the
+// CVaR level of agent.py:249-267.  The quantile samples come either from the caller (parity harnesses) or from the
+// counter-based Philox stream (seed, step) inside the kernel, which then also applies the epsilon-greedy rule of
+// agent.py:200-203 -- no tau tensor in HBM, no separate random / select launches.
+//
 // One persistent CTA per SM, 512 threads = two groups of 256, each group owns one tile (128 rows = 4 environments x 32 taus)
 // at a time, so that one group's epilogue overlaps the other group's MMAs:
 //   * all four weight matrices (with their bias as one extra reduction column) live in shared memory for the whole kernel
 //     as bf16 K-major core-matrix tiles (pre-packed by iqn_pack_tc, 73 KB);
 //   * A operands are produced in-kernel and written straight into the same UMMA canonical layout (no swizzle):
-//       A0 = cos(pi i tau)            (rotation recurrence from one sincospif per row)
+//       A0 = cos(pi i tau)            (Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1}: one FFMA per feature)
 //       A1 = bf16(relu(D1 + b_c)) * bf16(feat)    A2 = relu(D2 + b_1)    A3 = relu(D3 + b_2)     (cvt.rn.relu.bf16x2 + mul.bf16x2)
 //   * one elected thread issues tcgen05.mma (M = 128, N = 208 / 64 / 64 / 16, K = 16 per instruction), accumulators in
 //     TMEM (208 + 64 + 64 + 16 columns), completion through tcgen05.commit -> mbarrier;
@@ -23,6 +29,7 @@
 #include <math.h>
 
 #include "iqn_common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -44,8 +51,7 @@ struct __align__(128) GroupSmem {
     // ONE operand region per group: A0 (cos features, 16 KB) is consumed by layer 1 before the first epilogue overwrites
     // the region with A1 (52 KB); A2 / A3 (16 KB each) are written after layers 2 / 3 have consumed A1 / A2.
     __nv_bfloat16 a1[kRows * kK1];
-    __nv_bfloat16 feat[kEnvsPerTile * kFeat];            // observation-encoder output, bf16 (it only ever multiplies a bf16 operand)
-    float x[kEnvsPerTile * 28];
+    __nv_bfloat16 feat[kEnvsPerTile * kFeat];            // observation-encoder output of the tile's environments (from the pre-pass)
     float tau[kRows];
     unsigned long long bar;
 };
@@ -53,7 +59,6 @@ struct __align__(128) GroupSmem {
 struct __align__(128) Smem {
     __nv_bfloat16 wc[kWcEl], w1[kW1El], w2[kW2El], w3[kW3El];
     GroupSmem g[2];
-    float enc[oCW];                        // the three observation encoders (weights + biases, fp32, state_dict order)
     uint32_t tmem_base;
 };
 
@@ -183,13 +188,85 @@ __device__ __forceinline__ void issue_layer(const __nv_bfloat16* A, const __nv_b
     umma_commit(bar);
 }
 
+// ---- pre-pass: everything that depends on the environment alone -------------------------------------------------------
+// ObsEncoder's three encoders (model.py:125-127,169-172; no activation) for 32 environments per CTA: lane = environment
+// (its 26 observation values in registers), warp w = features [26 w, 26 w + 26) -- the weights of a feature are the same
+// for all lanes (shared-memory broadcast, 16-byte loads), so the loop is FFMA-bound.  Output: bf16 [B][208] rows, written
+// as one contiguous block per CTA.  Optionally the adaptive CVaR level of IQNAgent.adjust_cvar (agent.py:249-267):
+// closest sonar return / 10 if closer than 10 m, else 1; a beam with |x|, |y| < 1e-3 is "no return".
+constexpr int kEncEnvs = 32, kEncThreads = 256;
+
+__global__ void __launch_bounds__(kEncThreads)
+iqn_encode_kernel(const float* __restrict__ P, const float* __restrict__ obs, __nv_bfloat16* __restrict__ feat,
+                  float* __restrict__ cvar_out, long long B)
+{
+    __shared__ __align__(16) float s_w[oCW];                          // encoder weights + biases, state_dict order
+    __shared__ __align__(16) float s_x[kEncEnvs * kObs];
+    __shared__ __align__(16) __nv_bfloat16 s_f[kEncEnvs * kFeat];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const long long e0 = (long long)blockIdx.x * kEncEnvs;
+    const int n_env = (B - e0) < kEncEnvs ? (int)(B - e0) : kEncEnvs;
+    for (int i = t; i < oCW; i += kEncThreads) s_w[i] = P[i];
+    for (int i = t; i < n_env * kObs; i += kEncThreads) s_x[i] = obs[e0 * kObs + i];
+    __syncthreads();
+    float x[kObs];
+#pragma unroll
+    for (int k = 0; k < kObs; ++k) x[k] = lane < n_env ? s_x[lane * kObs + k] : 0.f;
+    for (int f = w * 26; f < w * 26 + 26; ++f) {                       // warp-uniform: no divergence
+        float v;
+        if (f < 16) v = fmaf(s_w[oVW + f * 2 + 1], x[1], fmaf(s_w[oVW + f * 2], x[0], s_w[oVB + f]));
+        else if (f < 32) v = fmaf(s_w[oGW + (f - 16) * 2 + 1], x[3], fmaf(s_w[oGW + (f - 16) * 2], x[2], s_w[oGB + f - 16]));
+        else {
+            const float* wr = s_w + oSW + (f - 32) * 22;               // 22 weights, 8-byte aligned rows
+            v = s_w[oSB + f - 32];
+#pragma unroll
+            for (int k = 0; k < 22; k += 2) {
+                const float2 w2 = *reinterpret_cast<const float2*>(wr + k);
+                v = fmaf(w2.x, x[4 + k], v); v = fmaf(w2.y, x[5 + k], v);
+            }
+        }
+        s_f[lane * kFeat + f] = __float2bfloat16_rn(v);
+    }
+    if (cvar_out != nullptr && w == 0 && lane < n_env) {
+        float closest = INFINITY;
+#pragma unroll
+        for (int b = 0; b < (kObs - 4) / 2; ++b) {
+            const float px = x[4 + 2 * b], py = x[5 + 2 * b];
+            if (fabsf(px) < 1e-3f && fabsf(py) < 1e-3f) continue;     // agent.py:256-258
+            closest = fminf(closest, sqrtf(px * px + py * py));
+        }
+        cvar_out[e0 + lane] = closest < 10.0f ? closest / 10.0f : 1.0f;   // agent.py:262-265 (sonar range 10 m)
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(s_f);
+    uint4* dst = reinterpret_cast<uint4*>(feat + e0 * kFeat);          // 32 x 416 bytes per CTA: 16-byte aligned
+    for (int i = t; i < n_env * kFeat / 8; i += kEncThreads) dst[i] = src[i];
+}
+
+struct ActArgs {
+    const __nv_bfloat16* Wp; const __nv_bfloat16* feat; const float* taus; const float* cvar; float cvar_scalar;
+    float* qmean; int32_t* greedy; int32_t* action; float* debug; long long B;
+    unsigned long long seed, step; float eps; int sample;             // sample != 0: taus / epsilon-greedy from Philox(seed, step)
+};
+
+// Random streams of the sampling mode, all from Philox4x32-10 keyed by `seed`, counter = (env, sub-stream, step):
+//   sub-stream 0..7: the 32 taus of the environment (4 per draw, torch.rand-style 24-bit uniforms, model.py:149)
+//   sub-stream 8:    .x -> the epsilon-greedy coin (greedy iff u > eps, agent.py:200), .y -> the random action (:203)
+__device__ __forceinline__ philox::u4 act_draw(const ActArgs& A, long long env, unsigned sub)
+{
+    return philox::philox4x32_10(philox::u4{(uint32_t)env, (uint32_t)((unsigned long long)env >> 32) ^ (sub << 24), (uint32_t)A.step, (uint32_t)(A.step >> 32)},
+                                  (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+}
+
 // Two groups of 256 threads per CTA, each owning one 128-row tile at a time (its own A buffers, TMEM columns and
 // mbarrier): while one group runs an epilogue on the CUDA cores the other group's MMAs occupy the tensor core.
 __global__ void __launch_bounds__(kThreads, 1)
-iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ obs,
-                  const float* __restrict__ taus, const float* __restrict__ cvar, float cvar_scalar,
-                  float* __restrict__ qmean, int32_t* __restrict__ greedy, float* __restrict__ debug, long long B)
+iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
 {
+    const __nv_bfloat16* __restrict__ Wp = A.Wp;
+    const float* __restrict__ taus = A.taus; const float* __restrict__ cvar = A.cvar; const float cvar_scalar = A.cvar_scalar;
+    float* __restrict__ qmean = A.qmean; int32_t* __restrict__ greedy = A.greedy; float* __restrict__ debug = A.debug;
+    const long long B = A.B;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -202,7 +279,6 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
         const uint4* src = reinterpret_cast<const uint4*>(Wp);
         uint4* dst = reinterpret_cast<uint4*>(s.wc);        // wc, w1, w2, w3 are contiguous in Smem and in the packed buffer
         for (int i = t; i < kPackedTcEl / 8; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = t; i < oCW; i += kThreads) s.enc[i] = P[i];
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(kTmemCols) : "memory");
@@ -223,58 +299,56 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
     const long long tile_step = (long long)gridDim.x * 2;
     long long tile = (long long)blockIdx.x * 2 + g;
 
-    // inputs of a tile, one element per thread: threads 0..127 carry tau of row tg, threads 128..239 one element of the
-    // tile's 4 x 26 observation block
-    auto load_in = [&](long long tl) -> float {
-        if (tl >= n_tiles) return 0.f;
-        if (tg < kRows) {
-            const long long b = tl * kEnvsPerTile + tg / kTaus;
-            return b < B ? taus[b * kTaus + (tg % kTaus)] * (cvar != nullptr ? cvar[b] : cvar_scalar) : 0.f;   // model.py:153
-        }
-        const int i = tg - kRows, e = i / 28, k = i % 28;
-        const long long b = tl * kEnvsPerTile + e;
-        return (e < kEnvsPerTile && b < B && k < kObs) ? obs[b * kObs + k] : 0.f;
+    // inputs of a tile, prefetched one tile ahead: threads 0..127 carry tau of row tg (from the caller's tensor, or drawn
+    // from the Philox stream), threads 128..231 one 16-byte chunk of the tile's 4 x 208 bf16 encoder features
+    auto load_tau = [&](long long tl) -> float {
+        if (tl >= n_tiles || tg >= kRows) return 0.f;
+        const long long b = tl * kEnvsPerTile + tg / kTaus;
+        if (b >= B) return 0.f;
+        const int k = tg % kTaus;
+        float u;
+        if (A.sample) {
+            const philox::u4 r = act_draw(A, b, (unsigned)(k >> 2));
+            const uint32_t rk = (k & 3) == 0 ? r.x : ((k & 3) == 1 ? r.y : ((k & 3) == 2 ? r.z : r.w));
+            u = philox::u01(rk);
+        } else u = taus[b * kTaus + k];
+        return u * (cvar != nullptr ? cvar[b] : cvar_scalar);          // model.py:153
     };
-    float n_in = load_in(tile);
+    auto load_feat = [&](long long tl) -> uint4 {
+        const int i = tg - kRows;                                       // chunk i = (env i / 26, 8 features (i % 26) * 8 ...)
+        if (tl >= n_tiles || i < 0 || i >= kEnvsPerTile * (kFeat / 8)) return make_uint4(0u, 0u, 0u, 0u);
+        const long long b = tl * kEnvsPerTile + i / (kFeat / 8);
+        if (b >= B) return make_uint4(0u, 0u, 0u, 0u);
+        return __ldg(reinterpret_cast<const uint4*>(A.feat + b * kFeat) + (i % (kFeat / 8)));
+    };
+    float n_tau = load_tau(tile);
+    uint4 n_feat = load_feat(tile);
 
     for (; tile < n_tiles; tile += tile_step) {
         const long long env0 = tile * kEnvsPerTile;
-        if (tg < kRows) gs.tau[tg] = n_in;
-        else if (tg < kRows + kEnvsPerTile * 28) gs.x[tg - kRows] = n_in;
-        n_in = load_in(tile + tile_step);                    // prefetch the next tile's inputs: consumed one iteration later
+        if (tg < kRows) gs.tau[tg] = n_tau;
+        else if (tg < kRows + kEnvsPerTile * (kFeat / 8)) reinterpret_cast<uint4*>(gs.feat)[tg - kRows] = n_feat;
+        n_tau = load_tau(tile + tile_step);                  // prefetch the next tile's inputs: consumed one iteration later
+        n_feat = load_feat(tile + tile_step);
         group_sync(g);
-        // ---- observation encoders (fp32, model.py:169-172) ----
-        for (int idx = tg; idx < kEnvsPerTile * kFeat; idx += kGroupThreads) {
-            const int e = idx / kFeat, f = idx % kFeat;
-            const float* x = gs.x + e * 28;
-            float v;
-            if (f < 16) v = fmaf(s.enc[oVW + f * 2 + 1], x[1], fmaf(s.enc[oVW + f * 2], x[0], s.enc[oVB + f]));
-            else if (f < 32) {
-                const int q = f - 16;
-                v = fmaf(s.enc[oGW + q * 2 + 1], x[3], fmaf(s.enc[oGW + q * 2], x[2], s.enc[oGB + q]));
-            } else {
-                const int q = f - 32;
-                v = s.enc[oSB + q];
-#pragma unroll
-                for (int k = 0; k < 22; ++k) v = fmaf(s.enc[oSW + q * 22 + k], x[4 + k], v);
-            }
-            gs.feat[idx] = __float2bfloat16_rn(v);
-        }
-        // ---- A0 = cos(pi * i * tau), i = 0..63: thread (row, half) fills i in [32 half, 32 half + 32) by rotating
-        //      (cos, sin)(i pi tau) with (cos, sin)(pi tau), starting from an exact sincospif at i = 32 half ----
+        // ---- A0 = cos(pi i tau), i = 0..63 (model.py:130,155): thread (row, half) fills i in [32 half, 32 half + 32) with the
+        //      Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1} (one FFMA per feature), started from cos.approx of the
+        //      argument reduced to [-pi, pi].  The values are rounded to bf16 (2^-9 relative) right away; the recurrence's
+        //      error over 32 steps stays below 1e-4. ----
         {
             const float tau = gs.tau[row];
-            float c1, s1, c, sn;
-            sincospif(tau, &s1, &c1);
-            sincospif(32.f * (float)half * tau, &sn, &c);
+            auto cospi = [](float x) { x = x - 2.f * rintf(0.5f * x); return __cosf(3.14159265358979f * x); };
+            const float c1 = cospi(tau), two_c1 = 2.f * c1;
+            float cm = half == 0 ? c1 : cospi(31.f * tau);           // c_{i-1} at i = 32 half  (c_{-1} = c_1)
+            float c = half == 0 ? 1.f : cospi(32.f * tau);           // c_i
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     v[j] = c;
-                    const float c2 = fmaf(c, c1, -sn * s1), s2 = fmaf(sn, c1, c * s1);
-                    c = c2; sn = s2;
+                    const float cn = fmaf(two_c1, c, -cm);
+                    cm = c; c = cn;
                 }
                 store_chunk(gs.a1, row, half * 4 + kc, kK0, v);
             }
@@ -406,6 +480,14 @@ iqn_act_tc_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__
                     if (q[a] > bv) { bv = q[a]; best = a; }                             // np.argmax: first maximum (agent.py:201)
                 }
                 if (greedy != nullptr) greedy[b] = best;
+                if (A.action != nullptr) {                                                  // agent.py:200-203
+                    int act = best;
+                    if (A.sample && A.eps > 0.f) {
+                        const philox::u4 r = act_draw(A, b, 8u);
+                        if (!(philox::u01(r.x) > A.eps)) act = (int)__umulhi(r.y, (uint32_t)kAct);
+                    }
+                    A.action[b] = act;
+                }
             }
         }
         tc_fence_before();
@@ -448,27 +530,57 @@ extern "C" int iqn_pack_tc(const float* d_params, void* d_packed_tc, void* strea
     return mnv_launch_status("iqn_pack_tc");
 }
 
-extern "C" int iqn_act_tc(const float* d_params, const void* d_packed_tc, const float* d_obs, const float* d_taus,
-                          const float* d_cvar, float cvar_scalar, float* d_qmean, int32_t* d_greedy, float* d_debug,
-                          int64_t B, int32_t n_tau, void* stream)
+extern "C" int64_t iqn_act_scratch_bytes(int64_t B) { return B > 0 ? ((B + kEncEnvs - 1) / kEncEnvs) * kEncEnvs * kFeat * 2 : 0; }
+
+namespace {
+
+int launch_act(const float* d_params, const void* d_packed_tc, const float* d_obs, float* d_cvar_adaptive, void* d_scratch, ActArgs A,
+               cudaStream_t st, const char* what)
 {
-    if (B <= 0) { mnv_set_error("iqn_act_tc: B must be > 0"); return MNV_E_SIZE; }
-    if (n_tau != kTaus) { mnv_set_error("iqn_act_tc: n_tau must be 32 (ObsEncoder.K), got %d", n_tau); return MNV_E_CAPACITY; }
-    MNV_CHECK_PTR(d_params); MNV_CHECK_PTR(d_packed_tc); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_taus);
-    if (d_qmean == nullptr && d_greedy == nullptr) { mnv_set_error("iqn_act_tc: no output"); return MNV_E_NULL; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     static unsigned long long attr_mask = 0;                       // the attribute is per device
     if (dev >= 64 || !((attr_mask >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(iqn_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute(iqn_act_tc): %s", cudaGetErrorString(e)); return (int)e; }
+        if (e != cudaSuccess) { mnv_set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e)); return (int)e; }
         if (dev < 64) attr_mask |= 1ull << dev;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long B = A.B;
+    iqn_encode_kernel<<<(unsigned)((B + kEncEnvs - 1) / kEncEnvs), kEncThreads, 0, st>>>(d_params, d_obs, (__nv_bfloat16*)d_scratch, d_cvar_adaptive, B);
+    A.Wp = (const __nv_bfloat16*)d_packed_tc; A.feat = (const __nv_bfloat16*)d_scratch;
     const long long n_tiles = (B + kEnvsPerTile - 1) / kEnvsPerTile;
     const long long pairs = (n_tiles + 1) / 2;                     // two tile groups per CTA
     const int grid = (int)(pairs < sms ? pairs : sms);
-    iqn_act_tc_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(
-        d_params, (const __nv_bfloat16*)d_packed_tc, d_obs, d_taus, d_cvar, cvar_scalar, d_qmean, d_greedy, d_debug, B);
-    return mnv_launch_status("iqn_act_tc");
+    iqn_act_tc_kernel<<<grid, kThreads, sizeof(Smem), st>>>(A);
+    return mnv_launch_status(what);
+}
+
+}  // namespace
+
+extern "C" int iqn_act_tc(const float* d_params, const void* d_packed_tc, const float* d_obs, const float* d_taus,
+                          const float* d_cvar, float cvar_scalar, float* d_qmean, int32_t* d_greedy, float* d_debug,
+                          void* d_scratch, int64_t B, int32_t n_tau, void* stream)
+{
+    if (B <= 0) { mnv_set_error("iqn_act_tc: B must be > 0"); return MNV_E_SIZE; }
+    if (n_tau != kTaus) { mnv_set_error("iqn_act_tc: n_tau must be 32 (ObsEncoder.K), got %d", n_tau); return MNV_E_CAPACITY; }
+    MNV_CHECK_PTR(d_params); MNV_CHECK_PTR(d_packed_tc); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_taus); MNV_CHECK_PTR(d_scratch);
+    if (d_qmean == nullptr && d_greedy == nullptr) { mnv_set_error("iqn_act_tc: no output"); return MNV_E_NULL; }
+    ActArgs A{};
+    A.taus = d_taus; A.cvar = d_cvar; A.cvar_scalar = cvar_scalar; A.qmean = d_qmean; A.greedy = d_greedy; A.debug = d_debug; A.B = B;
+    return launch_act(d_params, d_packed_tc, d_obs, nullptr, d_scratch, A, (cudaStream_t)stream, "iqn_act_tc");
+}
+
+extern "C" int iqn_act_tc_sample(const float* d_params, const void* d_packed_tc, const float* d_obs, int32_t adaptive_cvar,
+                                 float* d_cvar, float cvar_scalar, float eps, uint64_t seed, uint64_t step,
+                                 int32_t* d_action, int32_t* d_greedy, float* d_qmean, void* d_scratch, int64_t B, void* stream)
+{
+    if (B <= 0) { mnv_set_error("iqn_act_tc_sample: B must be > 0"); return MNV_E_SIZE; }
+    MNV_CHECK_PTR(d_params); MNV_CHECK_PTR(d_packed_tc); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_scratch);
+    if (d_action == nullptr) { mnv_set_error("iqn_act_tc_sample: null action output"); return MNV_E_NULL; }
+    if (adaptive_cvar && d_cvar == nullptr) { mnv_set_error("iqn_act_tc_sample: adaptive CVaR needs the d_cvar buffer"); return MNV_E_NULL; }
+    ActArgs A{};
+    A.cvar = adaptive_cvar ? d_cvar : nullptr; A.cvar_scalar = cvar_scalar; A.qmean = d_qmean; A.greedy = d_greedy; A.action = d_action; A.B = B;
+    A.seed = seed; A.step = step; A.eps = eps; A.sample = 1;
+    return launch_act(d_params, d_packed_tc, d_obs, adaptive_cvar ? d_cvar : nullptr, d_scratch, A, (cudaStream_t)stream, "iqn_act_tc_sample");
 }

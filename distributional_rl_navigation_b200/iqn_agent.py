@@ -166,16 +166,20 @@ class IQNAgent:
 
     def act_batch(self, obs, eps, cvar=1.0, adaptive=False, tensor_cores=True):
         """Epsilon-greedy actions (int32 [E]) for a device batch of observations; K = 32 taus per env drawn on the device.
-        tensor_cores=True: tcgen05 kernel (bf16 operands, only the argmax is consumed); False: the fp32 parity kernel."""
+        tensor_cores=True: ONE call of iqn_act_tc_sample (tcgen05 kernel, bf16 operands -- only the argmax is consumed; the
+        taus, the epsilon-greedy coin and the random action come from the kernel's Philox stream keyed by the agent seed
+        and an act counter, the adaptive CVaR level from its pre-pass); False: the fp32 parity kernel with torch-drawn taus."""
         net = self.qnetwork_local
         E = obs.shape[0]
         with torch.cuda.device(self.device):
+            if tensor_cores:
+                self._act_calls = getattr(self, "_act_calls", 0) + 1
+                action, _, _ = iqn_ops.act_tc_sample(net.flat, net.packed_tc, obs, eps, int(self.seed) + 0x5EED0000, self._act_calls,
+                                                     cvar=cvar, adaptive=adaptive)
+                return action
             taus = torch.rand(E, net.K, device=self.device, generator=self.gen)
             cv = self.adjust_cvar_batch(obs) if adaptive else cvar
-            if tensor_cores:
-                _, greedy = iqn_ops.act_tc(net.flat, net.packed_tc, obs, taus, cv)
-            else:
-                _, _, greedy = iqn_ops.forward(net.flat, net.packed, obs, taus, cv, want_quantiles=False, want_greedy=True)
+            _, _, greedy = iqn_ops.forward(net.flat, net.packed, obs, taus, cv, want_quantiles=False, want_greedy=True)
             if eps <= 0.0:
                 return greedy
             explore = torch.rand(E, device=self.device, generator=self.gen) <= eps           # agent.py:200: greedy iff random() > eps

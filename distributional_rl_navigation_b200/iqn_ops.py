@@ -101,6 +101,19 @@ def pack_tc(params, packed_tc):
     _lib.check(_lib.load().iqn_pack_tc(_lib.ptr(params), _lib.ptr(packed_tc), _stream()), "iqn_pack_tc")
 
 
+_act_scratch = {}
+
+
+def _scratch_for(B, dev):
+    """bf16 encoder-feature scratch of the acting kernels, cached per (device, size)."""
+    need = int(_lib.load().iqn_act_scratch_bytes(B))
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _act_scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = _act_scratch[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+    return buf
+
+
 def act_tc(params, packed_tc, obs, taus, cvar=1.0, want_qmean=False, want_greedy=True, debug=None):
     """get_qvals + argmax on the tensor cores (bf16 operands): obs f32 [B,26], taus f32 [B,32]."""
     B, n_tau = taus.shape
@@ -112,6 +125,26 @@ def act_tc(params, packed_tc, obs, taus, cvar=1.0, want_qmean=False, want_greedy
     qm = torch.empty(B, N_ACTIONS, dtype=torch.float32, device=dev) if want_qmean else None
     gr = torch.empty(B, dtype=torch.int32, device=dev) if want_greedy else None
     rc = _lib.load().iqn_act_tc(_lib.ptr(params), _lib.ptr(packed_tc), _lib.ptr(obs), _lib.ptr(taus), _lib.ptr(cvar_t),
-                                C.c_float(cvar_s), _lib.ptr(qm), _lib.ptr(gr), _lib.ptr(debug), B, n_tau, _stream())
+                                C.c_float(cvar_s), _lib.ptr(qm), _lib.ptr(gr), _lib.ptr(debug), _lib.ptr(_scratch_for(B, dev)),
+                                B, n_tau, _stream())
     _lib.check(rc, "iqn_act_tc")
     return qm, gr
+
+
+def act_tc_sample(params, packed_tc, obs, eps, seed, step, cvar=1.0, adaptive=False, action=None, want_greedy=False, want_qmean=False,
+                  cvar_out=None):
+    """IQNAgent.act / act_adaptive for an env batch with taus and the epsilon-greedy draw from the device Philox stream
+    (seed, step): -> (action i32 [B], greedy i32 [B] | None, qmean f32 [B, 9] | None)."""
+    B = obs.shape[0]
+    _f32(params, N_PARAMS, "params"); _f32(obs, B * OBS_DIM, "obs")
+    dev = obs.device
+    action = torch.empty(B, dtype=torch.int32, device=dev) if action is None else action
+    gr = torch.empty(B, dtype=torch.int32, device=dev) if want_greedy else None
+    qm = torch.empty(B, N_ACTIONS, dtype=torch.float32, device=dev) if want_qmean else None
+    if adaptive and cvar_out is None:
+        cvar_out = torch.empty(B, dtype=torch.float32, device=dev)
+    rc = _lib.load().iqn_act_tc_sample(_lib.ptr(params), _lib.ptr(packed_tc), _lib.ptr(obs), int(bool(adaptive)), _lib.ptr(cvar_out),
+                                       C.c_float(float(cvar)), C.c_float(float(eps)), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
+                                       _lib.ptr(action), _lib.ptr(gr), _lib.ptr(qm), _lib.ptr(_scratch_for(B, dev)), B, _stream())
+    _lib.check(rc, "iqn_act_tc_sample")
+    return action, gr, qm

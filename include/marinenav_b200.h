@@ -224,14 +224,26 @@ int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d
 /* Acting forward on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in TMEM): get_qvals + argmax for a
  * whole env batch, K = n_tau = 32 (ObsEncoder.K, model.py:118).  Same inputs as iqn_forward; outputs d_qmean f32 [B][9]
  * and/or d_greedy i32 [B].  d_packed_tc: iqn_packed_tc_bytes() bytes of bf16 weight tiles, refresh with iqn_pack_tc after
- * any parameter change.  d_debug (optional, NULL in production): 45 056 floats = the four raw accumulators of tile 0
- * (128x208, 128x64, 128x64, 128x16) for diagnostics.  Q-values differ from the fp32 path by bf16 rounding (~1e-2
- * relative): use where only the argmax is consumed (agent.py:200-203); iqn_forward stays the parity path. */
+ * any parameter change.  d_scratch: iqn_act_scratch_bytes(B) bytes (the bf16 observation-encoder features written by the
+ * pre-pass kernel of the same call).  d_debug (optional, NULL in production): 45 056 floats = the four raw accumulators of
+ * tile 0 (128x208, 128x64, 128x64, 128x16) for diagnostics.  Q-values differ from the fp32 path by bf16 rounding (~1e-2
+ * relative): use where only the argmax is consumed (agent.py:200-203); iqn_forward stays the parity path.  Two launches. */
 int     iqn_packed_tc_bytes(void);
 int     iqn_pack_tc(const float* d_params, void* d_packed_tc, void* stream);
+int64_t iqn_act_scratch_bytes(int64_t B);
 int     iqn_act_tc(const float* d_params, const void* d_packed_tc, const float* d_obs, const float* d_taus,
                    const float* d_cvar, float cvar_scalar, float* d_qmean, int32_t* d_greedy, float* d_debug,
-                   int64_t B, int32_t n_tau, void* stream);
+                   void* d_scratch, int64_t B, int32_t n_tau, void* stream);
+
+/* IQNAgent.act / act_adaptive for a whole env batch with the randomness drawn ON THE DEVICE (agent.py:186-215): the 32 taus of
+ * every environment (model.py:149) and the epsilon-greedy coin + random action (agent.py:200-203: greedy iff u > eps) come
+ * from the counter-based Philox4x32-10 stream keyed by `seed`, counter (environment, sub-stream, step) -- reproducible per
+ * (seed, step), no tau tensor in memory, no separate random / select launches.  adaptive_cvar != 0: the CVaR level of every
+ * environment is adjust_cvar(obs) (agent.py:249-267), computed by the pre-pass and left in d_cvar f32 [B]; otherwise
+ * cvar_scalar.  Outputs: d_action i32 [B] (required), d_greedy i32 [B] and d_qmean f32 [B][9] (optional).  Two launches. */
+int     iqn_act_tc_sample(const float* d_params, const void* d_packed_tc, const float* d_obs, int32_t adaptive_cvar,
+                          float* d_cvar, float cvar_scalar, float eps, uint64_t seed, uint64_t step,
+                          int32_t* d_action, int32_t* d_greedy, float* d_qmean, void* d_scratch, int64_t B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,3 +90,59 @@ def test_qmean_and_argmax_vs_fp32_kernel(weights, B):
         assert np.array_equal(gr.cpu().numpy()[clear], g32.cpu().numpy()[clear])
         assert (gr.cpu().numpy() == g32.cpu().numpy()).mean() > 0.9
         assert np.array_equal(gr.cpu().numpy(), qm.argmax(axis=1))
+
+
+def _philox(ctr, key):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    x, y, z, w = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0, p1 = M0 * x, M1 * z
+        x, y, z, w = (p1 >> 32) ^ y ^ k0, p1 & 0xffffffff, (p0 >> 32) ^ w ^ k1, p0 & 0xffffffff
+        k0, k1 = (k0 + W0) & 0xffffffff, (k1 + W1) & 0xffffffff
+    return x, y, z, w
+
+
+def model_draws(seed, step, B):
+    """The kernel's random streams (csrc/iqn_act_tc.cu act_draw): taus [B, 32], epsilon coin u [B], random action [B]."""
+    key = (seed & 0xffffffff, seed >> 32)
+    taus = np.zeros((B, 32), np.float32); coin = np.zeros(B, np.float32); rnd = np.zeros(B, np.int64)
+    for b in range(B):
+        for sub in range(8):
+            r = _philox((b & 0xffffffff, (b >> 32) ^ (sub << 24), step & 0xffffffff, step >> 32), key)
+            taus[b, 4 * sub:4 * sub + 4] = [np.float32(v >> 8) * np.float32(1.0 / 16777216.0) for v in r]
+        r = _philox((b & 0xffffffff, (b >> 32) ^ (8 << 24), step & 0xffffffff, step >> 32), key)
+        coin[b] = np.float32(r[0] >> 8) * np.float32(1.0 / 16777216.0)
+        rnd[b] = (r[1] * 9) >> 32
+    return taus, coin, rnd
+
+
+def test_sampling_mode_follows_the_philox_model(weights):
+    """iqn_act_tc_sample == iqn_act_tc fed with the model's taus; epsilon-greedy: greedy iff coin > eps (agent.py:200),
+    else the model's random action; adaptive CVaR = adjust_cvar (agent.py:249-267) of every observation."""
+    from distributional_rl_navigation_b200.iqn_agent import IQNAgent
+    rs = np.random.RandomState(5)
+    B, seed, step = 300, 0x1234ABCD5678, 77
+    x = (rs.randn(B, 26) * 3).astype(np.float32); x[:, 4:] *= (rs.rand(B, 22) > 0.6); x[::7, 4:] = 0.0
+    flat, ptc = setup(weights)
+    xd = torch.from_numpy(x).to(DEV)
+    taus, coin, rnd = model_draws(seed, step, B)
+    assert 0.0 <= taus.min() and taus.max() < 1.0 and abs(taus.mean() - 0.5) < 0.01
+    for adaptive in (False, True):
+        cv_ref = np.array([IQNAgent.adjust_cvar(None, o) for o in x], np.float32) if adaptive else None
+        cvar_arg = 0.7
+        if adaptive:                                      # the pre-pass's own CVaR levels (fp32 norm; checked against adjust_cvar below)
+            cvar_arg = torch.zeros(B, device=DEV)
+            iqn_ops.act_tc_sample(flat, ptc, xd, 0.0, seed, step, adaptive=True, cvar_out=cvar_arg)
+        qm_ref, gr_ref = iqn_ops.act_tc(flat, ptc, xd, torch.from_numpy(taus).to(DEV), cvar_arg, want_qmean=True)
+        for eps in (0.0, 0.3, 1.0):
+            cvar_out = torch.zeros(B, device=DEV)
+            act, gr, qm = iqn_ops.act_tc_sample(flat, ptc, xd, eps, seed, step, cvar=0.7, adaptive=adaptive, want_greedy=True,
+                                                want_qmean=True, cvar_out=cvar_out)
+            if adaptive:
+                np.testing.assert_allclose(cvar_out.cpu().numpy(), cv_ref, rtol=1e-6)
+            assert torch.equal(gr, gr_ref) and torch.equal(qm, qm_ref)            # same taus -> bit-identical forward
+            want = np.where(coin > eps, gr_ref.cpu().numpy(), rnd) if eps > 0 else gr_ref.cpu().numpy()
+            np.testing.assert_array_equal(act.cpu().numpy(), want)
+    a2, _, _ = iqn_ops.act_tc_sample(flat, ptc, xd, 1.0, seed, step + 1)
+    assert not np.array_equal(a2.cpu().numpy(), rnd) and set(a2.cpu().numpy().tolist()) <= set(range(9))
