@@ -359,13 +359,9 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- layer 1: D1[128 x 208] = A0 . Wc^T ----
-        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
-            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.wc, kK0, kFeat, tmem + kD1, &gs.bar); }
-            __syncwarp();
-            mbar_wait(&gs.bar, phase);
-        }
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.wc, kK0, kFeat, tmem + kD1, &gs.bar); }
+        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
         phase ^= 1;
-        group_sync(g);
         tc_fence_after();
         {
             // this warp's 104 columns [104 half, 104 half + 104) = 3 x 32 + 8
@@ -397,13 +393,9 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- layer 2: D2[128 x 64] = A1 . W1^T ----
-        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
-            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kK1, kHid, tmem + kD2, &gs.bar); }
-            __syncwarp();
-            mbar_wait(&gs.bar, phase);
-        }
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kK1, kHid, tmem + kD2, &gs.bar); }
+        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
         phase ^= 1;
-        group_sync(g);
         tc_fence_after();
         {
             float v[32];
@@ -420,13 +412,9 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- layer 3: D3[128 x 64] = A2 . W2^T ----
-        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
-            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w2, kK2, kHid, tmem + kD3, &gs.bar); }
-            __syncwarp();
-            mbar_wait(&gs.bar, phase);
-        }
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w2, kK2, kHid, tmem + kD3, &gs.bar); }
+        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
         phase ^= 1;
-        group_sync(g);
         tc_fence_after();
         {
             float v[32];
@@ -443,13 +431,9 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- output layer: D4[128 x 16] = A3 . W3^T, then mean over the 32 taus of each env (one warp) + argmax ----
-        if (tg < 32) {                                   // one warp issues and polls; the other seven sleep in the barrier
-            if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w3, kK3, kN4, tmem + kD4, &gs.bar); }
-            __syncwarp();
-            mbar_wait(&gs.bar, phase);
-        }
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w3, kK3, kN4, tmem + kD4, &gs.bar); }
+        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
         phase ^= 1;
-        group_sync(g);
         tc_fence_after();
         if (half == 0) {
             float q[kN4];
@@ -490,8 +474,7 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
                 }
             }
         }
-        tc_fence_before();
-        group_sync(g);
+        tc_fence_before();                                   // (the next tile's first barrier orders these TMEM reads before its MMAs)
     }
 
     // ---- teardown ----

@@ -186,6 +186,14 @@ class IQNAgent:
             rand_a = torch.randint(0, self.action_size, (E,), device=self.device, generator=self.gen, dtype=torch.int32)
             return torch.where(explore, rand_a, greedy)
 
+    def _act_with(self, enc_params, packed_tc, obs, eps, cvar=1.0, adaptive=False):
+        """act_batch's tensor-core path on an explicit weight snapshot (encoder parameters + bf16 tiles)."""
+        self._act_calls = getattr(self, "_act_calls", 0) + 1
+        with torch.cuda.device(self.device):
+            action, _, _ = iqn_ops.act_tc_sample(enc_params, packed_tc, obs, eps, int(self.seed) + 0x5EED0000, self._act_calls,
+                                                 cvar=cvar, adaptive=adaptive)
+        return action
+
     # ---- learning --------------------------------------------------------------------------------------------------------
     def train(self, experiences, taus=None):
         """agent.py:269-304.  experiences = (states [B,26], actions [B,1] int64, rewards [B,1], next_states, dones [B,1]).
@@ -373,7 +381,7 @@ class IQNAgent:
 
     def learn_vec(self, total_timesteps, train_env, eval_config=None, eval_freq=None, eval_log_path=None, batch_size=None,
                   updates_per_step=1, learning_starts=None, target_update_interval=None, buffer_size=None, verbose=False,
-                  on_step=None, sample_without_replacement=False):
+                  on_step=None, sample_without_replacement=False, policy_lag=1):
         """Vectorised counterpart of learn(): E transitions per env.step, device replay buffer, `updates_per_step` IQN
         updates of `batch_size` per vector step once `learning_starts` transitions were collected.
 
@@ -385,7 +393,13 @@ class IQNAgent:
         `target_update_interval` updates... see below) count UPDATES x UPDATE_EVERY, so that `target_update_interval` and
         `eval_freq` keep the reference's meaning ("learning timesteps" = transitions since learning started).
         Schedules (epsilon, curriculum, termination) are keyed on GLOBAL transitions: E x world size per vector step.
-        Order inside a learning step as in the reference: train, then soft_update, then evaluation (agent.py:129-148)."""
+        Order inside a learning step as in the reference: train, then soft_update, then evaluation (agent.py:129-148).
+
+        policy_lag=1 (default): the acting forward of vector step t uses the weights after the updates of step t-2 -- a
+        snapshot (encoder weights + bf16 tensor-core tiles, two alternating buffers) the learner stream leaves behind after
+        every vector step -- so that act(t) never waits for an update in flight and the learner runs entirely beside the
+        env stream (act -> step -> reset).  Two vector steps of lag are far inside what the replay buffer's off-policy data
+        already tolerates.  policy_lag=0: act waits for the latest weights, like the reference's loop."""
         E = train_env.num_envs
         world = mdist.world_size()
         if world > 1:                                           # every rank must run the same number of all-reduces
@@ -418,11 +432,24 @@ class IQNAgent:
             self._learn_stream = torch.cuda.Stream(device=self.device)
         learn_stream = self._learn_stream
         ev_step, ev_added, ev_update = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        net = self.qnetwork_local
+        n_enc = iqn_ops.N_ENCODER_PARAMS
+        snaps = [(net.flat[:n_enc].clone(), net.packed_tc.clone(), torch.cuda.Event()) for _ in range(2)] if policy_lag else None
+        vstep = 0
         learn_stream.wait_stream(env_stream)
         while self.current_timestep <= total_timesteps:
             eps = self.linear_eps(total_timesteps)
-            env_stream.wait_event(ev_update)                      # the weights of the last update (no-op before the first)
-            action = self.act_batch(obs, eps)
+            if policy_lag:
+                # the learner leaves snaps[k % 2] behind at the end of vector step k; while step vstep acts, the learner may
+                # still be writing snaps[(vstep - 1) % 2], so act reads the other one, snaps[vstep % 2] = the weights after
+                # step vstep - 2 (complete long ago: no waiting in steady state), and the learner of THIS step overwrites
+                # it only after the step kernel, i.e. after this act has finished reading
+                w_flat, w_tc, w_ev = snaps[vstep % 2]
+                env_stream.wait_event(w_ev)
+                action = self._act_with(w_flat, w_tc, obs, eps)
+            else:
+                env_stream.wait_event(ev_update)                  # the weights of the last update (no-op before the first)
+                action = self.act_batch(obs, eps)
             next_obs, reward, done, _ = train_env.step_begin(action)
             ev_step.record(env_stream)
             self.current_timestep += E * world
@@ -449,7 +476,12 @@ class IQNAgent:
                     if verbose:
                         losses.append(loss.clone())
                     do_eval = eval_config is not None and bool(eval_freq) and self.learning_timestep >= next_eval
+                if policy_lag:                                    # leave the weights of this vector step behind for act(vstep + 2)
+                    s_flat, s_tc, s_ev = snaps[vstep % 2]
+                    s_flat.copy_(net.flat[:n_enc]); s_tc.copy_(net.packed_tc)
+                    s_ev.record(learn_stream)
                 ev_update.record(learn_stream)
+            vstep += 1
             train_env.step_finish(auto_reset=True)                # env stream: overlaps the update
             env_stream.wait_event(ev_added)                       # the replay append has read the previous obs
             obs.copy_(train_env.buf["obs"])

@@ -6,6 +6,7 @@ import torch
 from . import _lib
 
 N_PARAMS = 35785
+N_ENCODER_PARAMS = 4144      # velocity / goal / sensor encoders: the first tensors of the flat vector (iqn_common.cuh oCW)
 N_PACKED = 30720
 N_ACTIONS = 9
 OBS_DIM = 26
@@ -134,9 +135,12 @@ def act_tc(params, packed_tc, obs, taus, cvar=1.0, want_qmean=False, want_greedy
 def act_tc_sample(params, packed_tc, obs, eps, seed, step, cvar=1.0, adaptive=False, action=None, want_greedy=False, want_qmean=False,
                   cvar_out=None):
     """IQNAgent.act / act_adaptive for an env batch with taus and the epsilon-greedy draw from the device Philox stream
-    (seed, step): -> (action i32 [B], greedy i32 [B] | None, qmean f32 [B, 9] | None)."""
+    (seed, step): -> (action i32 [B], greedy i32 [B] | None, qmean f32 [B, 9] | None).  `params`: the flat parameter vector,
+    or just its first N_ENCODER_PARAMS floats (the observation encoders -- all the pre-pass reads)."""
     B = obs.shape[0]
-    _f32(params, N_PARAMS, "params"); _f32(obs, B * OBS_DIM, "obs")
+    if not (params.is_cuda and params.dtype == torch.float32 and params.is_contiguous() and params.numel() >= N_ENCODER_PARAMS):
+        raise _lib.MarinenavError("params: expected a contiguous CUDA float32 vector holding at least the encoder parameters")
+    _f32(obs, B * OBS_DIM, "obs")
     dev = obs.device
     action = torch.empty(B, dtype=torch.int32, device=dev) if action is None else action
     gr = torch.empty(B, dtype=torch.int32, device=dev) if want_greedy else None
