@@ -51,7 +51,7 @@ def create_eval_configs(eval_env):
     return eval_config
 
 
-def run_trial(device, params, num_envs, batch_size):
+def run_trial(device, params, num_envs, batch_size, updates_per_step=1):
     import marinenav_env  # noqa: F401  (registers 'marinenav_env-v0')
     from distributional_rl_navigation_b200 import distributed as mdist
     from distributional_rl_navigation_b200 import marinenav_env as impl
@@ -86,7 +86,8 @@ def run_trial(device, params, num_envs, batch_size):
         model = IQNAgent(train_env.get_state_space_dimension(), train_env.get_action_space_dimension(), device=device,
                          seed=params["seed"] + 100, BATCH_SIZE=batch_size)
         model.learn_vec(total_timesteps=params["total_timesteps"], train_env=train_env, eval_config=eval_config,
-                        eval_freq=params["eval_freq"], eval_log_path=log_dir, batch_size=batch_size)
+                        eval_freq=params["eval_freq"], eval_log_path=log_dir, batch_size=batch_size,
+                        updates_per_step=updates_per_step, sample_without_replacement=True)
     train_env.close(); eval_env.close()
     return exp_dir, model
 
@@ -97,7 +98,10 @@ def main():
     ap.add_argument("-D", "--device", dest="device", type=str, default="cuda:0", help="device to run all trials")
     ap.add_argument("--num-envs", type=int, default=0, help="environments per GPU of the vectorised trainer (0: single-env loop)")
     ap.add_argument("--batch-size", type=int, default=1024)
+    ap.add_argument("--updates-per-step", default="1", help="IQN updates per vector step, or 'reference' = the reference's replay "
+                    "ratio (one update of 32 per 4 transitions, agent.py:127-136) in vector form")
     args = ap.parse_args()
+    ups = args.updates_per_step if args.updates_per_step == "reference" else int(args.updates_per_step)
     params = json.load(args.config_file)
     trials = trial_params(params)
     stamp = datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
@@ -105,7 +109,7 @@ def main():
         args.device = "cuda:%d" % int(os.environ["LOCAL_RANK"])
     for p in trials:
         p["training_time"] = stamp
-        exp_dir, _ = run_trial(args.device, p, args.num_envs, args.batch_size)
+        exp_dir, _ = run_trial(args.device, p, args.num_envs, args.batch_size, ups)
         print("trial done:", exp_dir)
 
 
