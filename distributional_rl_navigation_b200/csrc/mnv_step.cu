@@ -442,46 +442,83 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         //      every beam.  Geometries whose intervals could wrap around (field of view >= pi, or more than 16 beams)
         //      flag every beam of every obstacle within reach (K.precise_bins = 0). ----
         {
-            const float cf = (float)c, sf = (float)s;
-            const unsigned all_beams = K.n_beams >= 32 ? 0xffffffffu : ((1u << K.n_beams) - 1u);
             unsigned short* my_bm = s_bm + tid * kBmStride;
 #pragma unroll
             for (int j4 = 0; j4 < kBmStride / 8; ++j4) reinterpret_cast<uint4*>(my_bm)[j4] = make_uint4(0u, 0u, 0u, 0u);
-            const unsigned sb1 = (bs1 >= 0 && bs1 < K.n_beams) ? (unsigned)(bs1 + 1) : 0u, sb2 = (bs2 >= 0 && bs2 < K.n_beams) ? (unsigned)(bs2 + 1) : 0u;
-            s_rel[tid] = rel | (sb1 << 16) | (sb2 << 24);   // [15:0] obstacles within reach, [23:16] / [31:24] Q10 candidate beams + 1
-            if (!K.precise_bins) beams = rel != 0u ? 0xffffffffu : 0u;
-            else {
-                unsigned todo = rel;
-                while (todo != 0u) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1u;
-                    const float dxf = (float)(ob[j * kBlock] - x), dyf = (float)(ob[(max_o + j) * kBlock] - y);
-                    const float rf = (float)ob[(2 * max_o + j) * kBlock];
-                    float qx = fmaf(cf, dxf, sf * dyf), qy = fmaf(cf, dyf, -sf * dxf);      // R^T (centre - pos)
-                    const float d2f = fmaf(qx, qx, qy * qy), rrf = rf * rf;
-                    unsigned bm = all_beams;
-                    const bool inside = d2f < rrf;
-                    if (fabsf(d2f - rrf) > 2e-3f * fmaxf(1.0f, rrf) && !(inside && d2f < 1.0f)) {
-                        float alpha = 1.57079632679f + 2e-3f;                               // inside: the half plane q . dir <= 1e-3
-                        if (inside) { qx = -qx; qy = -qy; }
-                        else alpha = asin_approx(fminf(1.0f, (rf + 1e-3f) * rsqrtf(d2f))) + 4e-4f;
-                        const float ci = (atan2_approx(qy, qx) - K.beam0f) * K.inv_phi;
-                        const float wi = fmaf(alpha, K.inv_phi, 1e-3f);
-                        const int lo = max(0, (int)ceilf(ci - wi)), hi = min(K.n_beams - 1, (int)floorf(ci + wi));
-                        bm = lo <= hi ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
-                    }
-                    my_bm[j] = (unsigned short)bm;
-                    beams |= bm;
-                }
-                if (rel != 0u) {                            // a beam that may be snapped to the vertical (Q10) is decided exactly
-                    if (sb1) beams |= 1u << (sb1 - 1u);
-                    if (sb2) beams |= 1u << (sb2 - 1u);
-                }
-            }
             // "no return" everywhere (marinenav_env.py:318-320); the exact tests overwrite the beams that hit
 #pragma unroll 4
             for (int b = 0; b < K.n_beams; ++b) *reinterpret_cast<float2*>(my_obs + 4 + 2 * b) = make_float2(0.0f, 0.0f);
         }
+    }
+
+    // ---- the intervals, warp-wide: an environment has ~1.3 obstacles within reach (at most 3-4 in a warp), so the
+    //      (environment, obstacle) pairs of the warp are compacted into a list (slots from a prefix sum of the per-lane
+    //      counts) and evaluated 32 pairs at a time, every lane busy; the evaluator fetches the owner's pose with shuffles
+    //      and leaves the beam mask in the owner's row of s_bm. ----
+    const unsigned sb1 = (live && bs1 >= 0 && bs1 < K.n_beams) ? (unsigned)(bs1 + 1) : 0u, sb2 = (live && bs2 >= 0 && bs2 < K.n_beams) ? (unsigned)(bs2 + 1) : 0u;
+    s_rel[tid] = rel | (sb1 << 16) | (sb2 << 24);           // [15:0] obstacles within reach, [23:16] / [31:24] Q10 candidate beams + 1
+    if (!K.precise_bins) beams = rel != 0u ? 0xffffffffu : 0u;
+    else {
+        const float cf = (float)c, sf = (float)s;
+        const unsigned all_beams = (1u << K.n_beams) - 1u;  // precise_bins implies <= 16 beams
+        const int cnt = __popc(rel);
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            int slot = incl - cnt;
+            unsigned todo = rel;
+            while (todo != 0u) {                            // pair: [4:0] owner lane, [8:5] obstacle
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                ring[slot++] = (unsigned short)((unsigned)lane | ((unsigned)j << 5));
+            }
+        }
+        __syncwarp();
+        const double* obw = s_ob + w0;
+        for (int base = 0; base < total; base += 32) {
+            const bool mine = base + lane < total;
+            const unsigned ent = mine ? ring[base + lane] : (unsigned)lane;
+            const int owner = ent & 31, j = ent >> 5;
+            const double ox_ = __shfl_sync(0xffffffffu, x, owner), oy_ = __shfl_sync(0xffffffffu, y, owner);
+            const float ocf = __shfl_sync(0xffffffffu, cf, owner), osf = __shfl_sync(0xffffffffu, sf, owner);
+            if (mine) {
+                const double* ob = obw + owner;
+                const float dxf = (float)(ob[j * kBlock] - ox_), dyf = (float)(ob[(max_o + j) * kBlock] - oy_);
+                const float rf = (float)ob[(2 * max_o + j) * kBlock];
+                float qx = fmaf(ocf, dxf, osf * dyf), qy = fmaf(ocf, dyf, -osf * dxf);      // R^T (centre - pos)
+                const float d2f = fmaf(qx, qx, qy * qy), rrf = rf * rf;
+                unsigned bm = all_beams;
+                const bool inside = d2f < rrf;
+                if (fabsf(d2f - rrf) > 2e-3f * fmaxf(1.0f, rrf) && !(inside && d2f < 1.0f)) {
+                    float alpha = 1.57079632679f + 2e-3f;                               // inside: the half plane q . dir <= 1e-3
+                    if (inside) { qx = -qx; qy = -qy; }
+                    else alpha = asin_approx(fminf(1.0f, (rf + 1e-3f) * rsqrtf(d2f))) + 4e-4f;
+                    const float ci = (atan2_approx(qy, qx) - K.beam0f) * K.inv_phi;
+                    const float wi = fmaf(alpha, K.inv_phi, 1e-3f);
+                    const int lo = max(0, (int)ceilf(ci - wi)), hi = min(K.n_beams - 1, (int)floorf(ci + wi));
+                    bm = lo <= hi ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+                }
+                s_bm[(w0 + owner) * kBmStride + j] = (unsigned short)bm;
+            }
+        }
+        __syncwarp();
+        if (rel != 0u) {                                    // union over my obstacles; a beam that may be snapped (Q10) is decided exactly
+            const unsigned short* my_bm = s_bm + tid * kBmStride;
+#pragma unroll
+            for (int j4 = 0; j4 < kBmStride / 8; ++j4) {
+                const uint4 v = reinterpret_cast<const uint4*>(my_bm)[j4];
+                beams |= v.x | v.y | v.z | v.w;
+            }
+            beams = (beams | (beams >> 16)) & 0xffffu;
+            if (sb1) beams |= 1u << (sb1 - 1u);
+            if (sb2) beams |= 1u << (sb2 - 1u);
+        }
+        __syncwarp();                                       // the list buffer is reused for the exact tests below
     }
 
     // ================= sonar (robot.py:125-198), warp-wide =================

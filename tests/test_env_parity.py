@@ -288,7 +288,7 @@ def test_reset_masked_and_stream_continuation():
     rp = _lib.default_reset_params()
     rp.num_cores, rp.num_obs, rp.min_start_goal_dis = 4, 8, 30.0
     env_ops.reset(buf, key, pos, rp)
-    first = {k: v.clone() for k, v in buf.items()}
+    first = {k: v.clone() for k, v in buf.items() if torch.is_tensor(v)}
     mask = torch.from_numpy((np.arange(E) % 5 == 0).astype(np.uint8)).to(DEV)
     env_ops.reset(buf, key, pos, rp, mask=mask)
     m = mask.bool()
