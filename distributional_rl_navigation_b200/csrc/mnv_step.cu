@@ -47,12 +47,10 @@ struct KParams {
     double snap_t1, snap_t2;        // pi/2 - beam_angle[0], 3pi/2 - beam_angle[0]   (Q10 pre-test, see snap_beam)
     float inv_phi, snap_tol;        // 1 / beam spacing, (1e-3 / spacing) + 1e-4 in beam-index units
     float beam0f; int precise_bins; // beam_angle[0]; 1: per-obstacle beam intervals (<= 16 beams, field of view < pi), 0: every beam of every obstacle within reach
+    int dense_bins;                 // dense kernel: per-obstacle beam intervals (<= 64 beams, field of view < pi)
     double beam_angle[MNV_MAX_BEAMS];
     double beam_cos[MNV_MAX_BEAMS];
     double beam_sin[MNV_MAX_BEAMS];
-    float2 beam_dirf[MNV_MAX_BEAMS];   // (cos, sin) of the beam in the robot frame, fp32, for the candidate filter
-    alignas(8) float beam_cosf[MNV_MAX_BEAMS + 2];   // the same as two planar arrays (beam pairs of the dense kernel; zero padded)
-    alignas(8) float beam_sinf[MNV_MAX_BEAMS + 2];
 };
 
 struct EnvPtrs {
@@ -146,30 +144,6 @@ __device__ __forceinline__ bool collides(double d2, double thr)
 // check_reach_goal (marinenav_env.py:338-342): sqrt(d2) <= goal_dis, decided like collides()
 __device__ __forceinline__ bool reaches(double d2, double thr) { return collides(d2, thr); }
 
-// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2: one issue slot for two lanes of the candidate filter) ----
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi)
-{
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, unsigned& lo, unsigned& hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 // programmatic dependent launch: no-ops unless the launch carries the programmatic-stream-serialization attribute
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -661,10 +635,12 @@ mnv_env_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
 //            mnv_env_kernel); the pose after the sub-steps goes to shared memory.  The other warps have their obstacle table
 //            in flight meanwhile; CTAs of different waves are in different phases, so the SM stays busy.
 //   phase 2  every warp takes 2 of the environments in turn, one WARP per environment, lane j owning obstacle j:
-//   * candidate filter: every lane tests its obstacle against TWO beams per FFMA2 (same fp32 test as mnv_env_kernel);
-//   * the exact fp64 tests are not run beam by beam (a beam has ~1.4 candidates, i.e. ~1.4 busy lanes): the candidate
-//     (beam, obstacle) pairs are appended in (beam, obstacle) order to a 32-entry ring in shared memory and evaluated 32
-//     at a time, one pair per lane (the obstacle's robot-frame centre comes from its owner lane by shuffle);
+//   * candidate beams: every lane computes ONE conservative interval of beam indices for its obstacle (the obstacle-major
+//     binning of mnv_env_kernel: fp32 atan2 / asin bounds with margins -- it can only add beams);
+//   * the candidate (beam, obstacle) pairs go beam-major into batches of <= 32 for the exact fp64 tests: per pass of 32
+//     beams, lane L collects the candidate obstacles of beam L (one ballot per beam), a prefix sum over the lanes' counts
+//     gives every beam its slot range and a batch is the longest run of whole beams that fits 32 slots (one ballot per
+//     batch); the batch is evaluated one pair per lane (the obstacle's robot-frame centre comes from its owner lane by shuffle);
 //   * the reference's ordered first-hit scan (robot.py:192-195, Q3) is rebuilt per beam from warp ballots restricted to
 //     the beam's SEGMENT of the batch (match.any on the beam index; a batch only holds complete beams):
 //       V  = ballot(valid hit) & segment                          valid = real root, 0 <= t <= range (robot.py:172-190)
@@ -730,7 +706,7 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 }
             }
             double c, s;
-            sincos(th, &s, &c);
+            sincos_heading(th, &s, &c);
 #pragma unroll
             for (int i = 0; i < MAXC; ++i) ck[i] *= (1.0 / (2.0 * MNV_PI));
             auto current = [&](double px, double py, double& ux, double& uy) {
@@ -748,7 +724,7 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             if (STEP) {
                 const int ai = action / 3, wi = action - 3 * ai;
                 const double acc = K.accel[ai], wdt = K.wdt[wi], cw = K.cos_wdt[wi], sw = K.sin_wdt[wi];
-                const double dis_before = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
+                const double dis_before = fast_sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
                 for (int it = 0; it < K.n_substeps; ++it) {
                     double ux, uy;
                     current(x, y, ux, uy);
@@ -770,8 +746,8 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                     c = c2; s = s2;
                     if (P.traj != nullptr) { P.traj[(long long)(2 * it) * E + e] = x; P.traj[(long long)(2 * it + 1) * E + e] = y; }
                 }
-                dis_after = sqrt(fma(gx - x, gx - x, (gy - y) * (gy - y)));
-                reward = K.pen_step + (dis_before - dis_after);            // marinenav_env.py:220,229
+                dis_after = fma(gx - x, gx - x, (gy - y) * (gy - y));        // kept SQUARED for the goal test (reaches())
+                reward = K.pen_step + (dis_before - fast_sqrt(dis_after));  // marinenav_env.py:220,229
             } else {
                 if (K.velocity_from_state) {
                     double ux, uy;
@@ -815,14 +791,6 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
         const double lim = K.range_slack + orad;
         const bool relevant = on && d2o <= lim * lim;              // reachable within the sonar range at all
         const bool borderline = relevant && fabs(d2o - rr) <= 1e-9 * rr;   // robot on the circle: never filter
-        // fp32 filter operands: sigma q (inside the circle the nearer root is in front iff tc <= 0), -(r^2 + 1e-3);
-        // "always a candidate" = q = 0 with a very negative nr, "never" = nr = +1e30
-        const float sg = d2o < rr ? -1.f : 1.f;
-        const float qxf = borderline ? 0.f : sg * (float)qx, qyf = borderline ? 0.f : sg * (float)qy;
-        const float nrf = !relevant ? 1e30f : (borderline ? -1e30f : -((float)rr + 1e-3f));
-        const f32x2 qx2 = pack2(qxf, qxf), qy2 = pack2(qyf, qyf), nqx2 = pack2(-qxf, -qxf), nr2 = pack2(nrf, nrf);
-        const f32x2 margin2 = pack2(1e-3f, 1e-3f);
-
         // ---- Q4: collision against the nearest CENTRE only (marinenav_env.py:329-336): warp arg-min ----
         double best_d2 = on ? d2o : INFINITY, best_r = orad;
         int best_i = lane;
@@ -863,7 +831,7 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
                 const double tc = fma(oqx, bx, oqy * by), cr = fma(oqx, by, -oqy * bx);
                 const double disc = fma(-cr, cr, orr2);
                 if (disc >= 0.0) {
-                    const double h = sqrt(disc);
+                    const double h = fast_sqrt(disc);
                     t = tc > 0.0 ? tc - h : tc + h;                // nearer root first (robot.py:184)
                     valid = (t <= K.range) && (t >= 0.0);
                 }
@@ -883,29 +851,70 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             n_pend = 0;
             __syncwarp();
         };
-        auto push = [&](bool cand, int b) {
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (bal == 0u) return;
-            const int cnt = __popc(bal);
-            if (n_pend + cnt > 32) drain();                        // a batch only holds complete beams (cnt <= 32)
-            if (cand) ring[n_pend + __popc(bal & lt_mask)] = (unsigned)lane | ((unsigned)b << 5);
-            n_pend += cnt;
-        };
-        for (int b = 0; b < n_beams; b += 2) {
-            // conservative fp32 filter (see mnv_env_kernel), two beams per FFMA2: cr^2 - r^2 - 1e-3 < 0 and tc + 1e-3 >= 0
-            const f32x2 bx2 = *reinterpret_cast<const f32x2*>(&K.beam_cosf[b]), by2 = *reinterpret_cast<const f32x2*>(&K.beam_sinf[b]);
-            const f32x2 tc = fma2(qx2, bx2, fma2(qy2, by2, margin2));
-            const f32x2 ncr = fma2(qy2, bx2, mul2(nqx2, by2));
-            const f32x2 nd = fma2(ncr, ncr, nr2);
-            unsigned t0, t1, d0, d1;
-            unpack2(tc, t0, t1); unpack2(nd, d0, d1);
-            bool c0 = (int)(d0 & ~t0) < 0, c1 = (int)(d1 & ~t1) < 0 && (b + 1 < n_beams);
-            if (b == bs1 || b == bs2) c0 = relevant;               // possibly snapped beam: its direction is not the table's
-            if (b + 1 == bs1 || b + 1 == bs2) c1 = relevant && (b + 1 < n_beams);
-            push(c0, b);
-            push(c1, b + 1);
+        // ---- which beams can my obstacle return a hit on?  ONE conservative interval of beam indices per obstacle
+        //      (the obstacle-major binning of mnv_env_kernel: robot outside the circle -> |beta_b - atan2(q)| < asin(r / d),
+        //      inside -> the half plane q . dir <= 0; fp32 with margins, so it can only add beams); wrap-prone geometries
+        //      (field of view >= pi) flag every beam of every obstacle within reach. ----
+        int blo = 1, bhi = 0;                                      // candidate beams [blo, bhi] (empty unless within reach)
+        if (relevant) {
+            blo = 0; bhi = n_beams - 1;
+            float fqx = (float)qx, fqy = (float)qy;
+            const float rf = (float)orad, d2f = fmaf(fqx, fqx, fqy * fqy), rrf = rf * rf;
+            const bool inside = d2f < rrf;
+            if (K.dense_bins && !borderline && fabsf(d2f - rrf) > 2e-3f * fmaxf(1.0f, rrf) && !(inside && d2f < 1.0f)) {
+                float alpha = 1.57079632679f + 2e-3f;
+                if (inside) { fqx = -fqx; fqy = -fqy; }
+                else alpha = asin_approx(fminf(1.0f, (rf + 1e-3f) * rsqrtf(d2f))) + 4e-4f;
+                const float ci = (atan2_approx(fqy, fqx) - K.beam0f) * K.inv_phi;
+                const float wi = fmaf(alpha, K.inv_phi, 1e-3f);
+                blo = max(0, (int)ceilf(ci - wi)); bhi = min(n_beams - 1, (int)floorf(ci + wi));
+            }
         }
-        if (n_pend > 0) drain();
+        const int sn1 = (relevant && bs1 >= 0 && bs1 < n_beams) ? bs1 : -1000;   // possibly snapped beams (Q10): their direction is
+        const int sn2 = (relevant && bs2 >= 0 && bs2 < n_beams) ? bs2 : -1000;   // not the table's -> every obstacle within reach
+        // ---- (beam, obstacle) candidate pairs -> batches of <= 32 for the exact tests, beam-major, 32 beams per pass.
+        //      Lane L owns beam 32 pass + L: its candidate obstacles are one ballot; a prefix sum over the lanes' counts gives
+        //      every beam its slot range, and a batch = the longest run of whole beams that fits 32 slots (one ballot). ----
+        for (int b0 = 0; b0 < n_beams; b0 += 32) {
+            const int nb = n_beams - b0 < 32 ? n_beams - b0 : 32;
+            unsigned mybits = 0u;                                  // my candidate beams of this pass
+            {
+                const int l = max(blo - b0, 0), h = min(bhi - b0, 31);
+                if (l <= h) mybits = ((2u << h) - 1u) & ~((1u << l) - 1u);
+                if (sn1 >= b0 && sn1 < b0 + 32) mybits |= 1u << (sn1 - b0);
+                if (sn2 >= b0 && sn2 < b0 + 32) mybits |= 1u << (sn2 - b0);
+            }
+            unsigned cand = 0u;                                    // lane L: obstacles (lanes) that may return on beam b0 + L
+            for (int b = 0; b < nb; ++b) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (mybits >> b) & 1u);
+                if (lane == b) cand = bal;
+            }
+            const int cnt = __popc(cand);
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0, start = 0;                               // slots / beams already handed to earlier batches
+            while (base < total) {
+                const unsigned fits = __ballot_sync(0xffffffffu, lane >= start && incl - base <= 32);
+                const int end = 32 - __clz(fits);                  // beams [start, end) form this batch (>= 1 beam: cnt <= 32)
+                if (lane >= start && lane < end) {
+                    int slot = incl - cnt - base;
+                    unsigned m = cand;
+                    while (m != 0u) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1u;
+                        ring[slot++] = (unsigned)j | ((unsigned)(b0 + lane) << 5);
+                    }
+                }
+                n_pend = __shfl_sync(0xffffffffu, incl, end - 1) - base;
+                base += n_pend; start = end;
+                if (n_pend > 0) drain();
+            }
+        }
 
         if (STEP && lane == 0) {
             double reward = ps.reward;
@@ -914,7 +923,7 @@ mnv_env_dense_kernel(const EnvPtrs P, const __grid_constant__ KParams K)
             if (K.set_boundary && oob) { done = 1; info = MNV_INFO_OUT_OF_BOUNDARY; }
             else if (ps.ep >= K.max_ep_steps) { done = 1; info = MNV_INFO_TOO_LONG; }
             else if (collides(best_d2, best_r + K.robot_r)) { reward += K.pen_coll; done = 1; info = MNV_INFO_COLLISION; }
-            else if (ps.dis_after <= K.goal_dis) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }
+            else if (reaches(ps.dis_after, K.goal_dis)) { reward += K.rew_goal; done = 1; info = MNV_INFO_REACH_GOAL; }   // ps.dis_after = squared distance
             P.state[e] = x; P.state[E + e] = y; P.state[2 * E + e] = th; P.state[3 * E + e] = ps.sp;
             P.velocity[e] = ps.vx; P.velocity[E + e] = ps.vy;
             P.ep_step[e] = ps.ep + 1;
@@ -1009,13 +1018,12 @@ int fill_kparams(KParams& K, const mnv_params* p, int64_t E, int max_c, int max_
     for (int i = 0; i < p->n_beams; ++i) {
         K.beam_angle[i] = a0 + i * phi;
         K.beam_cos[i] = cos(K.beam_angle[i]); K.beam_sin[i] = sin(K.beam_angle[i]);
-        K.beam_dirf[i] = make_float2((float)K.beam_cos[i], (float)K.beam_sin[i]);
-        K.beam_cosf[i] = (float)K.beam_cos[i]; K.beam_sinf[i] = (float)K.beam_sin[i];
     }
     K.snap_t1 = 0.5 * MNV_PI - a0; K.snap_t2 = 1.5 * MNV_PI - a0;      // Q10 pre-test (see the kernel)
     K.inv_phi = (float)(1.0 / phi); K.snap_tol = (float)(1e-3 / phi + 1e-4);
     K.beam0f = (float)a0;
     K.precise_bins = (p->n_beams <= 16 && p->sonar_angle < MNV_PI - 0.01 && p->sonar_angle > 0.0) ? 1 : 0;
+    K.dense_bins = (p->sonar_angle < MNV_PI - 0.01 && p->sonar_angle > 0.0) ? 1 : 0;
     return 0;
 }
 
