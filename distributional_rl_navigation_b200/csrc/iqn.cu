@@ -4,12 +4,19 @@
 //
 // Work decomposition: one CTA (256 threads) owns a tile of 64 "rows" = (sample, quantile) pairs (8 samples x 8 taus
 // when training, 2 samples x 32 taus when acting).  All activations of the tile live in shared memory; each weight
-// matrix is staged into shared memory once per layer and consumed by a register-tiled rank-1-update loop
-// (4x13 / 4x4 / 13x4 outputs per thread).  The training kernel runs target forward -> local forward -> pairwise quantile
-// Huber loss (warp-shuffle reduction) -> full backward inside the SAME CTA and writes one partial gradient per tile;
-// iqn_reduce sums the partials in a fixed order (deterministic), iqn_clip_adam applies the global-norm clip + Adam.
-// FP32 FFMA on purpose: north_star asks for the loss within 1e-4 of the PyTorch fp32 path, which bf16/tf32 tensor-core
-// operands do not give; tensor cores are for the acting path where only the argmax is consumed.
+// matrix is staged into shared memory once per layer.  The training kernel runs target forward -> local forward ->
+// pairwise quantile Huber loss (warp-shuffle reduction) -> full backward inside the SAME CTA and writes one partial
+// gradient per tile; iqn_reduce sums the partials in a fixed order (deterministic), iqn_clip_adam applies the global-norm
+// clip + Adam.
+//
+// GEMM core: warp-level tensor-core MMAs (mma.sync.m16n8k8, TF32 operands, FP32 accumulation) with the error-compensated
+// 3xTF32 split -- every fp32 operand x is used as x_hi + x_lo (x_hi = the top 19 bits of x, x_lo = x - x_hi, exact) and a
+// product is accumulated as a_lo b_hi + a_hi b_lo + a_hi b_hi.  What is dropped is a_lo b_lo and the truncation of the lo
+// parts, both <= 2^-20 relative per product: the results stay at fp32 level (loss within ~1e-6 of the PyTorch fp32 path,
+// tests/test_iqn_parity.py; north_star asks for 1e-4), while a warp issues ~4x fewer instructions than the register-tiled
+// FFMA loop it replaces (which ran at 28 % of the FMA pipe: shared-memory-operand bound).  Plain TF32 / bf16 operands
+// (one MMA per product) would NOT meet the loss tolerance -- those are for the acting path (iqn_act_tc.cu), where only
+// the argmax is consumed.
 #include <math.h>
 
 #include <cuda_bf16.h>
@@ -20,9 +27,7 @@ namespace {
 
 using namespace iqn;
 
-constexpr int kThreads = 256;     // 8 warps per 64-row tile, thread tiles 4x13 / 4x4 / 13x4 (512 threads with 2x13 / 2x4 tiles measured slower: 145 vs 135 us per update, shared-memory-load bound)
-constexpr int kMT = 64 * 16 / kThreads;   // rows per thread tile: (64 / kMT) * 16 column groups == kThreads
-constexpr int kGroups = 64 / kMT;  // row groups of a tile (d(feat) partial sums)
+constexpr int kThreads = 256;     // 8 warps per 64-row tile (the warp tiling of MmaAcc assumes exactly 8)
 constexpr int R = 64;              // rows per tile
 constexpr int LD64 = 68;           // padded leading dimension of [64][64] activation tiles (== 4 mod 32, multiple of 4)
 constexpr int LD208 = 212;         // padded leading dimension of [64][208] activation tiles
@@ -32,9 +37,9 @@ struct Smem {
     float c[R * LD208];            // relu(cos_embedding(cos)); the backward pass overwrites it with dzc
     float h1[R * LD64];            // ... overwritten with dz1
     float h2[R * LD64];            // ... overwritten with dz2
-    float w[13312];                // weight stage: two halves (reduction rows [0,RED/2) and [RED/2,RED)), filled by cp.async
+    float w[2 * 7488];             // weight stage: two halves (reduction rows [0,RED/2) and [RED/2,RED), rows padded by 8), filled by cp.async
     float w3[kAct * kHid + 12];    // output layer weights + bias of the network being evaluated
-    float dfp[kGroups * kFeat];    // per row-group partial sums of d(feat)
+    float dfp[128];                // small scratch (mean over taus of the acting forward)
     float feat[8 * kFeat];
     float dfeat[8 * kFeat];
     float x[8 * 28];
@@ -45,85 +50,137 @@ struct Smem {
     int   act[8];
 };
 
-// out(m, n) = sum_{r < RED} xf(r, m) * Y(r, n)     m in [0, M), n in [0, N)
-// thread tile MT x NT with (M/MT)*(N/NT) == 256 threads.  yf(r, n0, yv) loads NT values of row r starting at column n0.
-template <int M, int N, int MT, int NT>
-struct TileAcc {
-    static_assert((M / MT) * (N / NT) == kThreads && M % MT == 0 && N % NT == 0, "tile shape");
-    float acc[MT][NT];
-    int m0, n0;
-    __device__ __forceinline__ TileAcc()
+// ---- 3xTF32 tensor-core GEMM:  out(m, n) = sum_{r < RED} X(r, m) * Y(r, n),  m in [0, M), n in [0, N) ----------------
+// xf(r, m) / yf(r, n) return single fp32 elements (shared memory).  Fragment layout of mma.m16n8k8 (g = lane >> 2,
+// t = lane & 3):  A (16 x 8, rows = m): a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4);  B (8 x 8, cols = n):
+// b0 (t, g) b1 (t + 4, g);  C (16 x 8): c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1).
+// Warp tiling over the CTA's 8 warps:
+//   M == 64  ("row split"):  warp w owns the 16-row block w & 3 and the N / 16 column blocks of half w >> 2
+//                            (A fragment loaded once per 8 reduction rows, reused for every column block);
+//   M == 208 ("col split"):  warp w owns the 8-column block w (N == 64) and all 13 row blocks (B fragment reused).
+__device__ __forceinline__ void split3(float v, uint32_t& hi, uint32_t& lo)
+{
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;                // v rounded to the 19 bits a TF32 operand keeps
+    lo = __float_as_uint(v - __uint_as_float(hi));                    // exact; the MMA truncates it to TF32 itself
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                     uint32_t bl0, uint32_t bl1)
+{
+    mma_tf32(c, al, bh0, bh1);                                        // small terms first
+    mma_tf32(c, ah, bl0, bl1);
+    mma_tf32(c, ah, bh0, bh1);
+}
+
+template <int M, int N>
+struct MmaAcc {
+    static constexpr bool kRowSplit = (M == 64);
+    static_assert((kRowSplit && N % 16 == 0) || (M == 208 && N == 64), "supported tile shapes");
+    static constexpr int kBlocks = kRowSplit ? N / 16 : M / 16;       // accumulator blocks per warp
+    float acc[kBlocks][4];
+    int m0, n0, g, t;                                                 // first row / column of this warp's blocks
+    __device__ __forceinline__ MmaAcc()
     {
-        const int tn = threadIdx.x % (N / NT), tm = threadIdx.x / (N / NT);
-        m0 = tm * MT; n0 = tn * NT;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        g = lane >> 2; t = lane & 3;
+        m0 = kRowSplit ? (w & 3) * 16 : 0;
+        n0 = kRowSplit ? (w >> 2) * (N / 2) : w * 8;
 #pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+        for (int i = 0; i < kBlocks; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
     }
-    // accumulate reduction rows [r0, r1); yf sees the row index relative to yrow0
+    // accumulate reduction rows [r0, r1) (a multiple of 8); yf sees the row index relative to yrow0.
+    // The tensor core adds into its FP32 accumulator with truncation: chaining all RED / 8 x 3 MMAs on one accumulator
+    // biases the sum by ~n 2^-24 (measured 3e-6 on the loss).  So the MMAs of TWO reduction steps (16 rows, 6 MMAs) go
+    // into a zeroed scratch accumulator, which is then added to the running sum with round-to-nearest FADDs: the error
+    // returns to the level of the FFMA kernel (~2e-7) for 4 extra FADDs per block and 16 rows.
     template <class XF, class YF>
     __device__ __forceinline__ void run(int r0, int r1, int yrow0, XF xf, YF yf)
     {
-#pragma unroll 2
-        for (int r = r0; r < r1; ++r) {
-            float xv[MT], yv[NT];
+        float tmp[kBlocks][4];
+        auto zero = [&]() {
 #pragma unroll
-            for (int i = 0; i < MT; ++i) xv[i] = xf(r, m0 + i);
-            yf(r - yrow0, n0, yv);
+            for (int i = 0; i < kBlocks; ++i) { tmp[i][0] = 0.f; tmp[i][1] = 0.f; tmp[i][2] = 0.f; tmp[i][3] = 0.f; }
+        };
+        auto flush = [&]() {
 #pragma unroll
-            for (int i = 0; i < MT; ++i)
+            for (int i = 0; i < kBlocks; ++i) { acc[i][0] += tmp[i][0]; acc[i][1] += tmp[i][1]; acc[i][2] += tmp[i][2]; acc[i][3] += tmp[i][3]; }
+        };
+        zero();
+        int pending = 0;
+#pragma unroll 1
+        for (int k0 = r0; k0 < r1; k0 += 8) {
+            if constexpr (kRowSplit) {
+                uint32_t ah[4], al[4];
+                split3(xf(k0 + t, m0 + g), ah[0], al[0]); split3(xf(k0 + t, m0 + g + 8), ah[1], al[1]);
+                split3(xf(k0 + t + 4, m0 + g), ah[2], al[2]); split3(xf(k0 + t + 4, m0 + g + 8), ah[3], al[3]);
 #pragma unroll
-                for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+                for (int i = 0; i < kBlocks; ++i) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split3(yf(k0 + t - yrow0, n0 + i * 8 + g), bh0, bl0);
+                    split3(yf(k0 + t + 4 - yrow0, n0 + i * 8 + g), bh1, bl1);
+                    mma3(tmp[i], ah, al, bh0, bh1, bl0, bl1);
+                }
+            } else {
+                uint32_t bh0, bl0, bh1, bl1;
+                split3(yf(k0 + t - yrow0, n0 + g), bh0, bl0);
+                split3(yf(k0 + t + 4 - yrow0, n0 + g), bh1, bl1);
+#pragma unroll
+                for (int i = 0; i < kBlocks; ++i) {
+                    uint32_t ah[4], al[4];
+                    const int mb = i * 16;
+                    split3(xf(k0 + t, mb + g), ah[0], al[0]); split3(xf(k0 + t, mb + g + 8), ah[1], al[1]);
+                    split3(xf(k0 + t + 4, mb + g), ah[2], al[2]); split3(xf(k0 + t + 4, mb + g + 8), ah[3], al[3]);
+                    mma3(tmp[i], ah, al, bh0, bh1, bl0, bl1);
+                }
+            }
+            if (++pending == 2) { flush(); zero(); pending = 0; }
+        }
+        if (pending) flush();
+    }
+    // epi4(m, n, c0, c1, c2, c3): (m, n) (m, n + 1) (m + 8, n) (m + 8, n + 1); every lane calls it for every block (uniform)
+    template <class Epi4>
+    __device__ __forceinline__ void finish4(Epi4 epi4)
+    {
+#pragma unroll
+        for (int i = 0; i < kBlocks; ++i) {
+            const int m = (kRowSplit ? m0 : i * 16) + g, n = (kRowSplit ? n0 + i * 8 : n0) + 2 * t;
+            epi4(m, n, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
     }
     template <class Epi>
     __device__ __forceinline__ void finish(Epi epi)
     {
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < NT; ++j) epi(m0 + i, n0 + j, acc[i][j]);
+        finish4([&](int m, int n, float c0, float c1, float c2, float c3) { epi(m, n, c0); epi(m, n + 1, c1); epi(m + 8, n, c2); epi(m + 8, n + 1, c3); });
     }
 };
 
-template <int RED, int M, int N, int MT, int NT, class XF, class YF, class Epi>
+template <int RED, int M, int N, class XF, class YF, class Epi>
 __device__ __forceinline__ void tile_mm(XF xf, YF yf, Epi epi)
 {
-    TileAcc<M, N, MT, NT> t;
+    static_assert(RED % 8 == 0, "reduction length");
+    MmaAcc<M, N> t;
     t.run(0, RED, 0, xf, yf);
     t.finish(epi);
 }
 
-// Y loaders for a shared-memory matrix [RED][ld]
-template <int NT>
-struct YMat {
-    const float* p; int ld;
-    __device__ __forceinline__ void operator()(int r, int n0, float (&yv)[NT]) const
-    {
-        if constexpr (NT % 4 == 0) {
-#pragma unroll
-            for (int j = 0; j < NT; j += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(p + r * ld + n0 + j);
-                yv[j] = v.x; yv[j + 1] = v.y; yv[j + 2] = v.z; yv[j + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NT; ++j) yv[j] = p[r * ld + n0 + j];
-        }
-    }
-};
-
-// ---- weight staging: global [RED][N] fp32 -> shared memory with cp.async, in two halves of the reduction dimension.
+// ---- weight staging: global [RED][N] fp32 -> shared memory rows of N + 8 floats (the pad makes the B-fragment loads of a
+// warp -- 4 reduction rows x 8 columns -- hit 32 different banks) with cp.async, in two halves of the reduction dimension.
 // While a GEMM consumes half 0 its half 1 is in flight, and while it consumes half 1 the NEXT GEMM's half 0 is in flight,
 // so only the very first half of a kernel is an exposed L2 round trip.
-constexpr int kHalfStage = 13312 / 2;                              // floats per half buffer (largest matrix / 2)
+constexpr int kStagePad = 8;
+constexpr int kHalfStage = 104 * (64 + kStagePad);                 // floats per half buffer: the largest half, W1^T [104][64 + 8]
 
-__device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int n)
+__device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int rows, int n)
 {
-    for (int i = threadIdx.x * 4; i < n; i += kThreads * 4) {       // n % 4 == 0, both 16-byte aligned
-        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    const int chunks_per_row = n >> 2, ld = n + kStagePad;          // n % 4 == 0; rows are 16-byte aligned in both spaces
+    for (int i = threadIdx.x; i < rows * chunks_per_row; i += kThreads) {
+        const int r = i / chunks_per_row, c = i - r * chunks_per_row;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + r * ld + c * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + r * n + c * 4) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -132,28 +189,29 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 // request half 0 of a [RED][N] matrix into buffer A (= s.w)
 __device__ __forceinline__ void request_first_half(Smem& s, const float* __restrict__ W, int red, int n)
 {
-    stage_async(s.w, W, (red / 2) * n);
+    stage_async(s.w, W, red / 2, n);
 }
 
 // out = xf x W with W [RED][N] in global memory whose half 0 has already been requested into s.w; after half 1 landed the
 // first half of `next` ([next_red][next_n], may be null) is requested.  Ends with the epilogue, no trailing barrier.
-template <int RED, int M, int N, int MT, int NT, class XF, class Epi>
+template <int RED, int M, int N, class XF, class Fin>
 __device__ __forceinline__ void tile_mm_staged(Smem& s, const float* __restrict__ W, const float* __restrict__ next, int next_red,
-                                               int next_n, XF xf, Epi epi)
+                                               int next_n, XF xf, Fin fin)
 {
-    static_assert(RED % 2 == 0 && ((RED / 2) * N) % 4 == 0 && (RED / 2) * N <= kHalfStage, "stage halves");
+    static_assert(RED % 16 == 0 && (RED / 2) * (N + kStagePad) <= kHalfStage, "stage halves");
     float* A = s.w;
     float* B = s.w + kHalfStage;
-    TileAcc<M, N, MT, NT> t;
+    constexpr int LDW = N + kStagePad;
+    MmaAcc<M, N> t;
     stage_wait();
     __syncthreads();                                               // half 0 visible; nobody still reads buffer B
-    stage_async(B, W + (RED / 2) * N, (RED / 2) * N);
-    t.run(0, RED / 2, 0, xf, YMat<NT>{A, N});
+    stage_async(B, W + (RED / 2) * N, RED / 2, N);
+    t.run(0, RED / 2, 0, xf, [&](int r, int n) { return A[r * LDW + n]; });
     stage_wait();
     __syncthreads();                                               // half 1 visible; nobody still reads buffer A
-    if (next != nullptr) stage_async(A, next, (next_red / 2) * next_n);
-    t.run(RED / 2, RED, RED / 2, xf, YMat<NT>{B, N});
-    t.finish(epi);
+    if (next != nullptr) stage_async(A, next, next_red / 2, next_n);
+    t.run(RED / 2, RED, RED / 2, xf, [&](int r, int n) { return B[r * LDW + n]; });
+    fin(t);
 }
 
 // ObsEncoder.forward (model.py:160-186) for one 64-row tile; row r belongs to sample r / n_tau of the tile.
@@ -191,17 +249,17 @@ __device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* 
     for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads)     // output layer of this network -> shared memory
         s.w3[idx] = __ldg(P + oOW + idx);                          // (output_layer.weight and .bias are contiguous)
     // c = relu(cos_embedding(cos))  (model.py:177)      [the staged GEMM starts with a barrier: cos / feat are visible]
-    tile_mm_staged<kCos, R, kFeat, kMT, 13>(s, PT + ptWc, PT + ptW1, kFeat, kHid,
-                                          [&](int k, int row) { return s.cos[row * LD64 + k]; },
-                                          [&](int row, int f, float a) { s.c[row * LD208 + f] = fmaxf(a + __ldg(P + oCB + f), 0.f); });
+    tile_mm_staged<kCos, R, kFeat>(s, PT + ptWc, PT + ptW1, kFeat, kHid,
+                                   [&](int k, int row) { return s.cos[row * LD64 + k]; },
+                                   [&](auto& acc) { acc.finish([&](int row, int f, float a) { s.c[row * LD208 + f] = fmaxf(a + __ldg(P + oCB + f), 0.f); }); });
     // h1 = relu(hidden_layer(feat * c))  (model.py:180-182)
-    tile_mm_staged<kFeat, R, kHid, kMT, 4>(s, PT + ptW1, PT + ptW2, kHid, kHid,
-                                         [&](int k, int row) { return s.c[row * LD208 + k] * s.feat[(row / n_tau) * kFeat + k]; },
-                                         [&](int row, int o, float a) { s.h1[row * LD64 + o] = fmaxf(a + __ldg(P + oH1B + o), 0.f); });
+    tile_mm_staged<kFeat, R, kHid>(s, PT + ptW1, PT + ptW2, kHid, kHid,
+                                   [&](int k, int row) { return s.c[row * LD208 + k] * s.feat[(row / n_tau) * kFeat + k]; },
+                                   [&](auto& acc) { acc.finish([&](int row, int o, float a) { s.h1[row * LD64 + o] = fmaxf(a + __ldg(P + oH1B + o), 0.f); }); });
     // h2 = relu(hidden_layer_2(h1))  (model.py:183)
-    tile_mm_staged<kHid, R, kHid, kMT, 4>(s, PT + ptW2, next, next_red, next_n,
-                                        [&](int k, int row) { return s.h1[row * LD64 + k]; },
-                                        [&](int row, int o, float a) { s.h2[row * LD64 + o] = fmaxf(a + __ldg(P + oH2B + o), 0.f); });
+    tile_mm_staged<kHid, R, kHid>(s, PT + ptW2, next, next_red, next_n,
+                                  [&](int k, int row) { return s.h1[row * LD64 + k]; },
+                                  [&](auto& acc) { acc.finish([&](int row, int o, float a) { s.h2[row * LD64 + o] = fmaxf(a + __ldg(P + oH2B + o), 0.f); }); });
     __syncthreads();
     // q = output_layer(h2)  (model.py:184)
     for (int idx = t; idx < R * kAct; idx += kThreads) {
@@ -349,7 +407,6 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) li += __shfl_xor_sync(0xffffffffu, li, off);
     if ((t & 31) == 0) s.red[t >> 5] = li;
-    for (int idx = t; idx < kGroups * kFeat; idx += kThreads) s.dfp[idx] = 0.f;
     __syncthreads();
     if (t == 0) loss_part[tile] = s.red[0] + s.red[1];
 
@@ -378,8 +435,8 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     }
     __syncthreads();
     // dW2[o][k] = sum_r dz2[r][o] h1[r][k] ; db2
-    tile_mm<R, kHid, kHid, kMT, 4>([&](int r, int o) { return s.h2[r * LD64 + o]; }, YMat<4>{s.h1, LD64},
-                                 [&](int o, int k, float a) { g[oH2W + o * kHid + k] = a; });
+    tile_mm<R, kHid, kHid>([&](int r, int o) { return s.h2[r * LD64 + o]; }, [&](int r, int k) { return s.h1[r * LD64 + k]; },
+                           [&](int o, int k, float a) { g[oH2W + o * kHid + k] = a; });
     if (t < kHid) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) acc += s.h2[r * LD64 + t];
@@ -388,46 +445,50 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     __syncthreads();
     // dz1 = (dz2 W2) * (h1 > 0), in place over h1  (W2 in torch layout [o][k], prefetched during the forward pass;
     // W1 in torch layout is prefetched for dh0 meanwhile)
-    tile_mm_staged<kHid, R, kHid, kMT, 4>(s, PL + oH2W, PL + oH1W, kHid, kFeat,
-                                        [&](int o, int r) { return s.h2[r * LD64 + o]; },
-                                        [&](int r, int k, float a) { float& h = s.h1[r * LD64 + k]; h = h > 0.f ? a : 0.f; });
+    tile_mm_staged<kHid, R, kHid>(s, PL + oH2W, PL + oH1W, kHid, kFeat,
+                                  [&](int o, int r) { return s.h2[r * LD64 + o]; },
+                                  [&](auto& acc) { acc.finish([&](int r, int k, float a) { float& h = s.h1[r * LD64 + k]; h = h > 0.f ? a : 0.f; }); });
     __syncthreads();
     // dW1[o][k] = sum_r dz1[r][o] h0[r][k], h0 = feat * c ; db1
-    tile_mm<R, kHid, kFeat, kMT, 13>([&](int r, int o) { return s.h1[r * LD64 + o]; },
-                                   [&](int r, int n0, float (&yv)[13]) {
-#pragma unroll
-                                       for (int j = 0; j < 13; ++j)
-                                           yv[j] = s.c[r * LD208 + n0 + j] * s.feat[(r / NT8) * kFeat + n0 + j];
-                                   },
-                                   [&](int o, int k, float a) { g[oH1W + o * kFeat + k] = a; });
+    tile_mm<R, kHid, kFeat>([&](int r, int o) { return s.h1[r * LD64 + o]; },
+                            [&](int r, int k) { return s.c[r * LD208 + k] * s.feat[(r / NT8) * kFeat + k]; },
+                            [&](int o, int k, float a) { g[oH1W + o * kFeat + k] = a; });
     if (t < kHid) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) acc += s.h1[r * LD64 + t];
         g[oH1B + t] = acc;
     }
     __syncthreads();
-    // dh0 = dz1 W1 ; dzc = dh0 * feat * (c > 0) in place over c ; d(feat) += dh0 * c
-    {
-        const int tm = threadIdx.x / 16;                                             // row group of kMT rows (one sample = 8 / kMT groups)
-        tile_mm_staged<kHid, R, kFeat, kMT, 13>(s, PL + oH1W, nullptr, 0, 0, [&](int o, int r) { return s.h1[r * LD64 + o]; },
-                                       [&](int r, int k, float a) {
-                                           float& cv = s.c[r * LD208 + k];
-                                           const float c0 = cv;
-                                           s.dfp[tm * kFeat + k] += a * c0;             // (tm, k) is private to this thread
-                                           cv = c0 > 0.f ? a * s.feat[(r / NT8) * kFeat + k] : 0.f;
-                                       });
-    }
-    __syncthreads();
-    for (int idx = t; idx < 8 * kFeat; idx += kThreads) {
-        const int smp = idx / kFeat, k = idx % kFeat;
-        float acc = 0.f;
+    // dh0 = dz1 W1 ; dzc = dh0 * feat * (c > 0) in place over c ; d(feat)[sample] = sum over the sample's 8 rows of dh0 * c.
+    // In the accumulator layout a warp's 16-row block is exactly two samples (rows g and g + 8 of lane group g), so the sum
+    // over a sample's rows is a butterfly over the lane bits 2..4 (fixed order: deterministic) and lane group 0 owns the result.
+    tile_mm_staged<kHid, R, kFeat>(s, PL + oH1W, nullptr, 0, 0, [&](int o, int r) { return s.h1[r * LD64 + o]; },
+                                   [&](auto& acc) {
+                                       acc.finish4([&](int r, int k, float a0, float a1, float a2, float a3) {
+                                           const int smp = r >> 3;                       // r = 16 mb + g, g < 8: sample 2 mb; r + 8: sample 2 mb + 1
+                                           float* c_top = s.c + r * LD208 + k;
+                                           float* c_bot = s.c + (r + 8) * LD208 + k;
+                                           const float ct0 = c_top[0], ct1 = c_top[1], cb0 = c_bot[0], cb1 = c_bot[1];
+                                           float d0 = a0 * ct0, d1 = a1 * ct1, d2 = a2 * cb0, d3 = a3 * cb1;
 #pragma unroll
-        for (int gq = 0; gq < 8 / kMT; ++gq) acc += s.dfp[((8 / kMT) * smp + gq) * kFeat + k];      // fixed order: deterministic
-        s.dfeat[idx] = acc;
-    }
+                                           for (int off = 4; off < 32; off <<= 1) {
+                                               d0 += __shfl_xor_sync(0xffffffffu, d0, off); d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+                                               d2 += __shfl_xor_sync(0xffffffffu, d2, off); d3 += __shfl_xor_sync(0xffffffffu, d3, off);
+                                           }
+                                           if ((r & 7) == 0) {
+                                               s.dfeat[smp * kFeat + k] = d0; s.dfeat[smp * kFeat + k + 1] = d1;
+                                               s.dfeat[(smp + 1) * kFeat + k] = d2; s.dfeat[(smp + 1) * kFeat + k + 1] = d3;
+                                           }
+                                           const float* f_top = s.feat + smp * kFeat + k;
+                                           const float* f_bot = s.feat + (smp + 1) * kFeat + k;
+                                           c_top[0] = ct0 > 0.f ? a0 * f_top[0] : 0.f; c_top[1] = ct1 > 0.f ? a1 * f_top[1] : 0.f;
+                                           c_bot[0] = cb0 > 0.f ? a2 * f_bot[0] : 0.f; c_bot[1] = cb1 > 0.f ? a3 * f_bot[1] : 0.f;
+                                       });
+                                   });
+    __syncthreads();
     // dWc[f][i] = sum_r dzc[r][f] cos[r][i] ; dbc
-    tile_mm<R, kFeat, kCos, 13, kMT>([&](int r, int f) { return s.c[r * LD208 + f]; }, YMat<kMT>{s.cos, LD64},
-                                   [&](int f, int i, float a) { g[oCW + f * kCos + i] = a; });
+    tile_mm<R, kFeat, kCos>([&](int r, int f) { return s.c[r * LD208 + f]; }, [&](int r, int i) { return s.cos[r * LD64 + i]; },
+                            [&](int f, int i, float a) { g[oCW + f * kCos + i] = a; });
     if (t < kFeat) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) acc += s.c[r * LD208 + t];
