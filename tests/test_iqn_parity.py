@@ -96,7 +96,10 @@ def test_train_loss_grad_adam_vs_reference(kat, weights, B):
             assert resolved.mean() > 0.9 and d1[resolved].max() <= 1e-6 and d1.max() <= 2.1e-4, (d1[resolved].max(), d1.max())
     d3 = np.abs(flat.cpu().numpy() - kat[f"params_after3_B{B}"])
     assert d3[resolved].max() <= 5e-6 and d3.max() <= 6.1e-4, (d3[resolved].max(), d3.max())
-    np.testing.assert_allclose(m.cpu().numpy()[resolved], kat[f"adam_m_after3_B{B}"][resolved], rtol=2e-3, atol=1e-8)
+    # first moment after three steps: 2e-3 relative, with an absolute floor at the gradient noise level of steps 2 and 3
+    # (the `resolved` mask describes step 1 only; 5e-5 of the largest entry = half the 1e-4 max|g| bar on the gradients)
+    m_ref = kat[f"adam_m_after3_B{B}"]
+    np.testing.assert_allclose(m.cpu().numpy()[resolved], m_ref[resolved], rtol=2e-3, atol=5e-5 * float(np.abs(m_ref).max()))
     # the kernel-side copies (fp32 transposes, bf16 tensor-core tiles) were kept current by clip_adam itself
     assert torch.equal(packed, packed_of(flat))
     fresh = torch.empty_like(ptc)
