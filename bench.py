@@ -25,10 +25,10 @@ UNIT = "env_steps/s"
 N_CORES, N_OBS, N_BEAMS = 4, 8, 11
 ENVS_PER_GPU = 65536
 N_BATCHES = 8
-NCU_DRAM_BYTES_PER_LAUNCH = 22.587e6     # measured, profiles/r1_step_kernel_v5_ncu_full.csv (algorithmic read volume: 22.5 MB)
-NCU_WARP_INST_PER_LAUNCH = 6.69e6        # smsp__inst_executed.sum of the same capture
+NCU_DRAM_BYTES_PER_LAUNCH = 22.589e6     # measured, profiles/r2_step_kernel_v8_ncu_full.csv (algorithmic read volume: 22.5 MB)
+NCU_WARP_INST_PER_LAUNCH = 5.43e6        # smsp__inst_executed.sum of the same capture
 NCU_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                      "(profiles/r1_step_kernel_v5_ncu_full.csv); the 9.6 MB of writes were still in L2 when the profiled launch ended")
+                      "(profiles/r2_step_kernel_v8_ncu_full.csv); the 9.6 MB of writes were still in L2 when the profiled launch ended")
 
 
 def algorithmic_bytes_per_env_step(n_c=N_CORES, n_o=N_OBS, n_b=N_BEAMS, s=8):
@@ -466,9 +466,13 @@ def dense_leg(args, dev, world, rank):
     ms = float(ms.item())
     ab = algorithmic_bytes_per_env_step(n_c, n_o, n_b)
     peak, _ = measured_peak_hbm()
+    inst = 23.30e6          # smsp__inst_executed.sum of one launch, profiles/r2_dense_kernel_v4_ncu_full.csv
+    floor_us = inst / (148 * 4) / 1.965e3
     return {"workload": "dense map: 32 obstacles, 64 sonar beams, 16384 envs/GPU (BASELINE configs[4] per-GPU shard), mnv_env_dense_kernel",
             "ms_per_step": ms, "env_steps_per_s": world * E / (ms * 1e-3), "algorithmic_bytes_per_env_step": ab,
-            "hbm_roofline_frac": E * ab / (ms * 1e-3) / 1e9 / peak, "bound": "fp64 / issue (2048 ray-circle tests per env-step), not HBM"}
+            "hbm_roofline_frac": E * ab / (ms * 1e-3) / 1e9 / peak, "bound": "issue (2048 ray-circle pairs per env-step), not HBM",
+            "issue_bound": {"warp_instructions_per_launch": inst, "floor_us_at_1_ipc_per_scheduler": floor_us, "frac": floor_us / (ms * 1e3),
+                            "note": "second roofline (SURVEY 8d): ncu smsp__inst_executed.sum of one launch / (592 schedulers x 1.965 GHz) / measured time"}}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -522,7 +526,12 @@ def iqn_bench(args, dev, world):
     ms = float(ms.item())
     out["updates_per_s"] = 1e3 / ms
     out["update_ms"] = ms
-    out["update_config"] = f"batch {B} per GPU, N=N'=8, fp32 FFMA, loss_grad + " + ("NCCL all-reduce(35785 f32) + " if world > 1 else "") + "clip_adam (kernel-side weight copies refreshed in the same kernel)"
+    peer = agent._tail is not None and agent._tail.world == world
+    out["update_config"] = (f"batch {B} per GPU, N=N'=8, 3xTF32 mma.sync (fp32-level accuracy); two launches: iqn_loss_partials + iqn_update_tail "
+                            "(tile-partial sum" + (", one-shot all-reduce of the 35785-float gradient over peer memory (NVLink)" if world > 1 and peer else "")
+                            + ", clip_grad_norm_, Adam, kernel-side weight copies)") if agent.fused_tail and (world == 1 or peer) else \
+                           (f"batch {B} per GPU, N=N'=8, 3xTF32 mma.sync; loss_grad + " + ("NCCL all-reduce(35785 f32) + " if world > 1 else "") + "clip_adam")
+    out["update_gradient_exchange"] = "none (1 GPU)" if world == 1 else ("peer-memory one-shot all-reduce inside iqn_update_tail" if peer else "NCCL all_reduce")
     out["update_tflops_fp32"] = IQN_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
     out["samples_per_s_all_gpus"] = world * B * 1e3 / ms
     out["loss_finite"] = bool(torch.isfinite(agent._loss).all().item())

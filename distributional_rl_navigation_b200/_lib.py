@@ -65,6 +65,15 @@ _SIGNATURES = {
     "iqn_train_scratch_floats": (C.c_int64, [_i64]),
     "iqn_loss_grad": (C.c_int, [_vp] * 11 + [C.c_float] + [_vp] * 3 + [_i64, _vp]),
     "iqn_clip_adam": (C.c_int, [_vp] * 6 + [C.c_float] * 6 + [_i64, _vp, _vp]),
+    "iqn_loss_partials": (C.c_int, [_vp] * 11 + [C.c_float] + [_vp] + [_i64, _vp]),
+    "iqn_tail_sync_bytes": (C.c_int64, []),
+    "iqn_xchg_bytes": (C.c_int64, []),
+    "iqn_xchg_handle_bytes": (C.c_int32, []),
+    "iqn_xchg_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
+    "iqn_xchg_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "iqn_xchg_close": (C.c_int, [_vp]),
+    "iqn_xchg_free": (C.c_int, [_vp]),
+    "iqn_update_tail": (C.c_int, [_vp] * 6 + [_i64] + [_vp] * 4 + [C.POINTER(C.c_void_p), _i32, _i32] + [C.c_float] * 5 + [_i64, _vp]),
     "iqn_packed_tc_bytes": (C.c_int, []),
     "iqn_pack_tc": (C.c_int, [_vp, _vp, _vp]),
     "iqn_act_scratch_bytes": (C.c_int64, [_i64]),

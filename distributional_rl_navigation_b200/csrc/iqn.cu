@@ -38,7 +38,7 @@ struct Smem {
     float h1[R * LD64];            // ... overwritten with dz1
     float h2[R * LD64];            // ... overwritten with dz2
     float w[2 * 7488];             // weight stage: two halves (reduction rows [0,RED/2) and [RED/2,RED), rows padded by 8), filled by cp.async
-    float w3[kAct * kHid + 12];    // output layer weights + bias of the network being evaluated
+    float w3[kAct * LD64 + 12];    // output layer of the network being evaluated: rows padded to LD64 (conflict-free 16-byte loads), then the bias
     float dfp[128];                // small scratch (mean over taus of the acting forward)
     float feat[8 * kFeat];
     float dfeat[8 * kFeat];
@@ -167,6 +167,20 @@ __device__ __forceinline__ void tile_mm(XF xf, YF yf, Epi epi)
     t.finish(epi);
 }
 
+// out(m, n) -> dst[m * ld + n] in global memory with 8-byte stores (an accumulator block holds the column pairs (n, n + 1),
+// n even; dst and ld even -> aligned): half the store instructions of the scalar epilogue
+template <int RED, int M, int N, class XF, class YF>
+__device__ __forceinline__ void tile_mm_store2(XF xf, YF yf, float* __restrict__ dst, int ld)
+{
+    static_assert(RED % 8 == 0, "reduction length");
+    MmaAcc<M, N> t;
+    t.run(0, RED, 0, xf, yf);
+    t.finish4([&](int m, int n, float c0, float c1, float c2, float c3) {
+        *reinterpret_cast<float2*>(dst + m * ld + n) = make_float2(c0, c1);
+        *reinterpret_cast<float2*>(dst + (m + 8) * ld + n) = make_float2(c2, c3);
+    });
+}
+
 // ---- weight staging: global [RED][N] fp32 -> shared memory rows of N + 8 floats (the pad makes the B-fragment loads of a
 // warp -- 4 reduction rows x 8 columns -- hit 32 different banks) with cp.async, in two halves of the reduction dimension.
 // While a GEMM consumes half 0 its half 1 is in flight, and while it consumes half 1 the NEXT GEMM's half 0 is in flight,
@@ -224,21 +238,27 @@ __device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* 
     const int t = threadIdx.x;
     __syncthreads();
     // observation encoders, no activation (model.py:169-172)
-    for (int idx = t; idx < 8 * kFeat; idx += kThreads) {
-        const int smp = idx / kFeat, f = idx % kFeat;
-        const float* x = s.x + smp * 28;
-        float v;
-        if (f < 16) v = fmaf(__ldg(P + oVW + f * 2 + 1), x[1], fmaf(__ldg(P + oVW + f * 2), x[0], __ldg(P + oVB + f)));
-        else if (f < 32) {
-            const int g = f - 16;
-            v = fmaf(__ldg(P + oGW + g * 2 + 1), x[3], fmaf(__ldg(P + oGW + g * 2), x[2], __ldg(P + oGB + g)));
+    if (t < kFeat) {                                               // thread = feature: its weights are loaded ONCE (independent loads, one round trip)
+        const int f = t;
+        if (f < 32) {                                              // velocity (f < 16) / goal encoder: two inputs
+            const int j = f & 15, ow = f < 16 ? oVW : oGW, ob = f < 16 ? oVB : oGB, xi = f < 16 ? 0 : 2;
+            const float w0 = __ldg(P + ow + j * 2), w1 = __ldg(P + ow + j * 2 + 1), b = __ldg(P + ob + j);
+#pragma unroll
+            for (int smp = 0; smp < 8; ++smp) s.feat[smp * kFeat + f] = fmaf(w1, s.x[smp * 28 + xi + 1], fmaf(w0, s.x[smp * 28 + xi], b));
         } else {
             const int g = f - 32;
-            v = __ldg(P + oSB + g);
+            float w[22];
 #pragma unroll
-            for (int k = 0; k < 22; ++k) v = fmaf(__ldg(P + oSW + g * 22 + k), x[4 + k], v);
+            for (int k = 0; k < 22; ++k) w[k] = __ldg(P + oSW + g * 22 + k);
+            const float b = __ldg(P + oSB + g);
+#pragma unroll
+            for (int smp = 0; smp < 8; ++smp) {
+                float v = b;
+#pragma unroll
+                for (int k = 0; k < 22; ++k) v = fmaf(w[k], s.x[smp * 28 + 4 + k], v);
+                s.feat[smp * kFeat + f] = v;
+            }
         }
-        s.feat[idx] = v;
     }
     // cos(tau * pi*i): fp32 product with fp32(pi*i), then fp32 cos (model.py:130,155)
     for (int idx = t; idx < R * kCos; idx += kThreads) {
@@ -246,8 +266,11 @@ __device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* 
         const float pis = (float)(MNV_PI_D * (double)i);
         s.cos[r * LD64 + i] = cosf(s.tau[r] * pis);
     }
-    for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads)     // output layer of this network -> shared memory
-        s.w3[idx] = __ldg(P + oOW + idx);                          // (output_layer.weight and .bias are contiguous)
+    for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads) {   // output layer of this network -> shared memory
+        const float v = __ldg(P + oOW + idx);                      // (output_layer.weight and .bias are contiguous)
+        if (idx < kAct * kHid) s.w3[(idx / kHid) * LD64 + (idx % kHid)] = v;
+        else s.w3[kAct * LD64 + (idx - kAct * kHid)] = v;
+    }
     // c = relu(cos_embedding(cos))  (model.py:177)      [the staged GEMM starts with a barrier: cos / feat are visible]
     tile_mm_staged<kCos, R, kFeat>(s, PT + ptWc, PT + ptW1, kFeat, kHid,
                                    [&](int k, int row) { return s.cos[row * LD64 + k]; },
@@ -264,9 +287,14 @@ __device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* 
     // q = output_layer(h2)  (model.py:184)
     for (int idx = t; idx < R * kAct; idx += kThreads) {
         const int row = idx / kAct, a = idx % kAct;
-        float v = s.w3[kAct * kHid + a];
-#pragma unroll 8
-        for (int k = 0; k < kHid; ++k) v = fmaf(s.h2[row * LD64 + k], s.w3[a * kHid + k], v);
+        float v = s.w3[kAct * LD64 + a];
+        const float4* h4 = reinterpret_cast<const float4*>(s.h2 + row * LD64);
+        const float4* w4 = reinterpret_cast<const float4*>(s.w3 + a * LD64);
+#pragma unroll 4
+        for (int k4 = 0; k4 < kHid / 4; ++k4) {                    // same summation order as a scalar k loop
+            const float4 h = h4[k4], w = w4[k4];
+            v = fmaf(h.x, w.x, v); v = fmaf(h.y, w.y, v); v = fmaf(h.z, w.z, v); v = fmaf(h.w, w.w, v);
+        }
         s.q[row * 12 + a] = v;
     }
     __syncthreads();
@@ -356,6 +384,7 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a dependent launch (iqn_update_tail) may be placed early; it waits for this grid's completion itself
     const int t = threadIdx.x;
     const long long tile = blockIdx.x, s0 = tile * 8;
     float* __restrict__ g = gpart_all + tile * (long long)kParams;
@@ -411,20 +440,27 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     if (t == 0) loss_part[tile] = s.red[0] + s.red[1];
 
     // ================= backward =================
-    // output layer: only the taken action's row sees a gradient
-    for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads) {
+    // output layer: only the taken action's row sees a gradient.  Per sample first: v[smp][o] = sum over its 8 rows of
+    // dE[r] h2[r][o] (and the sum of dE for the bias) into s.q (free after the loss), then row a of dW3 adds the samples that
+    // took action a in sample order (fixed order; no divergent 64-row loops)
+    for (int idx = t; idx < 8 * (kHid + 1); idx += kThreads) {
+        const int smp = idx / (kHid + 1), o = idx % (kHid + 1);
         float acc = 0.f;
-        if (idx < kAct * kHid) {
-            const int a = idx / kHid, o = idx % kHid;
-            for (int r = 0; r < R; ++r)
-                if (s.act[r / NT8] == a) acc = fmaf(s.dE[r], s.h2[r * LD64 + o], acc);
-            g[oOW + idx] = acc;
-        } else {
-            const int a = idx - kAct * kHid;
-            for (int r = 0; r < R; ++r)
-                if (s.act[r / NT8] == a) acc += s.dE[r];
-            g[oOB + a] = acc;
+#pragma unroll
+        for (int j = 0; j < NT8; ++j) {
+            const int r = smp * NT8 + j;
+            acc = o < kHid ? fmaf(s.dE[r], s.h2[r * LD64 + o], acc) : acc + s.dE[r];
         }
+        s.q[smp * (kHid + 1) + o] = acc;                           // 8 x 65 floats <= R * 12
+    }
+    __syncthreads();
+    for (int idx = t; idx < kAct * kHid + kAct; idx += kThreads) {
+        const int a = idx < kAct * kHid ? idx / kHid : idx - kAct * kHid, o = idx < kAct * kHid ? idx % kHid : kHid;
+        float acc = 0.f;
+#pragma unroll
+        for (int smp = 0; smp < 8; ++smp)
+            if (s.act[smp] == a) acc += s.q[smp * (kHid + 1) + o];
+        g[oOW + idx] = acc;                                        // (output_layer.weight and .bias are contiguous: oOB = oOW + 576)
     }
     __syncthreads();
     // dz2 = dE * W3[a,:] * (h2 > 0), in place over h2
@@ -435,8 +471,8 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     }
     __syncthreads();
     // dW2[o][k] = sum_r dz2[r][o] h1[r][k] ; db2
-    tile_mm<R, kHid, kHid>([&](int r, int o) { return s.h2[r * LD64 + o]; }, [&](int r, int k) { return s.h1[r * LD64 + k]; },
-                           [&](int o, int k, float a) { g[oH2W + o * kHid + k] = a; });
+    tile_mm_store2<R, kHid, kHid>([&](int r, int o) { return s.h2[r * LD64 + o]; }, [&](int r, int k) { return s.h1[r * LD64 + k]; },
+                                  g + oH2W, kHid);
     if (t < kHid) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) acc += s.h2[r * LD64 + t];
@@ -450,9 +486,9 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
                                   [&](auto& acc) { acc.finish([&](int r, int k, float a) { float& h = s.h1[r * LD64 + k]; h = h > 0.f ? a : 0.f; }); });
     __syncthreads();
     // dW1[o][k] = sum_r dz1[r][o] h0[r][k], h0 = feat * c ; db1
-    tile_mm<R, kHid, kFeat>([&](int r, int o) { return s.h1[r * LD64 + o]; },
-                            [&](int r, int k) { return s.c[r * LD208 + k] * s.feat[(r / NT8) * kFeat + k]; },
-                            [&](int o, int k, float a) { g[oH1W + o * kFeat + k] = a; });
+    tile_mm_store2<R, kHid, kFeat>([&](int r, int o) { return s.h1[r * LD64 + o]; },
+                                   [&](int r, int k) { return s.c[r * LD208 + k] * s.feat[(r / NT8) * kFeat + k]; },
+                                   g + oH1W, kFeat);
     if (t < kHid) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) acc += s.h1[r * LD64 + t];
@@ -487,8 +523,8 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
                                    });
     __syncthreads();
     // dWc[f][i] = sum_r dzc[r][f] cos[r][i] ; dbc
-    tile_mm<R, kFeat, kCos>([&](int r, int f) { return s.c[r * LD208 + f]; }, [&](int r, int i) { return s.cos[r * LD64 + i]; },
-                            [&](int f, int i, float a) { g[oCW + f * kCos + i] = a; });
+    tile_mm_store2<R, kFeat, kCos>([&](int r, int f) { return s.c[r * LD208 + f]; }, [&](int r, int i) { return s.cos[r * LD64 + i]; },
+                                   g + oCW, kCos);
     if (t < kFeat) {
         float acc = 0.f;
         for (int r = 0; r < R; ++r) acc += s.c[r * LD208 + t];
@@ -636,17 +672,19 @@ extern "C" int iqn_forward(const float* d_params, const float* d_packed, const f
     return mnv_launch_status("iqn_forward");
 }
 
-extern "C" int iqn_loss_grad(const float* d_params_local, const float* d_packed_local, const float* d_params_target,
-                             const float* d_packed_target, const float* d_states, const int64_t* d_actions,
-                             const float* d_rewards, const float* d_next_states, const float* d_dones,
-                             const float* d_taus_target, const float* d_taus_local, float gamma_n,
-                             float* d_scratch, float* d_loss, float* d_grad, int64_t B, void* stream)
+namespace {
+
+// the fused per-tile kernel alone: tile partials of the gradient + loss into d_scratch
+int launch_train(const float* d_params_local, const float* d_packed_local, const float* d_params_target,
+                 const float* d_packed_target, const float* d_states, const int64_t* d_actions,
+                 const float* d_rewards, const float* d_next_states, const float* d_dones,
+                 const float* d_taus_target, const float* d_taus_local, float gamma_n, float* d_scratch, int64_t B, void* stream,
+                 const char* what)
 {
-    if (B <= 0) { mnv_set_error("iqn_loss_grad: B must be > 0"); return MNV_E_SIZE; }
+    if (B <= 0) { mnv_set_error("%s: B must be > 0", what); return MNV_E_SIZE; }
     MNV_CHECK_PTR(d_params_local); MNV_CHECK_PTR(d_packed_local); MNV_CHECK_PTR(d_params_target); MNV_CHECK_PTR(d_packed_target);
     MNV_CHECK_PTR(d_states); MNV_CHECK_PTR(d_actions); MNV_CHECK_PTR(d_rewards); MNV_CHECK_PTR(d_next_states); MNV_CHECK_PTR(d_dones);
-    MNV_CHECK_PTR(d_taus_target); MNV_CHECK_PTR(d_taus_local); MNV_CHECK_PTR(d_scratch); MNV_CHECK_PTR(d_grad);
-    if (d_loss == nullptr) { mnv_set_error("iqn_loss_grad: null loss"); return MNV_E_NULL; }
+    MNV_CHECK_PTR(d_taus_target); MNV_CHECK_PTR(d_taus_local); MNV_CHECK_PTR(d_scratch);
     int rc = set_smem(iqn_train_kernel);
     if (rc) return rc;
     const long long tiles = (B + 7) / 8;
@@ -655,9 +693,35 @@ extern "C" int iqn_loss_grad(const float* d_params_local, const float* d_packed_
     iqn_train_kernel<<<(unsigned)tiles, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(
         d_params_local, d_packed_local, d_params_target, d_packed_target, d_states, (const long long*)d_actions, d_rewards,
         d_next_states, d_dones, d_taus_target, d_taus_local, gamma_n, gpart, lpart, B);
-    rc = mnv_launch_status("iqn_loss_grad(train)");
+    return mnv_launch_status(what);
+}
+
+}  // namespace
+
+extern "C" int iqn_loss_partials(const float* d_params_local, const float* d_packed_local, const float* d_params_target,
+                                 const float* d_packed_target, const float* d_states, const int64_t* d_actions,
+                                 const float* d_rewards, const float* d_next_states, const float* d_dones,
+                                 const float* d_taus_target, const float* d_taus_local, float gamma_n,
+                                 float* d_scratch, int64_t B, void* stream)
+{
+    return launch_train(d_params_local, d_packed_local, d_params_target, d_packed_target, d_states, d_actions, d_rewards, d_next_states,
+                        d_dones, d_taus_target, d_taus_local, gamma_n, d_scratch, B, stream, "iqn_loss_partials");
+}
+
+extern "C" int iqn_loss_grad(const float* d_params_local, const float* d_packed_local, const float* d_params_target,
+                             const float* d_packed_target, const float* d_states, const int64_t* d_actions,
+                             const float* d_rewards, const float* d_next_states, const float* d_dones,
+                             const float* d_taus_target, const float* d_taus_local, float gamma_n,
+                             float* d_scratch, float* d_loss, float* d_grad, int64_t B, void* stream)
+{
+    MNV_CHECK_PTR(d_grad);
+    if (d_loss == nullptr) { mnv_set_error("iqn_loss_grad: null loss"); return MNV_E_NULL; }
+    int rc = launch_train(d_params_local, d_packed_local, d_params_target, d_packed_target, d_states, d_actions, d_rewards, d_next_states,
+                          d_dones, d_taus_target, d_taus_local, gamma_n, d_scratch, B, stream, "iqn_loss_grad(train)");
     if (rc) return rc;
-    iqn_reduce_kernel<<<(kParams + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gpart, lpart, (int)tiles, d_grad, d_loss);
+    const long long tiles = (B + 7) / 8;
+    iqn_reduce_kernel<<<(kParams + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_scratch, d_scratch + tiles * (long long)kParams, (int)tiles,
+                                                                                 d_grad, d_loss);
     return mnv_launch_status("iqn_loss_grad(reduce)");
 }
 

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kTailThreads, 1)
 iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict__ v, float* __restrict__ PT,
                 __nv_bfloat16* __restrict__ Wtc, const float* __restrict__ gpart, const float* __restrict__ loss_part, int n_tiles,
                 float* __restrict__ loss, float* __restrict__ grad_out, float* __restrict__ grad_norm,
-                unsigned long long* __restrict__ sync, const TailPeers peers, const TailHyper H)
+                unsigned long long* __restrict__ sync, const __grid_constant__ TailPeers peers, const __grid_constant__ TailHyper H)
 {
     __shared__ float s_part[kGroups][kSlice];
     __shared__ float s_red[32];
@@ -91,7 +91,7 @@ iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict_
 #pragma unroll
                 for (int k = 0; k < 8; ++k) a[k] += __ldcg(g + (long long)k * kParams);
             }
-            for (int k = 0; tile < t1; ++tile, ++k, g += kParams) a[k] += __ldcg(g);
+            for (; tile < t1; ++tile, g += kParams) a[0] += __ldcg(g);
         }
         s_part[q][p] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
@@ -110,22 +110,27 @@ iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict_
     // ---- 2. one-shot all-reduce over peer memory (data-parallel replicas) ----
     if (peers.world > 1) {
         const int slot = (int)(epoch & 1ull);                      // double-buffered: a rank cannot run two launches ahead of a peer
-        float* mine = peers.buf[peers.rank] + (size_t)slot * kSlotFloats + blk * kSlice;
-        if (q == 0) mine[p] = g;
+        const size_t off = (size_t)slot * kSlotFloats + blk * kSlice + p;
+        float* mine = peers.buf[peers.rank];                       // (__grid_constant__: indexed straight in the constant bank)
+        if (q == 0) mine[off] = g;
         __syncthreads();
         if (t < peers.world && t != peers.rank) {
+            float* peer = peers.buf[t];
             __threadfence_system();                                // the slice (written by other threads, ordered by the barrier) before the flag
-            unsigned long long* theirs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers.buf[t]) + kFlagsOffset);
+            unsigned long long* theirs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer) + kFlagsOffset);
             st_release_sys(theirs + peers.rank * kFlagStride + blk, epoch + 1ull);
-            const unsigned long long* own = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(peers.buf[peers.rank]) + kFlagsOffset);
+            const unsigned long long* own = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(mine) + kFlagsOffset);
             while (ld_acquire_sys(own + t * kFlagStride + blk) < epoch + 1ull) { }
         }
         __syncthreads();
         if (q == 0) {
             float sum = 0.f;
-            for (int r = 0; r < peers.world; ++r) {                // rank order: identical on every replica
-                const float x = (r == peers.rank) ? g : ld_relaxed_sys(peers.buf[r] + (size_t)slot * kSlotFloats + blk * kSlice + p);
-                sum = r == 0 ? x : sum + x;
+#pragma unroll
+            for (int r = 0; r < kMaxWorld; ++r) {                  // rank order: identical on every replica
+                if (r < peers.world) {
+                    const float x = (r == peers.rank) ? g : ld_relaxed_sys(peers.buf[r] + off);
+                    sum = r == 0 ? x : sum + x;
+                }
             }
             g = sum * (1.f / (float)peers.world);
         }

@@ -83,6 +83,9 @@ class IQNAgent:
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._scratch = None
+        self.fused_tail = os.environ.get("MNV_FUSED_TAIL", "1") != "0"   # iqn_update_tail (one launch behind the backward) vs reduce + all_reduce + clip_adam
+        self.keep_grad = False                 # True: the fused tail also leaves the averaged gradient in self._grad
+        self._tail = None
         self.device_memory = None              # DeviceReplayBuffer of the vectorised trainer
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed) + 12345)
@@ -213,36 +216,46 @@ class IQNAgent:
             taus_l = self.qnetwork_local.draw_taus(B, 8)
         else:
             taus_t, taus_l = (t.to(dev, torch.float32).contiguous() for t in taus)
-        need = iqn_ops.train_scratch_floats(B)
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(need, dtype=torch.float32, device=dev)
-        L, T, opt = self.qnetwork_local, self.qnetwork_target, self.optimizer
         with torch.cuda.device(dev):
-            iqn_ops.loss_grad(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus_t, taus_l,
-                              float(self.GAMMA ** self.n_step), self._scratch, self._loss, self._grad)
-            world = mdist.all_reduce_sum_(self._grad)             # no-op (returns 1) unless torch.distributed is initialised
-            opt.step_count += 1
-            iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
-                              grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm,
-                              packed_tc=L.packed_tc)
+            self._update((states, actions, rewards, next_states, dones), (taus_t, taus_l))
         return self._loss.detach().cpu().numpy()[0]
 
     def train_async(self, experiences, taus):
         """train() without the device->host read of the loss (for CUDA-graph / benchmark loops). Returns the loss tensor."""
+        self._update(experiences, taus)
+        return self._loss
+
+    def _update(self, experiences, taus):
+        """loss.backward() ... optimizer.step() (agent.py:296-300) in two launches: the fused per-tile kernel (iqn_loss_partials)
+        and the fused tail (iqn_update_tail: fixed-order sum of the tile partials, one-shot all-reduce of the gradient over peer
+        memory when torch.distributed is initialised, clip_grad_norm_ 0.5, Adam, refresh of the kernel-side weight copies).
+        `fused_tail = False` (or GPUs without peer access) keeps the three-launch path with torch.distributed's all-reduce."""
         states, actions, rewards, next_states, dones = experiences
         B = states.shape[0]
         need = iqn_ops.train_scratch_floats(B)
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.float32, device=self.device)
         L, T, opt = self.qnetwork_local, self.qnetwork_target, self.optimizer
+        gamma_n = float(self.GAMMA ** self.n_step)
+        if self.fused_tail and self._tail is None:
+            self._tail = iqn_ops.UpdateTail(self.device)
+            if self._tail.peer_error is not None:
+                warnings.warn("IQNAgent: peer-memory gradient exchange unavailable (%s); using torch.distributed all_reduce" % self._tail.peer_error)
+        if self.fused_tail and self._tail.world == mdist.world_size():
+            iqn_ops.loss_partials(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus[0], taus[1],
+                                  gamma_n, self._scratch)
+            opt.step_count += 1
+            self._tail.step(L.flat, opt.m, opt.v, L.packed, L.packed_tc, self._scratch, B, opt.step_count, loss=self._loss,
+                            grad=self._grad if self.keep_grad else None, grad_norm=self._grad_norm, lr=opt.lr, max_norm=0.5,
+                            beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps)
+            return
         iqn_ops.loss_grad(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus[0], taus[1],
-                          float(self.GAMMA ** self.n_step), self._scratch, self._loss, self._grad)
-        world = mdist.all_reduce_sum_(self._grad)
+                          gamma_n, self._scratch, self._loss, self._grad)
+        world = mdist.all_reduce_sum_(self._grad)                 # no-op (returns 1) unless torch.distributed is initialised
         opt.step_count += 1
         iqn_ops.clip_adam(L.flat, self._grad, opt.m, opt.v, L.packed, step=opt.step_count, lr=opt.lr, max_norm=0.5,
                           grad_scale=1.0 / world, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, grad_norm=self._grad_norm,
                           packed_tc=L.packed_tc)
-        return self._loss
 
     def soft_update(self, local_model, target_model):
         """agent.py:307-317: theta_target = TAU * theta_local + (1 - TAU) * theta_target (TAU = 1: hard copy)."""

@@ -90,6 +90,104 @@ def clip_adam(params, grad, m, v, packed, step, lr=1e-4, max_norm=0.5, grad_scal
     _lib.check(rc, "iqn_clip_adam")
 
 
+def loss_partials(params_l, packed_l, params_t, packed_t, states, actions, rewards, next_states, dones, taus_t, taus_l, gamma_n, scratch):
+    """iqn_loss_grad without the reduction: per-tile partial gradients / losses stay in `scratch` (consumed by UpdateTail.step)."""
+    B = states.shape[0]
+    _f32(params_l, N_PARAMS, "params_local"); _f32(params_t, N_PARAMS, "params_target")
+    _f32(packed_l, N_PACKED, "packed_local"); _f32(packed_t, N_PACKED, "packed_target")
+    _f32(states, B * OBS_DIM, "states"); _f32(next_states, B * OBS_DIM, "next_states")
+    _f32(rewards, B, "rewards"); _f32(dones, B, "dones"); _f32(taus_t, B * 8, "taus_target"); _f32(taus_l, B * 8, "taus_local")
+    if actions.dtype != torch.int64 or actions.numel() != B or not actions.is_cuda or not actions.is_contiguous():
+        raise _lib.MarinenavError("actions: expected contiguous CUDA int64 [B]")
+    if scratch.numel() < train_scratch_floats(B):
+        raise _lib.MarinenavError("scratch too small")
+    rc = _lib.load().iqn_loss_partials(_lib.ptr(params_l), _lib.ptr(packed_l), _lib.ptr(params_t), _lib.ptr(packed_t),
+                                       _lib.ptr(states), _lib.ptr(actions), _lib.ptr(rewards), _lib.ptr(next_states),
+                                       _lib.ptr(dones), _lib.ptr(taus_t), _lib.ptr(taus_l), C.c_float(gamma_n),
+                                       _lib.ptr(scratch), B, _stream())
+    _lib.check(rc, "iqn_loss_partials")
+
+
+class UpdateTail:
+    """Host-side state of iqn_update_tail: the grid-barrier words and, for data-parallel replicas, the peer-mapped exchange
+    buffers of the one-shot all-reduce (CUDA IPC handles exchanged once through torch.distributed).
+
+    peer_exchange: None (auto: on when torch.distributed is initialised with more than one rank), True (required) or False
+    (single-GPU tail; the caller all-reduces itself).  If the buffers cannot be mapped (no peer access between the GPUs) and
+    peer_exchange is None, `self.world` stays 1 and `self.peer_error` says why -- the caller then keeps the NCCL path."""
+
+    def __init__(self, device, peer_exchange=None):
+        import torch.distributed as dist
+        L = _lib.load()
+        self.device = torch.device(device)
+        self.sync = torch.zeros(int(L.iqn_tail_sync_bytes()), dtype=torch.uint8, device=self.device)
+        self.world, self.rank, self.peer_error = 1, 0, None
+        self._own, self._opened, self._peer_array = None, [], None
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if peer_exchange is False or not distributed:
+            if peer_exchange is True and not distributed:
+                raise _lib.MarinenavError("UpdateTail(peer_exchange=True) needs an initialised torch.distributed group of > 1 ranks")
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        nh = int(L.iqn_xchg_handle_bytes())
+        own, handle = C.c_void_p(), C.create_string_buffer(nh)
+        with torch.cuda.device(self.device):
+            rc = L.iqn_xchg_alloc(C.byref(own), handle)
+            err = None if rc == 0 else L.mnv_last_error_string().decode()
+            mine = torch.tensor(list(handle.raw) + [0 if rc == 0 else 1], dtype=torch.uint8, device=self.device)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ptrs = (C.c_void_p * world)()
+            ok = all(int(h[-1]) == 0 for h in allh) and world <= 8
+            if ok:
+                for r in range(world):
+                    if r == rank:
+                        ptrs[r] = own.value
+                        continue
+                    q = C.c_void_p()
+                    rc = L.iqn_xchg_open(bytes(allh[r][:nh].cpu().tolist()), C.byref(q))
+                    if rc != 0:
+                        ok, err = False, L.mnv_last_error_string().decode()
+                        break
+                    ptrs[r] = q.value
+                    self._opened.append(q)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)                 # all ranks or none
+            if int(flag.item()) == 1:
+                self._own, self._peer_array, self.world, self.rank = own, ptrs, world, rank
+            else:
+                for q in self._opened:
+                    L.iqn_xchg_close(q)
+                self._opened = []
+                if own.value:
+                    L.iqn_xchg_free(own)
+                self.peer_error = err or "a peer rank could not map the exchange buffers"
+                if peer_exchange is True:
+                    raise _lib.MarinenavError(f"UpdateTail: peer exchange unavailable: {self.peer_error}")
+
+    def step(self, params, m, v, packed, packed_tc, scratch, B, step, loss=None, grad=None, grad_norm=None, lr=1e-4, max_norm=0.5,
+             beta1=0.9, beta2=0.999, eps=1e-8):
+        for t, n in ((params, "params"), (m, "m"), (v, "v")):
+            _f32(t, N_PARAMS, n)
+        if grad is not None:
+            _f32(grad, N_PARAMS, "grad")
+        rc = _lib.load().iqn_update_tail(_lib.ptr(params), _lib.ptr(m), _lib.ptr(v), _lib.ptr(packed), _lib.ptr(packed_tc),
+                                         _lib.ptr(scratch), int(B), _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(grad_norm),
+                                         _lib.ptr(self.sync), self._peer_array, self.rank, self.world,
+                                         C.c_float(max_norm), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                         int(step), _stream())
+        _lib.check(rc, "iqn_update_tail")
+
+    def close(self):
+        L = _lib.load()
+        if self._own is not None:
+            torch.cuda.synchronize(self.device)
+            for q in self._opened:
+                L.iqn_xchg_close(q)
+            L.iqn_xchg_free(self._own)
+            self._own, self._opened, self._peer_array, self.world = None, [], None, 1
+
+
 def packed_tc_bytes():
     return int(_lib.load().iqn_packed_tc_bytes())
 

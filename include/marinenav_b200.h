@@ -221,6 +221,35 @@ int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d
                       float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                       float* d_grad_norm, void* stream);
 
+/* The data-parallel update in two launches.  iqn_loss_partials = iqn_loss_grad without the reduction: the per-tile partial
+ * gradients and losses stay in d_scratch.  iqn_update_tail then does, in ONE launch, everything behind loss.backward()
+ * (agent.py:298-300): fixed-order sum of the tile partials, (world > 1) a one-shot all-reduce of the gradient through peer
+ * memory over NVLink -- every CTA publishes its 256-parameter slice in this rank's exchange buffer, flags the peers with
+ * system-scope release stores, and sums the peers' slices in rank order (bit-identical replicas; gradient = mean over ranks)
+ * -- then clip_grad_norm_(max_norm) + Adam.step + refresh of d_packed / d_packed_tc like iqn_clip_adam.  Outputs d_loss,
+ * d_grad (the averaged unclipped gradient) and d_grad_norm are optional.
+ *   d_sync: iqn_tail_sync_bytes() bytes, zeroed ONCE by the caller, then owned by the kernels (grid-barrier epochs);
+ *   peer_xchg: HOST array of `world` device pointers, entry r = rank r's exchange buffer (iqn_xchg_bytes() bytes each, zeroed
+ *   once) as mapped into THIS process -- own entry from iqn_xchg_alloc, the others from iqn_xchg_open on the 64-byte handles
+ *   the ranks exchange once at start-up (CUDA IPC; same node).  NULL / world == 1: single GPU.  Every rank must issue the
+ *   same sequence of iqn_update_tail calls (the epochs advance in lockstep); world <= 8. */
+int     iqn_loss_partials(const float* d_params_local, const float* d_packed_local, const float* d_params_target,
+                          const float* d_packed_target, const float* d_states, const int64_t* d_actions,
+                          const float* d_rewards, const float* d_next_states, const float* d_dones,
+                          const float* d_taus_target, const float* d_taus_local, float gamma_n,
+                          float* d_scratch, int64_t B, void* stream);
+int64_t iqn_tail_sync_bytes(void);
+int64_t iqn_xchg_bytes(void);
+int32_t iqn_xchg_handle_bytes(void);
+int     iqn_xchg_alloc(void** d_ptr, unsigned char* handle);
+int     iqn_xchg_open(const unsigned char* handle, void** d_ptr);
+int     iqn_xchg_close(void* d_ptr);
+int     iqn_xchg_free(void* d_ptr);
+int     iqn_update_tail(float* d_params, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
+                        const float* d_scratch, int64_t B, float* d_loss, float* d_grad, float* d_grad_norm,
+                        void* d_sync, void* const* peer_xchg, int32_t rank, int32_t world,
+                        float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
 /* Acting forward on the tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in TMEM): get_qvals + argmax for a
  * whole env batch, K = n_tau = 32 (ObsEncoder.K, model.py:118).  Same inputs as iqn_forward; outputs d_qmean f32 [B][9]
  * and/or d_greedy i32 [B].  d_packed_tc: iqn_packed_tc_bytes() bytes of bf16 weight tiles, refresh with iqn_pack_tc after

@@ -2,7 +2,7 @@
 """Per-source-line summary of an ncu report (CPU only): warp instructions executed per warp, share of the stall samples and
 the top stall reasons, from `ncu -i REP --page source --csv --print-source cuda,sass` (needs -lineinfo at compile time).
 
-    python scripts/ncu_lines.py gpurun_out/r2_step_v6.ncu-rep [n_warps] > profiles/..._source_stalls.txt
+    python scripts/ncu_lines.py gpurun_out/r2_step_v6.ncu-rep [n_warps] [kernel-name regex] > profiles/..._source_stalls.txt
 """
 import csv
 import io
@@ -11,7 +11,8 @@ import sys
 
 rep = sys.argv[1]
 n_warps = float(sys.argv[2]) if len(sys.argv) > 2 else 2048.0
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kfilter = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kfilter, capture_output=True, text=True).stdout
 # the output holds one table per (file, function); take the first function's table (launch 0)
 lines = txt.splitlines()
 start = next(i for i, ln in enumerate(lines) if ln.startswith('"Line No"'))
