@@ -387,7 +387,7 @@ iqn_train_kernel(const float* __restrict__ PL, const float* __restrict__ PTL, co
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a dependent launch (iqn_update_tail) may be placed early; it waits for this grid's completion itself
     const int t = threadIdx.x;
     const long long tile = blockIdx.x, s0 = tile * 8;
-    float* __restrict__ g = gpart_all + tile * (long long)kParams;
+    float* __restrict__ g = gpart_all + tile * (long long)kPartStride;
     constexpr int NT8 = kTrainTaus;
 
     // ---- target network on next_states (taus drawn first: Q9) -> T_j = r + gamma^n (1 - done) max_a Q'(s', tau_j) ----
@@ -558,10 +558,10 @@ iqn_reduce_kernel(const float* __restrict__ gpart, const float* __restrict__ los
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const float* p = gpart + i;
         int tile = 0;
-        for (; tile + 4 <= n_tiles; tile += 4, p += 4ll * kParams) {
-            a0 += p[0]; a1 += p[kParams]; a2 += p[2ll * kParams]; a3 += p[3ll * kParams];
+        for (; tile + 4 <= n_tiles; tile += 4, p += 4ll * kPartStride) {
+            a0 += p[0]; a1 += p[kPartStride]; a2 += p[2ll * kPartStride]; a3 += p[3ll * kPartStride];
         }
-        for (; tile < n_tiles; ++tile, p += kParams) a0 += p[0];
+        for (; tile < n_tiles; ++tile, p += kPartStride) a0 += p[0];
         grad[i] = (a0 + a1) + (a2 + a3);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -643,7 +643,7 @@ extern "C" int iqn_packed_count(void) { return iqn::kPacked; }
 extern "C" int64_t iqn_train_scratch_floats(int64_t B)
 {
     const int64_t tiles = (B + 7) / 8;
-    return tiles * (iqn::kParams + 1);
+    return tiles * (iqn::kPartStride + 1);
 }
 
 extern "C" int iqn_pack(const float* d_params, float* d_packed, void* stream)
@@ -689,7 +689,7 @@ int launch_train(const float* d_params_local, const float* d_packed_local, const
     if (rc) return rc;
     const long long tiles = (B + 7) / 8;
     float* gpart = d_scratch;
-    float* lpart = d_scratch + tiles * (long long)kParams;
+    float* lpart = d_scratch + tiles * (long long)kPartStride;
     iqn_train_kernel<<<(unsigned)tiles, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(
         d_params_local, d_packed_local, d_params_target, d_packed_target, d_states, (const long long*)d_actions, d_rewards,
         d_next_states, d_dones, d_taus_target, d_taus_local, gamma_n, gpart, lpart, B);
@@ -720,7 +720,7 @@ extern "C" int iqn_loss_grad(const float* d_params_local, const float* d_packed_
                           d_dones, d_taus_target, d_taus_local, gamma_n, d_scratch, B, stream, "iqn_loss_grad(train)");
     if (rc) return rc;
     const long long tiles = (B + 7) / 8;
-    iqn_reduce_kernel<<<(kParams + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_scratch, d_scratch + tiles * (long long)kParams, (int)tiles,
+    iqn_reduce_kernel<<<(kParams + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_scratch, d_scratch + tiles * (long long)kPartStride, (int)tiles,
                                                                                  d_grad, d_loss);
     return mnv_launch_status("iqn_loss_grad(reduce)");
 }

@@ -10,6 +10,9 @@ constexpr int kObs = 26, kFeat = 208, kCos = 64, kHid = 64, kAct = 9, kTrainTaus
 // flat fp32 parameter vector = state_dict order (velocity_encoder.weight ... output_layer.bias), 35 785 floats
 constexpr int oVW = 0, oVB = 32, oGW = 48, oGB = 80, oSW = 96, oSB = 3968, oCW = 4144, oCB = 17456,
               oH1W = 17664, oH1B = 30976, oH2W = 31040, oH2B = 35136, oOW = 35200, oOB = 35776, kParams = 35785;
+// stride of one tile's partial gradient in the training scratch: kParams rounded up to a whole number of 128-byte lines
+// (kParams is odd; the weight-gradient epilogues store 8-byte pairs)
+constexpr int kPartStride = 35840;
 // per-tensor boundaries (for torch's per-tensor clip norm) in the same order
 __host__ __device__ constexpr int tensor_begin(int i)
 {

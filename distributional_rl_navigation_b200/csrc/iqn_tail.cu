@@ -85,13 +85,13 @@ iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict_
         const int t0 = q * per, t1 = min(n_tiles, t0 + per);
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (i < kParams) {
-            const float* g = gpart + (long long)t0 * kParams + i;
+            const float* g = gpart + (long long)t0 * kPartStride + i;
             int tile = t0;
-            for (; tile + 8 <= t1; tile += 8, g += 8ll * kParams) {
+            for (; tile + 8 <= t1; tile += 8, g += 8ll * kPartStride) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] += __ldcg(g + (long long)k * kParams);
+                for (int k = 0; k < 8; ++k) a[k] += __ldcg(g + (long long)k * kPartStride);
             }
-            for (; tile < t1; ++tile, g += kParams) a[0] += __ldcg(g);
+            for (; tile < t1; ++tile, g += kPartStride) a[0] += __ldcg(g);
         }
         s_part[q][p] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
@@ -259,7 +259,7 @@ extern "C" int iqn_update_tail(float* d_params, float* d_m, float* d_v, float* d
     TailHyper H{max_norm, (float)((double)lr / bc1), beta1, beta2, (float)(1.0 / sqrt(bc2)), eps};
     const long long tiles = (B + 7) / 8;
     const float* gpart = d_scratch;
-    const float* lpart = d_scratch + tiles * (long long)kParams;
+    const float* lpart = d_scratch + tiles * (long long)kPartStride;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(kTailBlocks); cfg.blockDim = dim3(kTailThreads); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
