@@ -14,19 +14,25 @@
 // agent.py:200-203 -- no tau tensor in HBM, no separate random / select launches.
 //
 // One persistent CTA per SM, 512 threads = two groups of 256, each group owns one tile (128 rows = 4 environments x 32 taus)
-// at a time, so that one group's epilogue overlaps the other group's MMAs:
-//   * all four weight matrices (with their bias as one extra reduction column) live in shared memory for the whole kernel
-//     as bf16 K-major core-matrix tiles (pre-packed by iqn_pack_tc, 73 KB);
+// at a time, so that one group's epilogue overlaps the other group's MMAs; inside a group the FIRST layer of the next tile is
+// software-pipelined under the later layers of the current one:
+//   * all four weight matrices live in shared memory for the whole kernel as bf16 K-major core-matrix tiles (pre-packed by
+//     iqn_pack_tc with the bias as one extra reduction column; layer 1's bias is folded into its cos_0 = 1 column when the
+//     tile is copied in, so its reduction length is exactly 64);
 //   * A operands are produced in-kernel and written straight into the same UMMA canonical layout (no swizzle):
-//       A0 = cos(pi i tau)            (Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1}: one FFMA per feature)
-//       A1 = bf16(relu(D1 + b_c)) * bf16(feat)    A2 = relu(D2 + b_1)    A3 = relu(D3 + b_2)     (cvt.rn.relu.bf16x2 + mul.bf16x2)
-//   * one elected thread issues tcgen05.mma (M = 128, N = 208 / 64 / 64 / 16, K = 16 per instruction), accumulators in
-//     TMEM (208 + 64 + 64 + 16 columns), completion through tcgen05.commit -> mbarrier;
-//   * epilogues read TMEM with tcgen05.ld.32x32b (thread = row), apply bias / relu / the feature product, convert to
-//     bf16 and store 16-byte chunks for the next layer; the last epilogue averages the 32 rows of an environment with
-//     warp shuffles (one warp == one environment) and takes the argmax.
+//       A0 = cos(pi i tau)            (Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1}: one FFMA per feature; own 16 KB buffer)
+//       A1 = bf16(relu(D1)) * bf16(feat)    A2 = relu(D2)    A3 = relu(D3)     (cvt.rn.relu.bf16x2 + mul.bf16x2; one 56 KB region)
+//   * one elected thread issues tcgen05.mma (M = 128, N = 192 + 16 / 64 / 64 / 16, K = 16 per instruction), accumulators in
+//     TMEM, completion through tcgen05.commit -> two mbarriers per group (layer 1 | layers 2-4);
+//   * per tile i:  wait D1(i) -> epilogue 1 -> issue layer 2 -> [while it runs: A0(i+1), issue layer 1a(i+1)] -> epilogue 2
+//     -> layer 3 -> epilogue 3 -> issue layer 4 (+ layer 1b(i+1), whose 16 TMEM columns are free only now) -> mean over the 32
+//     rows of an environment with warp shuffles (one warp == one environment), argmax, epsilon-greedy.
+//     TMEM columns of a group (256): D1a (features 0..191) at [64, 256), D1b (192..207) at [0, 16), D2 = D3 at [0, 64),
+//     D4 at [32, 48);
+//   * epilogues read TMEM with tcgen05.ld.32x32b (thread = row), convert to bf16 and store 16-byte chunks for the next layer.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <type_traits>
 
 #include "iqn_common.cuh"
 #include "philox.cuh"
@@ -42,22 +48,22 @@ constexpr int kTaus = 32;               // quantile samples per environment (Obs
 constexpr int kEnvsPerTile = kRows / kTaus;
 constexpr int kTmemCols = 512;
 
-// TMEM column bases of the four accumulators
-// (per tile group: 256 columns; D2 / D3 / D4 reuse D1's columns, which the first epilogue has drained by then)
-constexpr uint32_t kD1 = 0, kD2 = 0, kD3 = 64, kD4 = 128;
+// TMEM column bases inside a group's 256 columns (see the header comment)
+constexpr uint32_t kD1a = 64, kD1b = 0, kD2 = 0, kD3 = 0, kD4 = 32;
+constexpr int kN1a = 192, kN1b = kFeat - kN1a;      // layer 1 is issued as two MMAs: features [0, 192) and [192, 208)
+constexpr int kK0s = kCos;                          // layer 1's reduction length in shared memory: bias folded into column 0
 
 // per tile-group buffers (two groups of 256 threads keep two tiles in flight per CTA)
 struct __align__(128) GroupSmem {
-    // ONE operand region per group: A0 (cos features, 16 KB) is consumed by layer 1 before the first epilogue overwrites
-    // the region with A1 (52 KB); A2 / A3 (16 KB each) are written after layers 2 / 3 have consumed A1 / A2.
+    // A1 (52 KB + bias step) is written by the first epilogue; A2 / A3 (16 KB each) overwrite it after layers 2 / 3 consumed it
     __nv_bfloat16 a1[kRows * kK1];
+    __nv_bfloat16 a0[kRows * kK0s];                      // cos features of the NEXT tile while this tile is in layers 2-4
     __nv_bfloat16 feat[kEnvsPerTile * kFeat];            // observation-encoder output of the tile's environments (from the pre-pass)
-    float tau[kRows];
-    unsigned long long bar;
+    unsigned long long bar_a, bar_b;                     // layer 1 | layers 2-4
 };
 
 struct __align__(128) Smem {
-    __nv_bfloat16 wc[kWcEl], w1[kW1El], w2[kW2El], w3[kW3El];
+    __nv_bfloat16 wc[kFeat * kK0s], w1[kW1El], w2[kW2El], w3[kW3El];
     GroupSmem g[2];
     uint32_t tmem_base;
 };
@@ -116,6 +122,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // 32 consecutive columns of this thread's row with ONE round trip to TMEM
@@ -177,7 +196,7 @@ __device__ __forceinline__ void store_bias_step(__nv_bfloat16* base, int r, int 
     *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8 + 8, K)) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// issue the K/16 MMAs of one layer (one elected thread), then commit to the mbarrier
+// issue the K/16 MMAs of one layer (one elected thread), then commit to the mbarrier (if given)
 __device__ __forceinline__ void issue_layer(const __nv_bfloat16* A, const __nv_bfloat16* B, int K, int N, uint32_t tmem_d,
                                             unsigned long long* bar)
 {
@@ -185,7 +204,7 @@ __device__ __forceinline__ void issue_layer(const __nv_bfloat16* A, const __nv_b
     const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
     for (int k = 0; k < K / 16; ++k)                       // one instruction consumes K = 16 = two 128-byte core matrices
         umma(tmem_d, make_desc(a0 + k * 256, K), make_desc(b0 + k * 256, K), idesc, k > 0 ? 1u : 0u);
-    umma_commit(bar);
+    if (bar != nullptr) umma_commit(bar);
 }
 
 // ---- pre-pass: everything that depends on the environment alone -------------------------------------------------------
@@ -296,7 +315,7 @@ __device__ __forceinline__ philox::u4 act_draw(const ActArgs& A, long long env, 
 }
 
 // Two groups of 256 threads per CTA, each owning one 128-row tile at a time (its own A buffers, TMEM columns and
-// mbarrier): while one group runs an epilogue on the CUDA cores the other group's MMAs occupy the tensor core.
+// mbarriers): while one group runs an epilogue on the CUDA cores the other group's MMAs occupy the tensor core.
 __global__ void __launch_bounds__(kThreads, 1)
 iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
 {
@@ -311,17 +330,33 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
     const int half = (warp >> 2) & 1;                        // column half handled by this warp (warps q and q+4 share a lane quadrant)
     GroupSmem& gs = s.g[g];
 
-    // ---- one-time setup: weights + biases to shared memory, TMEM allocation, mbarriers ----
+    // ---- one-time setup: weights to shared memory, TMEM allocation, mbarriers ----
     {
+        // layer 1: packed [208][80] (64 weights | bias | 15 zeros) -> shared [208][64] with the bias folded into column 0
+        // (cos(pi 0 tau) = 1 for every row): 16-byte chunk (f, kc) keeps its place inside the row group, the row stride shrinks
         const uint4* src = reinterpret_cast<const uint4*>(Wp);
-        uint4* dst = reinterpret_cast<uint4*>(s.wc);        // wc, w1, w2, w3 are contiguous in Smem and in the packed buffer
-        for (int i = t; i < kPackedTcEl / 8; i += kThreads) dst[i] = __ldg(src + i);
+        uint4* dst = reinterpret_cast<uint4*>(s.wc);
+        for (int i = t; i < kFeat * (kK0s / 8); i += kThreads) {
+            const int f = i / (kK0s / 8), kc = i % (kK0s / 8);
+            uint4 v = __ldg(src + tile_offset(f, kc * 8, kK0) / 8);
+            if (kc == 0) {
+                const __nv_bfloat16 b = Wp[tile_offset(f, kCos, kK0)];
+                __nv_bfloat16 w0 = *reinterpret_cast<const __nv_bfloat16*>(&v.x);
+                w0 = __float2bfloat16_rn(__bfloat162float(w0) + __bfloat162float(b));
+                v.x = (v.x & 0xffff0000u) | (uint32_t)(*reinterpret_cast<const unsigned short*>(&w0));
+            }
+            dst[tile_offset(f, kc * 8, kK0s) / 8] = v;
+        }
+        // layers 2-4: contiguous in the packed buffer and in Smem
+        const uint4* src2 = reinterpret_cast<const uint4*>(Wp + kWcEl);
+        uint4* dst2 = reinterpret_cast<uint4*>(s.w1);
+        for (int i = t; i < (kW1El + kW2El + kW3El) / 8; i += kThreads) dst2[i] = __ldg(src2 + i);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tg == 32) mbar_init(&gs.bar, 1);
+    if (tg == 32) { mbar_init(&gs.bar_a, 1); mbar_init(&gs.bar_b, 1); }
     fence_async_smem();
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tc_fence_before();
@@ -330,19 +365,20 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
     const uint32_t tmem = s.tmem_base + (uint32_t)g * 256u;           // this group's 256 TMEM columns
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;     // this warp's TMEM lane quadrant
     const int row = (warp & 3) * 32 + lane;                           // TMEM lane == tile row of this thread
-    uint32_t phase = 0;
+    uint32_t phase_a = 0, phase_b = 0;
 
     const long long n_tiles = (B + kEnvsPerTile - 1) / kEnvsPerTile;
     const long long tile_step = (long long)gridDim.x * 2;
     long long tile = (long long)blockIdx.x * 2 + g;
 
-    // inputs of a tile, prefetched one tile ahead: threads 0..127 carry tau of row tg (from the caller's tensor, or drawn
-    // from the Philox stream), threads 128..231 one 16-byte chunk of the tile's 4 x 208 bf16 encoder features
+    // inputs of a tile, prefetched one tile ahead: every thread carries tau of ITS row (from the caller's tensor, or drawn
+    // from the Philox stream; both column halves of a row compute the same value), threads 128..231 one 16-byte chunk of
+    // the tile's 4 x 208 bf16 encoder features
     auto load_tau = [&](long long tl) -> float {
-        if (tl >= n_tiles || tg >= kRows) return 0.f;
-        const long long b = tl * kEnvsPerTile + tg / kTaus;
+        if (tl >= n_tiles) return 0.f;
+        const long long b = tl * kEnvsPerTile + row / kTaus;
         if (b >= B) return 0.f;
-        const int k = tg % kTaus;
+        const int k = row % kTaus;
         float u;
         if (A.sample) {
             const philox::u4 r = act_draw(A, b, (unsigned)(k >> 2));
@@ -358,87 +394,99 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         if (b >= B) return make_uint4(0u, 0u, 0u, 0u);
         return __ldg(reinterpret_cast<const uint4*>(A.feat + b * kFeat) + (i % (kFeat / 8)));
     };
+    // A0 = cos(pi i tau), i = 0..63 (model.py:130,155): thread (row, half) fills i in [32 half, 32 half + 32) with the
+    // Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1} (one FFMA per feature), started from cos.approx of the argument
+    // reduced to [-pi, pi].  The values are rounded to bf16 (2^-9 relative) right away; the recurrence's error over 32
+    // steps stays below 1e-4.  Column 0 is exactly 1: it carries layer 1's bias (folded into the weight tile).
+    auto produce_a0 = [&](float tau) {
+        auto cospi = [](float x) { x = x - 2.f * rintf(0.5f * x); return __cosf(3.14159265358979f * x); };
+        const float c1 = cospi(tau), two_c1 = 2.f * c1;
+        float cm = half == 0 ? c1 : cospi(31.f * tau);           // c_{i-1} at i = 32 half  (c_{-1} = c_1)
+        float c = half == 0 ? 1.f : cospi(32.f * tau);           // c_i
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = c;
+                const float cn = fmaf(two_c1, c, -cm);
+                cm = c; c = cn;
+            }
+            store_chunk(gs.a0, row, half * 4 + kc, kK0s, v);
+        }
+    };
+    // layer 1 of a tile as two MMAs: features [0, 192) -> D1a, [192, 208) -> D1b
+    auto issue_l1a = [&]() { issue_layer(gs.a0, s.wc, kK0s, kN1a, tmem + kD1a, nullptr); };
+    auto issue_l1b = [&]() { issue_layer(gs.a0, s.wc + tile_offset(kN1a, 0, kK0s), kK0s, kN1b, tmem + kD1b, nullptr); };
+    // one block of W (32 | 16 | 8) D1 columns starting at feature n0: relu(D1) * feat in bf16 -> A1 chunks (model.py:177-180)
+    auto e1_block = [&](auto width, int n0, const __nv_bfloat16* feat) {
+        constexpr int W = decltype(width)::value;
+        float v[W];
+        const uint32_t taddr = tmem + lane_base + (n0 < kN1a ? kD1a + (uint32_t)n0 : kD1b + (uint32_t)(n0 - kN1a));
+        if constexpr (W == 32) tmem_ld32(taddr, v); else if constexpr (W == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
+        if (debug != nullptr && tile == (long long)blockIdx.x * 2 + g && blockIdx.x == 0 && g == 0)
+            for (int j = 0; j < W; ++j) debug[row * kFeat + n0 + j] = v[j];
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) store_relu_chunk(gs.a1, row, (n0 >> 3) + q, kK1, v + q * 8, feat + n0 + q * 8);
+    };
+
     float n_tau = load_tau(tile);
     uint4 n_feat = load_feat(tile);
+    if (tile < n_tiles) {                                     // prologue: layer 1 of this group's first tile
+        produce_a0(n_tau);
+        fence_async_smem();
+        tc_fence_before();
+        group_sync(g);
+        if (tg == 0) { tc_fence_after(); issue_l1a(); issue_l1b(); umma_commit(&gs.bar_a); }
+        n_tau = load_tau(tile + tile_step);
+    }
 
     for (; tile < n_tiles; tile += tile_step) {
         const long long env0 = tile * kEnvsPerTile;
-        if (tg < kRows) gs.tau[tg] = n_tau;
-        else if (tg < kRows + kEnvsPerTile * (kFeat / 8)) reinterpret_cast<uint4*>(gs.feat)[tg - kRows] = n_feat;
-        n_tau = load_tau(tile + tile_step);                  // prefetch the next tile's inputs: consumed one iteration later
-        n_feat = load_feat(tile + tile_step);
-        group_sync(g);
-        // ---- A0 = cos(pi i tau), i = 0..63 (model.py:130,155): thread (row, half) fills i in [32 half, 32 half + 32) with the
-        //      Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1} (one FFMA per feature), started from cos.approx of the
-        //      argument reduced to [-pi, pi].  The values are rounded to bf16 (2^-9 relative) right away; the recurrence's
-        //      error over 32 steps stays below 1e-4. ----
-        {
-            const float tau = gs.tau[row];
-            auto cospi = [](float x) { x = x - 2.f * rintf(0.5f * x); return __cosf(3.14159265358979f * x); };
-            const float c1 = cospi(tau), two_c1 = 2.f * c1;
-            float cm = half == 0 ? c1 : cospi(31.f * tau);           // c_{i-1} at i = 32 half  (c_{-1} = c_1)
-            float c = half == 0 ? 1.f : cospi(32.f * tau);           // c_i
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[j] = c;
-                    const float cn = fmaf(two_c1, c, -cm);
-                    cm = c; c = cn;
-                }
-                store_chunk(gs.a1, row, half * 4 + kc, kK0, v);
-            }
-            if (half == 0) store_bias_step(gs.a1, row, kCos / 8, kK0);
-        }
-        fence_async_smem();
-        tc_fence_before();
+        const bool has_next = tile + tile_step < n_tiles;    // group-uniform
+        const bool dbg = debug != nullptr && blockIdx.x == 0 && g == 0 && tile == 0;
+        if (tg >= kRows && tg < kRows + kEnvsPerTile * (kFeat / 8)) reinterpret_cast<uint4*>(gs.feat)[tg - kRows] = n_feat;
+        n_feat = load_feat(tile + tile_step);                // prefetch the next tile's features: consumed one iteration later
         group_sync(g);
 
-        // ---- layer 1: D1[128 x 208] = A0 . Wc^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.wc, kK0, kFeat, tmem + kD1, &gs.bar); }
-        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
-        phase ^= 1;
+        // ---- D1 = A0 . Wc'^T (issued one tile ahead) -> epilogue 1: this warp's 104 features [104 half, 104 half + 104) ----
+        mbar_wait(&gs.bar_a, phase_a);                       // every thread of the group sleeps on the MMA's mbarrier
+        phase_a ^= 1;
         tc_fence_after();
         {
-            // this warp's 104 columns [104 half, 104 half + 104) = 3 x 32 + 8
             const __nv_bfloat16* feat = gs.feat + (row / kTaus) * kFeat;
-            const int c0 = half * 104;
-#pragma unroll 1
-            for (int blk = 0; blk < 3; ++blk) {
-                float v[32];
-                const int col = c0 + blk * 32;
-                tmem_ld32(tmem + lane_base + kD1 + col, v);
-                if (debug != nullptr && tile == 0)
-                    for (int j = 0; j < 32; ++j) debug[row * kFeat + col + j] = v[j];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)                       // model.py:177-180 (bias already in D1): relu(D1) * feat, bf16 x bf16
-                    store_relu_chunk(gs.a1, row, (col >> 3) + q, kK1, v + q * 8, feat + col + q * 8);
+            if (half == 0) {
+                e1_block(std::integral_constant<int, 32>{}, 0, feat); e1_block(std::integral_constant<int, 32>{}, 32, feat);
+                e1_block(std::integral_constant<int, 32>{}, 64, feat); e1_block(std::integral_constant<int, 8>{}, 96, feat);
+            } else {
+                e1_block(std::integral_constant<int, 32>{}, 104, feat); e1_block(std::integral_constant<int, 32>{}, 136, feat);
+                e1_block(std::integral_constant<int, 16>{}, 168, feat); e1_block(std::integral_constant<int, 8>{}, 184, feat);
+                e1_block(std::integral_constant<int, 16>{}, 192, feat);
+                store_bias_step(gs.a1, row, kFeat / 8, kK1);
             }
-            {
-                float v[8];
-                const int col = c0 + 96;
-                tmem_ld8(tmem + lane_base + kD1 + col, v);
-                if (debug != nullptr && tile == 0)
-                    for (int j = 0; j < 8; ++j) debug[row * kFeat + col + j] = v[j];
-                store_relu_chunk(gs.a1, row, col >> 3, kK1, v, feat + col);
-            }
-            if (half == 1) store_bias_step(gs.a1, row, kFeat / 8, kK1);
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
 
-        // ---- layer 2: D2[128 x 64] = A1 . W1^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kK1, kHid, tmem + kD2, &gs.bar); }
-        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
-        phase ^= 1;
+        // ---- layer 2: D2[128 x 64] = A1 . W1^T; while it runs: A0 of the next tile and its layer 1a ----
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kK1, kHid, tmem + kD2, &gs.bar_b); }
+        if (has_next) {                                      // (D1a and A0 of this tile were consumed: layer 1 completed above)
+            produce_a0(n_tau);
+            n_tau = load_tau(tile + 2 * tile_step);
+            fence_async_smem();
+            tc_fence_before();
+            group_sync(g);
+            if (tg == 0) { tc_fence_after(); issue_l1a(); umma_commit(&gs.bar_a); }
+        }
+        mbar_wait(&gs.bar_b, phase_b);
+        phase_b ^= 1;
         tc_fence_after();
         {
             float v[32];
             const int col = half * 32;
             tmem_ld32(tmem + lane_base + kD2 + col, v);
-            if (debug != nullptr && tile == 0)
+            if (dbg)
                 for (int j = 0; j < 32; ++j) debug[kRows * kFeat + row * kHid + col + j] = v[j];
 #pragma unroll
             for (int q = 0; q < 4; ++q) store_relu_chunk(gs.a1, row, (col >> 3) + q, kK2, v + q * 8, nullptr);   // A2 over the (consumed) A1
@@ -449,15 +497,15 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- layer 3: D3[128 x 64] = A2 . W2^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w2, kK2, kHid, tmem + kD3, &gs.bar); }
-        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
-        phase ^= 1;
+        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w2, kK2, kHid, tmem + kD3, &gs.bar_b); }
+        mbar_wait(&gs.bar_b, phase_b);
+        phase_b ^= 1;
         tc_fence_after();
         {
             float v[32];
             const int col = half * 32;
             tmem_ld32(tmem + lane_base + kD3 + col, v);
-            if (debug != nullptr && tile == 0)
+            if (dbg)
                 for (int j = 0; j < 32; ++j) debug[kRows * (kFeat + kHid) + row * kHid + col + j] = v[j];
 #pragma unroll
             for (int q = 0; q < 4; ++q) store_relu_chunk(gs.a1, row, (col >> 3) + q, kK3, v + q * 8, nullptr);   // A3 over the (consumed) A2
@@ -467,23 +515,26 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         tc_fence_before();
         group_sync(g);
 
-        // ---- output layer: D4[128 x 16] = A3 . W3^T, then mean over the 32 taus of each env (one warp) + argmax ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w3, kK3, kN4, tmem + kD4, &gs.bar); }
-        mbar_wait(&gs.bar, phase);                       // every thread of the group sleeps on the MMA's mbarrier (no second barrier)
-        phase ^= 1;
+        // ---- output layer: D4[128 x 16] = A3 . W3^T (+ layer 1b of the next tile: its TMEM columns [0, 16) are free only now),
+        //      then mean over the 32 taus of each env (one warp) + argmax ----
+        if (tg == 0) {
+            tc_fence_after();
+            issue_layer(gs.a1, s.w3, kK3, kN4, tmem + kD4, nullptr);
+            if (has_next) issue_l1b();
+            umma_commit(&gs.bar_b);
+        }
+        mbar_wait(&gs.bar_b, phase_b);
+        phase_b ^= 1;
         tc_fence_after();
         if (half == 0) {
             float q[kN4];
             {
-                float v[8];
-                tmem_ld8(tmem + lane_base + kD4, v);
+                float v[16];
+                tmem_ld16(tmem + lane_base + kD4, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) q[j] = v[j];
-                tmem_ld8(tmem + lane_base + kD4 + 8, v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) q[8 + j] = v[j];
+                for (int j = 0; j < 16; ++j) q[j] = v[j];
             }
-            if (debug != nullptr && tile == 0)
+            if (dbg)
                 for (int j = 0; j < kN4; ++j) debug[kRows * (kFeat + 2 * kHid) + row * kN4 + j] = q[j];
 #pragma unroll
             for (int a = 0; a < kAct; ++a) {

@@ -32,8 +32,11 @@ def emulate(P, x, taus, cvar=1.0):
                            x[:, 2:4] @ P["goal_encoder.weight"].T + P["goal_encoder.bias"],
                            x[:, 4:26] @ P["sensor_encoder.weight"].T + P["sensor_encoder.bias"]], axis=1).astype(np.float32)
     cos = np.cos(np.pi * np.arange(64)[None, None, :] * t[:, :, None].astype(np.float64)).astype(np.float32).reshape(B * K, 64)
-    # the biases ride inside the GEMMs as one extra reduction column (bf16-rounded like the weights)
-    d1 = bf(cos) @ bf(P["cos_embedding.weight"]).T + bf(P["cos_embedding.bias"])
+    # the biases ride inside the GEMMs as one extra reduction column (bf16-rounded like the weights); layer 1's bias is
+    # folded into the weight of cos_0 = 1 (bf16 sum of the two bf16 values, iqn_act_tc.cu)
+    wc = bf(P["cos_embedding.weight"]).copy()
+    wc[:, 0] = bf(wc[:, 0] + bf(P["cos_embedding.bias"]))
+    d1 = bf(cos) @ wc.T
     h0 = bf(np.maximum(d1, 0)) * bf(np.repeat(feat, K, axis=0))       # relu -> bf16, bf16 features, bf16 product (mul.bf16x2)
     d2 = bf(h0) @ bf(P["hidden_layer.weight"]).T + bf(P["hidden_layer.bias"])
     d3 = bf(np.maximum(d2, 0)) @ bf(P["hidden_layer_2.weight"]).T + bf(P["hidden_layer_2.bias"])
