@@ -196,15 +196,25 @@ __device__ __forceinline__ void store_bias_step(__nv_bfloat16* base, int r, int 
     *reinterpret_cast<uint4*>(base + tile_offset(r, kc * 8 + 8, K)) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// issue the K/16 MMAs of one layer (one elected thread), then commit to the mbarrier (if given)
-__device__ __forceinline__ void issue_layer(const __nv_bfloat16* A, const __nv_bfloat16* B, int K, int N, uint32_t tmem_d,
-                                            unsigned long long* bar)
+// issue the K/16 MMAs of one layer (one elected thread of a warp whose operand addresses are warp-uniform FOR THE COMPILER --
+// see the *_u values in the kernel -- so that the descriptors sit in uniform registers and every MMA is one UTCHMMA;
+// thread-dependent addresses make ptxas wrap each MMA in an ELECT / R2UR.BROADCAST waterfall, ~100 cycles per instruction),
+// then commit to the mbarrier (if given).  One instruction consumes K = 16 = two 128-byte core matrices: the descriptors'
+// address fields advance by 256 B >> 4.
+template <int K, int N, int K0 = 0, int K1 = K / 16>
+__device__ __forceinline__ void issue_layer(uint32_t a_saddr, uint32_t b_saddr, uint32_t tmem_d, unsigned long long* bar)
 {
-    const uint32_t idesc = make_idesc(kRows, N);
-    const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
-    for (int k = 0; k < K / 16; ++k)                       // one instruction consumes K = 16 = two 128-byte core matrices
-        umma(tmem_d, make_desc(a0 + k * 256, K), make_desc(b0 + k * 256, K), idesc, k > 0 ? 1u : 0u);
+    constexpr uint32_t idesc = make_idesc(kRows, N);
+    const uint64_t da = make_desc(a_saddr, K), db = make_desc(b_saddr, K);
+#pragma unroll
+    for (int k = K0; k < K1; ++k) umma(tmem_d, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), idesc, k > 0 ? 1u : 0u);   // K-steps [K0, K1)
     if (bar != nullptr) umma_commit(bar);
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- pre-pass: everything that depends on the environment alone -------------------------------------------------------
@@ -253,24 +263,27 @@ iqn_encode_kernel(const float* __restrict__ P, const float* __restrict__ obs, __
                   float* __restrict__ cvar_out, long long B)
 {
     __shared__ __align__(16) float s_w[kEncWFloats];
+    __shared__ __align__(16) float s_raw[oCW];                         // the encoder parameters as stored (coalesced 16-byte copy)
     __shared__ __align__(16) float s_x[kEncEnvs * kObs];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const long long e0 = (long long)blockIdx.x * kEncEnvs;
     const int n_env = (B - e0) < kEncEnvs ? (int)(B - e0) : kEncEnvs;
+    for (int i = t; i < oCW / 4; i += kEncThreads) reinterpret_cast<float4*>(s_raw)[i] = __ldg(reinterpret_cast<const float4*>(P) + i);
+    for (int i = t; i < n_env * kObs; i += kEncThreads) s_x[i] = obs[e0 * kObs + i];
+    __syncthreads();
     // parameters (state_dict order: oVW [16][2], oVB, oGW [16][2], oGB, oSW [176][22], oSB) -> [group][input][16] + bias rows
     for (int i = t; i < kEncWFloats; i += kEncThreads) {
         float v;
         if (i < 2 * kEncSmallFloats) {
             const int g = i / kEncSmallFloats, r = i % kEncSmallFloats, k = r / 16, j = r % 16;
             const int ow = g == 0 ? oVW : oGW, ob = g == 0 ? oVB : oGB;
-            v = k < 2 ? P[ow + j * 2 + k] : P[ob + j];
+            v = k < 2 ? s_raw[ow + j * 2 + k] : s_raw[ob + j];
         } else {
             const int r0 = i - 2 * kEncSmallFloats, g = r0 / kEncSensorFloats, r = r0 % kEncSensorFloats, k = r / 16, j = r % 16;
-            v = k < kEncSensorIn ? P[oSW + (g * 16 + j) * kEncSensorIn + k] : P[oSB + g * 16 + j];
+            v = k < kEncSensorIn ? s_raw[oSW + (g * 16 + j) * kEncSensorIn + k] : s_raw[oSB + g * 16 + j];
         }
         s_w[i] = v;
     }
-    for (int i = t; i < n_env * kObs; i += kEncThreads) s_x[i] = obs[e0 * kObs + i];
     __syncthreads();
     const int el = (w & 3) * 32 + lane;                                  // environment of this lane inside the CTA
     if (el >= n_env) return;
@@ -303,7 +316,9 @@ struct ActArgs {
     const __nv_bfloat16* Wp; const __nv_bfloat16* feat; const float* taus; const float* cvar; float cvar_scalar;
     float* qmean; int32_t* greedy; int32_t* action; float* debug; long long B;
     unsigned long long seed, step; float eps; int sample;             // sample != 0: taus / epsilon-greedy from Philox(seed, step)
+    long long* timing;                                                // lab ("act_timing" option): clock64 stamps of CTA 0's phases
 };
+constexpr int kStamps = 12, kStampTiles = 64;
 
 // Random streams of the sampling mode, all from Philox4x32-10 keyed by `seed`, counter = (env, sub-stream, step):
 //   sub-stream 0..7: the 32 taus of the environment (4 per draw, torch.rand-style 24-bit uniforms, model.py:149)
@@ -329,6 +344,13 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
     const int g = t >> 8, tg = t & 255;                      // tile group, thread index inside the group
     const int half = (warp >> 2) & 1;                        // column half handled by this warp (warps q and q+4 share a lane quadrant)
     GroupSmem& gs = s.g[g];
+    // the same values made warp-uniform for the compiler (a shuffle from lane 0, like cutlass::canonical_warp_idx_sync):
+    // the MMA-issuing warp of each group addresses its operands through these
+    const int warp_u = __shfl_sync(0xffffffffu, t >> 5, 0);
+    const int g_u = warp_u >> 3;
+    const bool issuer = (warp_u & 7) == 0;                    // first warp of the group; one elected lane issues
+    GroupSmem& gsu = s.g[g_u];
+    if (A.timing != nullptr && tg == 0 && blockIdx.x < 4) A.timing[2 * kStampTiles * kStamps + blockIdx.x * 4 + g] = clock64();        // lab: kernel entry
 
     // ---- one-time setup: weights to shared memory, TMEM allocation, mbarriers ----
     {
@@ -363,6 +385,9 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base + (uint32_t)g * 256u;           // this group's 256 TMEM columns
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, s.tmem_base, 0) + (uint32_t)g_u * 256u;
+    const uint32_t a0_u = smem_u32(gsu.a0), a1_u = smem_u32(gsu.a1);
+    const uint32_t wc_u = smem_u32(s.wc), w1_u = smem_u32(s.w1), w2_u = smem_u32(s.w2), w3_u = smem_u32(s.w3);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;     // this warp's TMEM lane quadrant
     const int row = (warp & 3) * 32 + lane;                           // TMEM lane == tile row of this thread
     uint32_t phase_a = 0, phase_b = 0;
@@ -398,26 +423,32 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
     // Chebyshev recurrence c_{i+1} = 2 c_1 c_i - c_{i-1} (one FFMA per feature), started from cos.approx of the argument
     // reduced to [-pi, pi].  The values are rounded to bf16 (2^-9 relative) right away; the recurrence's error over 32
     // steps stays below 1e-4.  Column 0 is exactly 1: it carries layer 1's bias (folded into the weight tile).
-    auto produce_a0 = [&](float tau) {
+    float a0_two_c1 = 0.f, a0_cm = 0.f, a0_c = 1.f;          // recurrence state between the chunks of one row
+    auto a0_begin = [&](float tau) {
         auto cospi = [](float x) { x = x - 2.f * rintf(0.5f * x); return __cosf(3.14159265358979f * x); };
-        const float c1 = cospi(tau), two_c1 = 2.f * c1;
-        float cm = half == 0 ? c1 : cospi(31.f * tau);           // c_{i-1} at i = 32 half  (c_{-1} = c_1)
-        float c = half == 0 ? 1.f : cospi(32.f * tau);           // c_i
+        const float c1 = cospi(tau);
+        a0_two_c1 = 2.f * c1;
+        a0_cm = half == 0 ? c1 : cospi(31.f * tau);           // c_{i-1} at i = 32 half  (c_{-1} = c_1)
+        a0_c = half == 0 ? 1.f : cospi(32.f * tau);           // c_i
+    };
+    auto a0_chunk = [&](int kc) {                             // 8 features: one 16-byte chunk of the operand tile
+        float v[8];
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[j] = c;
-                const float cn = fmaf(two_c1, c, -cm);
-                cm = c; c = cn;
-            }
-            store_chunk(gs.a0, row, half * 4 + kc, kK0s, v);
+        for (int j = 0; j < 8; ++j) {
+            v[j] = a0_c;
+            const float cn = fmaf(a0_two_c1, a0_c, -a0_cm);
+            a0_cm = a0_c; a0_c = cn;
         }
+        store_chunk(gs.a0, row, half * 4 + kc, kK0s, v);
+    };
+    auto produce_a0 = [&](float tau) {
+        a0_begin(tau);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) a0_chunk(kc);
     };
     // layer 1 of a tile as two MMAs: features [0, 192) -> D1a, [192, 208) -> D1b
-    auto issue_l1a = [&]() { issue_layer(gs.a0, s.wc, kK0s, kN1a, tmem + kD1a, nullptr); };
-    auto issue_l1b = [&]() { issue_layer(gs.a0, s.wc + tile_offset(kN1a, 0, kK0s), kK0s, kN1b, tmem + kD1b, nullptr); };
+    auto issue_l1a = [&]() { issue_layer<kK0s, kN1a>(a0_u, wc_u, tmem_u + kD1a, nullptr); };
+    auto issue_l1b = [&]() { issue_layer<kK0s, kN1b>(a0_u, wc_u + 2u * tile_offset(kN1a, 0, kK0s), tmem_u + kD1b, nullptr); };
     // one block of W (32 | 16 | 8) D1 columns starting at feature n0: relu(D1) * feat in bf16 -> A1 chunks (model.py:177-180)
     auto e1_block = [&](auto width, int n0, const __nv_bfloat16* feat) {
         constexpr int W = decltype(width)::value;
@@ -437,7 +468,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
-        if (tg == 0) { tc_fence_after(); issue_l1a(); issue_l1b(); umma_commit(&gs.bar_a); }
+        if (issuer) {
+            if (elect_one()) { tc_fence_after(); issue_l1a(); issue_l1b(); umma_commit(&gsu.bar_a); }
+            __syncwarp();
+        }
         n_tau = load_tau(tile + tile_step);
     }
 
@@ -445,6 +479,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         const long long env0 = tile * kEnvsPerTile;
         const bool has_next = tile + tile_step < n_tiles;    // group-uniform
         const bool dbg = debug != nullptr && blockIdx.x == 0 && g == 0 && tile == 0;
+        const long long it = (tile - ((long long)blockIdx.x * 2 + g)) / tile_step;
+        long long* stamps = (A.timing != nullptr && blockIdx.x == 0 && tg == 0 && it < kStampTiles) ? A.timing + (g * kStampTiles + it) * kStamps : nullptr;
+        auto stamp = [&](int k) { if (stamps != nullptr) stamps[k] = clock64(); };
+        stamp(0);
         if (tg >= kRows && tg < kRows + kEnvsPerTile * (kFeat / 8)) reinterpret_cast<uint4*>(gs.feat)[tg - kRows] = n_feat;
         n_feat = load_feat(tile + tile_step);                // prefetch the next tile's features: consumed one iteration later
         group_sync(g);
@@ -453,6 +491,7 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         mbar_wait(&gs.bar_a, phase_a);                       // every thread of the group sleeps on the MMA's mbarrier
         phase_a ^= 1;
         tc_fence_after();
+        stamp(1);
         {
             const __nv_bfloat16* feat = gs.feat + (row / kTaus) * kFeat;
             if (half == 0) {
@@ -470,18 +509,28 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- layer 2: D2[128 x 64] = A1 . W1^T; while it runs: A0 of the next tile and its layer 1a ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w1, kK1, kHid, tmem + kD2, &gs.bar_b); }
+        stamp(2);
+        if (issuer) {
+            if (elect_one()) { tc_fence_after(); issue_layer<kK1, kHid>(a1_u, w1_u, tmem_u + kD2, &gsu.bar_b); }
+            __syncwarp();
+        }
+        stamp(3);
         if (has_next) {                                      // (D1a and A0 of this tile were consumed: layer 1 completed above)
             produce_a0(n_tau);
             n_tau = load_tau(tile + 2 * tile_step);
             fence_async_smem();
             tc_fence_before();
             group_sync(g);
-            if (tg == 0) { tc_fence_after(); issue_l1a(); umma_commit(&gs.bar_a); }
+            if (issuer) {
+                if (elect_one()) { tc_fence_after(); issue_l1a(); umma_commit(&gsu.bar_a); }
+                __syncwarp();
+            }
         }
+        stamp(4);
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
         tc_fence_after();
+        stamp(5);
         {
             float v[32];
             const int col = half * 32;
@@ -497,10 +546,15 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         group_sync(g);
 
         // ---- layer 3: D3[128 x 64] = A2 . W2^T ----
-        if (tg == 0) { tc_fence_after(); issue_layer(gs.a1, s.w2, kK2, kHid, tmem + kD3, &gs.bar_b); }
+        stamp(6);
+        if (issuer) {
+            if (elect_one()) { tc_fence_after(); issue_layer<kK2, kHid>(a1_u, w2_u, tmem_u + kD3, &gsu.bar_b); }
+            __syncwarp();
+        }
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
         tc_fence_after();
+        stamp(7);
         {
             float v[32];
             const int col = half * 32;
@@ -517,15 +571,20 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
 
         // ---- output layer: D4[128 x 16] = A3 . W3^T (+ layer 1b of the next tile: its TMEM columns [0, 16) are free only now),
         //      then mean over the 32 taus of each env (one warp) + argmax ----
-        if (tg == 0) {
-            tc_fence_after();
-            issue_layer(gs.a1, s.w3, kK3, kN4, tmem + kD4, nullptr);
-            if (has_next) issue_l1b();
-            umma_commit(&gs.bar_b);
+        stamp(8);
+        if (issuer) {
+            if (elect_one()) {
+                tc_fence_after();
+                issue_layer<kK3, kN4>(a1_u, w3_u, tmem_u + kD4, nullptr);
+                if (has_next) issue_l1b();
+                umma_commit(&gsu.bar_b);
+            }
+            __syncwarp();
         }
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
         tc_fence_after();
+        stamp(9);
         if (half == 0) {
             float q[kN4];
             {
@@ -563,9 +622,11 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
             }
         }
         tc_fence_before();                                   // (the next tile's first barrier orders these TMEM reads before its MMAs)
+        stamp(10);
     }
 
     // ---- teardown ----
+    if (A.timing != nullptr && tg == 0 && blockIdx.x < 4) A.timing[2 * kStampTiles * kStamps + blockIdx.x * 4 + 2 + g] = clock64();    // lab: loop end
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -639,6 +700,7 @@ extern "C" int iqn_act_tc(const float* d_params, const void* d_packed_tc, const 
     if (d_qmean == nullptr && d_greedy == nullptr) { mnv_set_error("iqn_act_tc: no output"); return MNV_E_NULL; }
     ActArgs A{};
     A.taus = d_taus; A.cvar = d_cvar; A.cvar_scalar = cvar_scalar; A.qmean = d_qmean; A.greedy = d_greedy; A.debug = d_debug; A.B = B;
+    if (mnv_option(MNV_OPT_ACT_TIMING) && d_debug != nullptr) { A.timing = (long long*)d_debug; A.debug = nullptr; }   // lab: phase stamps instead of accumulators
     return launch_act(d_params, d_packed_tc, d_obs, nullptr, d_scratch, A, (cudaStream_t)stream, "iqn_act_tc");
 }
 

@@ -17,10 +17,10 @@ void mnv_set_error(const char* fmt, ...)
 }
 
 // tuning switches (mnv_set_option); MNV_TMA / MNV_PDL in the environment give the initial values
-static int g_opt[MNV_OPT_COUNT] = {-1, -1};
-static const char* const g_opt_name[MNV_OPT_COUNT] = {"tma", "pdl"};
-static const char* const g_opt_env[MNV_OPT_COUNT] = {"MNV_TMA", "MNV_PDL"};
-static const int g_opt_default[MNV_OPT_COUNT] = {0, 0};
+static int g_opt[MNV_OPT_COUNT] = {-1, -1, -1};
+static const char* const g_opt_name[MNV_OPT_COUNT] = {"tma", "pdl", "act_timing"};
+static const char* const g_opt_env[MNV_OPT_COUNT] = {"MNV_TMA", "MNV_PDL", "MNV_ACT_TIMING"};
+static const int g_opt_default[MNV_OPT_COUNT] = {0, 0, 0};
 
 int mnv_option(int which)
 {

@@ -9,7 +9,7 @@
 #define MNV_PI 3.14159265358979323846
 
 void mnv_set_error(const char* fmt, ...);
-enum { MNV_OPT_TMA = 0, MNV_OPT_PDL = 1, MNV_OPT_COUNT = 2 };
+enum { MNV_OPT_TMA = 0, MNV_OPT_PDL = 1, MNV_OPT_ACT_TIMING = 2, MNV_OPT_COUNT = 3 };
 int mnv_option(int which);     // tuning switches, see mnv_set_option
 
 #define MNV_CHECK_PTR(p)                                                            \
