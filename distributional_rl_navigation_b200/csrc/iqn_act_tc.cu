@@ -41,7 +41,8 @@ namespace {
 
 using namespace iqn;
 
-constexpr int kThreads = 512;            // two tile groups x 256 threads (8 warps: 4 TMEM lane quadrants x 2 column halves)
+constexpr int kComputeThreads = 512;     // two tile groups x 256 threads (8 warps: 4 TMEM lane quadrants x 2 column halves)
+constexpr int kThreads = kComputeThreads + 64;   // + one MMA-issuing warp per tile group (warps 16 and 17)
 constexpr int kGroupThreads = 256;
 constexpr int kRows = 128;              // rows per tile (UMMA M)
 constexpr int kTaus = 32;               // quantile samples per environment (ObsEncoder.K)
@@ -112,6 +113,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kGroupThreads) : "memory"); }
+// hand-off points between a group's 8 compute warps (arrive, never wait) and its MMA-issuing warp (sync): one named barrier
+// per point (0: A1 ready, 1: A0 of the next tile ready, 2: A2 ready, 3: A3 ready), 256 + 32 participants
+__device__ __forceinline__ void handoff_arrive(int g, int k) { asm volatile("bar.arrive %0, %1;" ::"r"(3 + 4 * g + k), "r"(kGroupThreads + 32) : "memory"); }
+__device__ __forceinline__ void handoff_wait(int g, int k) { asm volatile("bar.sync %0, %1;" ::"r"(3 + 4 * g + k), "r"(kGroupThreads + 32) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 {
@@ -341,14 +346,14 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int g = t >> 8, tg = t & 255;                      // tile group, thread index inside the group
+    // warp index made warp-uniform FOR THE COMPILER (a shuffle from lane 0, like cutlass::canonical_warp_idx_sync): the
+    // MMA-issuing warps address their operands through values derived from it, so the descriptors live in uniform registers
+    const int warp_u = __shfl_sync(0xffffffffu, t >> 5, 0);
+    const bool issuer = warp_u >= kComputeThreads / 32;       // warps 16, 17: MMA issue for tile group 0, 1 (one elected lane)
+    const int g_u = issuer ? warp_u - kComputeThreads / 32 : warp_u >> 3;
+    const int g = g_u, tg = issuer ? 256 + lane : (t & 255);  // tile group, thread index inside the group (issuer lanes: >= 256)
     const int half = (warp >> 2) & 1;                        // column half handled by this warp (warps q and q+4 share a lane quadrant)
     GroupSmem& gs = s.g[g];
-    // the same values made warp-uniform for the compiler (a shuffle from lane 0, like cutlass::canonical_warp_idx_sync):
-    // the MMA-issuing warp of each group addresses its operands through these
-    const int warp_u = __shfl_sync(0xffffffffu, t >> 5, 0);
-    const int g_u = warp_u >> 3;
-    const bool issuer = (warp_u & 7) == 0;                    // first warp of the group; one elected lane issues
     GroupSmem& gsu = s.g[g_u];
     if (A.timing != nullptr && tg == 0 && blockIdx.x < 4) A.timing[2 * kStampTiles * kStamps + blockIdx.x * 4 + g] = clock64();        // lab: kernel entry
 
@@ -463,15 +468,45 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
 
     float n_tau = load_tau(tile);
     uint4 n_feat = load_feat(tile);
-    if (tile < n_tiles) {                                     // prologue: layer 1 of this group's first tile
+    // ================= MMA-issuing warp of the group: waits at the hand-off points, one elected lane issues =================
+    // The tensor core takes an MMA from a thread only when the previous one has started, so the issuing thread is held for
+    // the whole execution time of a layer (~60 cycles per N = 64 K-step); a warp of its own keeps that off the compute warps.
+    if (issuer) {
+        const bool lead = elect_one();
+        if (tile < n_tiles) {
+            handoff_wait(g_u, 1);                            // A0 of the first tile
+            if (lead) { tc_fence_after(); issue_l1a(); issue_l1b(); umma_commit(&gsu.bar_a); }
+            __syncwarp();
+        }
+        for (; tile < n_tiles; tile += tile_step) {
+            const bool has_next = tile + tile_step < n_tiles;
+            handoff_wait(g_u, 0);                            // A1 ready, D1 drained
+            if (lead) { tc_fence_after(); issue_layer<kK1, kHid>(a1_u, w1_u, tmem_u + kD2, &gsu.bar_b); }
+            __syncwarp();
+            if (has_next) {
+                handoff_wait(g_u, 1);                        // A0 of the next tile ready (layer 1 of this tile completed long ago)
+                if (lead) { tc_fence_after(); issue_l1a(); umma_commit(&gsu.bar_a); }
+                __syncwarp();
+            }
+            handoff_wait(g_u, 2);                            // A2 ready, D2 drained
+            if (lead) { tc_fence_after(); issue_layer<kK2, kHid>(a1_u, w2_u, tmem_u + kD3, &gsu.bar_b); }
+            __syncwarp();
+            handoff_wait(g_u, 3);                            // A3 ready, D3 drained
+            if (lead) {
+                tc_fence_after();
+                issue_layer<kK3, kN4>(a1_u, w3_u, tmem_u + kD4, nullptr);
+                if (has_next) issue_l1b();                   // its 16 TMEM columns [0, 16) are free only now
+                umma_commit(&gsu.bar_b);
+            }
+            __syncwarp();
+        }
+    } else {
+    // ================= compute warps =================
+    if (tile < n_tiles) {                                     // prologue: A0 of this group's first tile
         produce_a0(n_tau);
         fence_async_smem();
         tc_fence_before();
-        group_sync(g);
-        if (issuer) {
-            if (elect_one()) { tc_fence_after(); issue_l1a(); issue_l1b(); umma_commit(&gsu.bar_a); }
-            __syncwarp();
-        }
+        handoff_arrive(g, 1);
         n_tau = load_tau(tile + tile_step);
     }
 
@@ -506,25 +541,17 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         }
         fence_async_smem();
         tc_fence_before();
-        group_sync(g);
+        handoff_arrive(g, 0);
 
-        // ---- layer 2: D2[128 x 64] = A1 . W1^T; while it runs: A0 of the next tile and its layer 1a ----
+        // ---- layer 2: D2[128 x 64] = A1 . W1^T (issuing warp); while it runs: A0 of the next tile, then its layer 1a ----
         stamp(2);
-        if (issuer) {
-            if (elect_one()) { tc_fence_after(); issue_layer<kK1, kHid>(a1_u, w1_u, tmem_u + kD2, &gsu.bar_b); }
-            __syncwarp();
-        }
         stamp(3);
         if (has_next) {                                      // (D1a and A0 of this tile were consumed: layer 1 completed above)
             produce_a0(n_tau);
             n_tau = load_tau(tile + 2 * tile_step);
             fence_async_smem();
             tc_fence_before();
-            group_sync(g);
-            if (issuer) {
-                if (elect_one()) { tc_fence_after(); issue_l1a(); umma_commit(&gsu.bar_a); }
-                __syncwarp();
-            }
+            handoff_arrive(g, 1);
         }
         stamp(4);
         mbar_wait(&gs.bar_b, phase_b);
@@ -543,14 +570,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         }
         fence_async_smem();
         tc_fence_before();
-        group_sync(g);
+        handoff_arrive(g, 2);
 
-        // ---- layer 3: D3[128 x 64] = A2 . W2^T ----
+        // ---- layer 3: D3[128 x 64] = A2 . W2^T (issuing warp) ----
         stamp(6);
-        if (issuer) {
-            if (elect_one()) { tc_fence_after(); issue_layer<kK2, kHid>(a1_u, w2_u, tmem_u + kD3, &gsu.bar_b); }
-            __syncwarp();
-        }
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
         tc_fence_after();
@@ -567,20 +590,11 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         }
         fence_async_smem();
         tc_fence_before();
-        group_sync(g);
+        handoff_arrive(g, 3);
 
-        // ---- output layer: D4[128 x 16] = A3 . W3^T (+ layer 1b of the next tile: its TMEM columns [0, 16) are free only now),
-        //      then mean over the 32 taus of each env (one warp) + argmax ----
+        // ---- output layer: D4[128 x 16] = A3 . W3^T (+ layer 1b of the next tile; issuing warp), then mean over the 32 taus of
+        //      each env (one warp) + argmax ----
         stamp(8);
-        if (issuer) {
-            if (elect_one()) {
-                tc_fence_after();
-                issue_layer<kK3, kN4>(a1_u, w3_u, tmem_u + kD4, nullptr);
-                if (has_next) issue_l1b();
-                umma_commit(&gsu.bar_b);
-            }
-            __syncwarp();
-        }
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
         tc_fence_after();
@@ -621,9 +635,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
                 }
             }
         }
-        tc_fence_before();                                   // (the next tile's first barrier orders these TMEM reads before its MMAs)
+        tc_fence_before();                                   // (the next hand-off orders these TMEM reads before the MMAs that overwrite them)
         stamp(10);
     }
+    }   // compute warps
 
     // ---- teardown ----
     if (A.timing != nullptr && tg == 0 && blockIdx.x < 4) A.timing[2 * kStampTiles * kStamps + blockIdx.x * 4 + 2 + g] = clock64();    // lab: loop end
