@@ -566,16 +566,17 @@ def iqn_bench(args, dev, world):
     env = VecMarineNavEnv(E, seed=12345 + E * (int(os.environ.get("RANK", 0))), device=dev, num_cores=N_CORES, num_obs=N_OBS,
                           min_start_goal_dis=30.0, num_beams=N_BEAMS)
     agent2 = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B, BUFFER_SIZE=4 * E)
-    n_roll = 41
-    agent2.learn_vec(total_timesteps=E * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E)
+    n_roll = 41                                                            # vector steps in the timed part (learn_vec's clock is GLOBAL transitions)
+    agent2.learn_vec(total_timesteps=E * world * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E * world)
     sync()
     t0 = time.perf_counter()
     start_ts = agent2.current_timestep
-    agent2.learn_vec(total_timesteps=start_ts + E * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E)
+    agent2.learn_vec(total_timesteps=start_ts + E * world * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E,
+                     target_update_interval=100 * E * world)
     sync()
     dt = time.perf_counter() - t0
     steps_done = agent2.current_timestep - start_ts
-    out["rollout_learn_env_steps_per_s"] = world * steps_done / dt
+    out["rollout_learn_env_steps_per_s"] = steps_done / dt                 # learn_vec counts GLOBAL transitions (E x world per vector step)
     out["rollout_learn_config"] = f"{E} envs/GPU, eps-greedy IQN act K=32 (tcgen05), fused env step + auto-reset, device replay, 1 update of {B} per vector step"
 
     if int(os.environ.get("RANK", 0)) == 0 and world == 1:

@@ -223,38 +223,24 @@ __device__ __forceinline__ bool elect_one()
 }
 
 // ---- pre-pass: everything that depends on the environment alone -------------------------------------------------------
-// ObsEncoder's three encoders (model.py:125-127,169-172; no activation), 128 environments per CTA.  lane = environment (its 26
-// observation values in registers); a warp owns 32 environments and HALF of the 13 groups of 16 features (group 0 = velocity
-// encoder, 1 = goal encoder, 2..12 = sensor encoder).  The weights sit in shared memory as [group][input][16 features], so the
-// 16 weights of one input are four broadcast 16-byte loads feeding eight packed FFMA2 (two features per instruction): one
-// shared-memory load per four FMAs instead of one per FMA, and half the FMA instructions.  Every feature is accumulated
-// bias-first in ascending input order (bit-identical to a scalar fmaf chain).  Output: bf16 [B][208]
-// rows, 32 contiguous bytes per (environment, group).  Optionally the adaptive CVaR level of IQNAgent.adjust_cvar
-// (agent.py:249-267): closest sonar return / 10 if closer than 10 m, else 1; a beam with |x|, |y| < 1e-3 is "no return".
-constexpr int kEncEnvs = 128, kEncThreads = 256, kEncGroups = kFeat / 16;     // 13 groups of 16 features
+// ObsEncoder's three encoders (model.py:125-127,169-172; no activation), 128 environments per CTA of 4 warps.  A lane owns TWO
+// environments (their 26 observation values in registers); a warp owns 64 environments and HALF of the 13 groups of 16
+// features (group 0 = velocity encoder, 1 = goal encoder, 2..12 = sensor encoder).  The weights sit in shared memory as
+// [group][input][16 features]: the 16 weights of one input are four broadcast 16-byte loads feeding sixteen packed FFMA2 (two
+// features per instruction, two environments per load).  A broadcast 16-byte load still moves 512 bytes into the register
+// file (4 cycles of the shared-memory pipe), so with one environment per lane the kernel was bound by that pipe (ncu: l1tex
+// 79 %, mio_throttle the top stall); two environments per lane put it back on the FMA pipe.  Every feature is accumulated
+// bias-first in ascending input order (bit-identical to a scalar fmaf chain).  Output: bf16 [B][208] rows, 32 contiguous
+// bytes per (environment, group).  Optionally the adaptive CVaR level of IQNAgent.adjust_cvar (agent.py:249-267): closest
+// sonar return / 10 if closer than 10 m, else 1; a beam with |x|, |y| < 1e-3 is "no return".
+constexpr int kEncEnvs = 128, kEncThreads = 128, kEncGroups = kFeat / 16;     // 13 groups of 16 features
 constexpr int kEncSensorIn = kObs - 4;                                        // 22 sonar inputs
 // shared-memory weight layout: group g < 2: [2 inputs][16] then bias [16]; sensor group: [22 inputs][16] then bias [16]
 constexpr int kEncSmallFloats = (2 + 1) * 16, kEncSensorFloats = (kEncSensorIn + 1) * 16;
 constexpr int kEncWFloats = 2 * kEncSmallFloats + (kEncGroups - 2) * kEncSensorFloats;     // 4 144: every encoder parameter once
 
-template <int NIN>
-__device__ __forceinline__ void enc_group(const float* __restrict__ wg, const float* x, __nv_bfloat16* __restrict__ out)
+__device__ __forceinline__ void enc_store16(const float2 (&acc)[8], __nv_bfloat16* __restrict__ out)
 {
-    float2 acc[8];
-    const float4* b4 = reinterpret_cast<const float4*>(wg + NIN * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { const float4 b = b4[q]; acc[2 * q] = make_float2(b.x, b.y); acc[2 * q + 1] = make_float2(b.z, b.w); }
-#pragma unroll
-    for (int k = 0; k < NIN; ++k) {
-        const float4* w4 = reinterpret_cast<const float4*>(wg + k * 16);
-        const float2 xx = make_float2(x[k], x[k]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 w = w4[q];
-            acc[2 * q] = __ffma2_rn(make_float2(w.x, w.y), xx, acc[2 * q]);
-            acc[2 * q + 1] = __ffma2_rn(make_float2(w.z, w.w), xx, acc[2 * q + 1]);
-        }
-    }
     uint4 u0, u1;
     auto pk = [](float2 v) { __nv_bfloat162 p = __floats2bfloat162_rn(v.x, v.y); return *reinterpret_cast<uint32_t*>(&p); };
     u0.x = pk(acc[0]); u0.y = pk(acc[1]); u0.z = pk(acc[2]); u0.w = pk(acc[3]);
@@ -263,7 +249,36 @@ __device__ __forceinline__ void enc_group(const float* __restrict__ wg, const fl
     reinterpret_cast<uint4*>(out)[1] = u1;
 }
 
-__global__ void __launch_bounds__(kEncThreads)
+// one group of 16 features for the lane's two environments (xa, xb: their inputs; outa / outb may be null for a missing env)
+template <int NIN>
+__device__ __forceinline__ void enc_group(const float* __restrict__ wg, const float* xa, const float* xb,
+                                          __nv_bfloat16* __restrict__ outa, __nv_bfloat16* __restrict__ outb)
+{
+    float2 acca[8], accb[8];
+    const float4* b4 = reinterpret_cast<const float4*>(wg + NIN * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b = b4[q];
+        acca[2 * q] = make_float2(b.x, b.y); acca[2 * q + 1] = make_float2(b.z, b.w);
+        accb[2 * q] = acca[2 * q]; accb[2 * q + 1] = acca[2 * q + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) {
+        const float4* w4 = reinterpret_cast<const float4*>(wg + k * 16);
+        const float2 xxa = make_float2(xa[k], xa[k]), xxb = make_float2(xb[k], xb[k]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 w = w4[q];
+            const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+            acca[2 * q] = __ffma2_rn(w01, xxa, acca[2 * q]); acca[2 * q + 1] = __ffma2_rn(w23, xxa, acca[2 * q + 1]);
+            accb[2 * q] = __ffma2_rn(w01, xxb, accb[2 * q]); accb[2 * q + 1] = __ffma2_rn(w23, xxb, accb[2 * q + 1]);
+        }
+    }
+    if (outa != nullptr) enc_store16(acca, outa);
+    if (outb != nullptr) enc_store16(accb, outb);
+}
+
+__global__ void __launch_bounds__(kEncThreads, 4)         // 4 CTAs per SM: the 512 CTAs of a 65 536-env batch are ONE wave
 iqn_encode_kernel(const float* __restrict__ P, const float* __restrict__ obs, __nv_bfloat16* __restrict__ feat,
                   float* __restrict__ cvar_out, long long B)
 {
@@ -290,30 +305,39 @@ iqn_encode_kernel(const float* __restrict__ P, const float* __restrict__ obs, __
         s_w[i] = v;
     }
     __syncthreads();
-    const int el = (w & 3) * 32 + lane;                                  // environment of this lane inside the CTA
-    if (el >= n_env) return;
-    float x[kObs];
+    // warp w: environments [64 (w & 1), 64 (w & 1) + 64) of the CTA (lane: el and el + 32), feature half w >> 1
+    const int ela = (w & 1) * 64 + lane, elb = ela + 32;
+    const bool has_a = ela < n_env, has_b = elb < n_env;
+    float xa[kObs], xb[kObs];
 #pragma unroll
-    for (int k = 0; k < kObs; ++k) x[k] = s_x[el * kObs + k];
-    __nv_bfloat16* out = feat + (e0 + el) * kFeat;
-    if ((w >> 2) == 0) {                                                  // warp-uniform: groups 0..6
-        enc_group<2>(s_w, x, out);
-        enc_group<2>(s_w + kEncSmallFloats, x + 2, out + 16);
+    for (int k = 0; k < kObs; ++k) { xa[k] = has_a ? s_x[ela * kObs + k] : 0.f; xb[k] = has_b ? s_x[elb * kObs + k] : 0.f; }
+    __nv_bfloat16* outa = has_a ? feat + (e0 + ela) * kFeat : nullptr;
+    __nv_bfloat16* outb = has_b ? feat + (e0 + elb) * kFeat : nullptr;
+    auto at = [](__nv_bfloat16* p, int off) { return p != nullptr ? p + off : nullptr; };
+    if ((w >> 1) == 0) {                                                  // warp-uniform: groups 0..6
+        enc_group<2>(s_w, xa, xb, outa, outb);
+        enc_group<2>(s_w + kEncSmallFloats, xa + 2, xb + 2, at(outa, 16), at(outb, 16));
 #pragma unroll 1
-        for (int g = 2; g < 7; ++g) enc_group<kEncSensorIn>(s_w + 2 * kEncSmallFloats + (g - 2) * kEncSensorFloats, x + 4, out + g * 16);
+        for (int g = 2; g < 7; ++g)
+            enc_group<kEncSensorIn>(s_w + 2 * kEncSmallFloats + (g - 2) * kEncSensorFloats, xa + 4, xb + 4, at(outa, g * 16), at(outb, g * 16));
         if (cvar_out != nullptr) {
-            float closest = INFINITY;
+            auto level = [](const float* x) {
+                float closest = INFINITY;
 #pragma unroll
-            for (int b = 0; b < kEncSensorIn / 2; ++b) {
-                const float px = x[4 + 2 * b], py = x[5 + 2 * b];
-                if (fabsf(px) < 1e-3f && fabsf(py) < 1e-3f) continue;     // agent.py:256-258
-                closest = fminf(closest, sqrtf(px * px + py * py));
-            }
-            cvar_out[e0 + el] = closest < 10.0f ? closest / 10.0f : 1.0f;   // agent.py:262-265 (sonar range 10 m)
+                for (int b = 0; b < kEncSensorIn / 2; ++b) {
+                    const float px = x[4 + 2 * b], py = x[5 + 2 * b];
+                    if (fabsf(px) < 1e-3f && fabsf(py) < 1e-3f) continue;     // agent.py:256-258
+                    closest = fminf(closest, sqrtf(px * px + py * py));
+                }
+                return closest < 10.0f ? closest / 10.0f : 1.0f;               // agent.py:262-265 (sonar range 10 m)
+            };
+            if (has_a) cvar_out[e0 + ela] = level(xa);
+            if (has_b) cvar_out[e0 + elb] = level(xb);
         }
     } else {                                                              // groups 7..12
 #pragma unroll 1
-        for (int g = 7; g < kEncGroups; ++g) enc_group<kEncSensorIn>(s_w + 2 * kEncSmallFloats + (g - 2) * kEncSensorFloats, x + 4, out + g * 16);
+        for (int g = 7; g < kEncGroups; ++g)
+            enc_group<kEncSensorIn>(s_w + 2 * kEncSmallFloats + (g - 2) * kEncSensorFloats, xa + 4, xb + 4, at(outa, g * 16), at(outb, g * 16));
     }
 }
 
