@@ -232,7 +232,7 @@ __device__ __forceinline__ void tile_mm_staged(Smem& s, const float* __restrict_
 // In: s.x (8 x 28, zero padded), s.tau (already multiplied by cvar); half 0 of PT's WcT ALREADY requested into s.w.
 // Out: s.feat, s.cos, s.c, s.h1, s.h2, s.q.  P: flat parameters (torch layout); PT: packed transposes (iqn_pack).
 // After the last staged GEMM the first half of `next` ([next_red][next_n]) is requested (the following pass's first matrix).
-__device__ void forward_tile(Smem& s, const float* __restrict__ P, const float* __restrict__ PT, int n_tau,
+__device__ __noinline__ void forward_tile(Smem& s, const float* __restrict__ P, const float* __restrict__ PT, int n_tau,
                              const float* __restrict__ next, int next_red, int next_n)
 {
     const int t = threadIdx.x;
