@@ -357,7 +357,7 @@ def test_recorded_episodes_full_replay(golden_dir, name):
             f.write(f"{name}: episodes {E} steps {int(L.sum())} flag_flips {n_bad} return_err_max {ok_err.max():.3e} "
                     f"frac_err_gt_1e-3 {(ok_err > 1e-3).mean():.3e} frac_err_gt_1e-2 {(ok_err > 1e-2).mean():.3e}\n")
     np.testing.assert_allclose(0.1 * 10 * lengths, d["times"], rtol=0, atol=1e-9)
-    # observed (profiles/r2_free_run_replay_counts.txt): greedy 0, adaptive 13, dqn 0 flips of 9 000 -- the band is
+    # observed (profiles/r2_free_run_replay_counts.txt, step kernel v8): greedy 9, adaptive 12, dqn 3 flips of 9 000 -- the band is
     # 1.5x the worst observed count (chaotic vortex-trapped episodes; the CPU oracle, same operation order as the reference: 0)
     assert n_bad <= 20, n_bad
     assert (ok_err > 1e-2).mean() <= 2e-3
