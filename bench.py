@@ -531,6 +531,7 @@ def iqn_bench(args, dev, world):
                             "(tile-partial sum" + (", one-shot all-reduce of the 35785-float gradient over peer memory (NVLink)" if world > 1 and peer else "")
                             + ", clip_grad_norm_, Adam, kernel-side weight copies)") if agent.fused_tail and (world == 1 or peer) else \
                            (f"batch {B} per GPU, N=N'=8, 3xTF32 mma.sync; loss_grad + " + ("NCCL all-reduce(35785 f32) + " if world > 1 else "") + "clip_adam")
+    out["update_tail_error_word"] = agent._tail.error() if agent._tail is not None else None
     out["update_gradient_exchange"] = "none (1 GPU)" if world == 1 else ("peer-memory one-shot all-reduce inside iqn_update_tail" if peer else "NCCL all_reduce")
     out["update_tflops_fp32"] = IQN_FLOP_PER_SAMPLE * B / (ms * 1e-3) / 1e12
     out["samples_per_s_all_gpus"] = world * B * 1e3 / ms

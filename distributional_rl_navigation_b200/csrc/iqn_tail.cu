@@ -32,7 +32,8 @@ constexpr int kMaxWorld = 8;
 constexpr size_t kFlagsOffset = 2 * (size_t)kSlotFloats * sizeof(float);           // [2 slots][35 840] f32 | flags u64 [8][160]
 constexpr int kFlagStride = 160;
 constexpr size_t kXchgBytes = kFlagsOffset + (size_t)kMaxWorld * kFlagStride * sizeof(unsigned long long);
-constexpr size_t kSyncBytes = 1024;                             // u64 epoch | u64 arrivals | pad to 64 B | f32 ss_part[160]
+constexpr size_t kSyncBytes = 1024;                             // u64 epoch | u64 arrivals | u64 error | pad to 64 B | f32 ss_part[160]
+constexpr unsigned long long kSpinLimit = 1ull << 24;           // x >= 64 ns sleeps: seconds, far beyond any legitimate wait
 
 struct TailPeers {
     float* buf[kMaxWorld];                                      // exchange buffer of every rank (own one included), peer-mapped
@@ -120,7 +121,12 @@ iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict_
             unsigned long long* theirs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer) + kFlagsOffset);
             st_release_sys(theirs + peers.rank * kFlagStride + blk, epoch + 1ull);
             const unsigned long long* own = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(mine) + kFlagsOffset);
-            while (ld_acquire_sys(own + t * kFlagStride + blk) < epoch + 1ull) { }
+            // bounded spin (~2 s): a peer that never launches (a rank died) must not hang this GPU; the error word is sticky
+            unsigned long long spins = 0;
+            while (ld_acquire_sys(own + t * kFlagStride + blk) < epoch + 1ull) {
+                if (++spins > kSpinLimit) { atomicExch(reinterpret_cast<unsigned long long*>(sync) + 2, 1ull); break; }
+                if (spins > 4096) __nanosleep(64);
+            }
         }
         __syncthreads();
         if (q == 0) {
@@ -153,7 +159,11 @@ iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict_
             __threadfence();
             atomicAdd(sync + 1, 1ull);
             const unsigned long long target = (epoch + 1ull) * (unsigned long long)gridDim.x;
-            while (ld_acquire_gpu(sync + 1) < target) { }
+            unsigned long long spins = 0;
+            while (ld_acquire_gpu(sync + 1) < target) {
+                if (++spins > kSpinLimit) { atomicExch(sync + 2, 2ull); break; }
+                if (spins > 4096) __nanosleep(64);
+            }
         }
         __syncthreads();
         // every CTA adds the per-CTA partials in the same order: 160 slots (zero beyond gridDim.x) over five warps, then 5 adds

@@ -178,6 +178,11 @@ class UpdateTail:
                                          int(step), _stream())
         _lib.check(rc, "iqn_update_tail")
 
+    def error(self):
+        """0, or the sticky error word of the kernel: 1 = a peer's slice never arrived, 2 = the grid barrier timed out (both after
+        seconds of spinning; the update that hit it is garbage).  Host-synchronising read: call it outside hot loops."""
+        return int(self.sync[16:24].view(torch.int64).item())
+
     def close(self):
         L = _lib.load()
         if self._own is not None:

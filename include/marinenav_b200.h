@@ -228,7 +228,9 @@ int     iqn_clip_adam(float* d_params, const float* d_grad, float* d_m, float* d
  * system-scope release stores, and sums the peers' slices in rank order (bit-identical replicas; gradient = mean over ranks)
  * -- then clip_grad_norm_(max_norm) + Adam.step + refresh of d_packed / d_packed_tc like iqn_clip_adam.  Outputs d_loss,
  * d_grad (the averaged unclipped gradient) and d_grad_norm are optional.
- *   d_sync: iqn_tail_sync_bytes() bytes, zeroed ONCE by the caller, then owned by the kernels (grid-barrier epochs);
+ *   d_sync: iqn_tail_sync_bytes() bytes, zeroed ONCE by the caller, then owned by the kernels (u64[0] completed launches,
+ *   u64[1] grid-barrier arrivals, u64[2] sticky error word: 1 = a peer's slice never arrived, 2 = grid barrier timed out --
+ *   both only after seconds of spinning, so that a dead rank cannot hang the surviving GPUs);
  *   peer_xchg: HOST array of `world` device pointers, entry r = rank r's exchange buffer (iqn_xchg_bytes() bytes each, zeroed
  *   once) as mapped into THIS process -- own entry from iqn_xchg_alloc, the others from iqn_xchg_open on the 64-byte handles
  *   the ranks exchange once at start-up (CUDA IPC; same node).  NULL / world == 1: single GPU.  Every rank must issue the

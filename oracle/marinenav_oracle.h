@@ -8,7 +8,7 @@
  * written from the algorithm description in SURVEY.md section 8(a) (quirks Q1..Q10), with every
  * function citing the reference file:line it follows.
  *
- * PARITY PINNED: tests/test_oracle_pinning.py checks this restatement against
+ * PARITY PINNED: tests/test_oracle_golden.py checks this restatement against
  *   (1) the reference itself imported in-process (teacher-forced step/observation/reset parity),
  *   (2) the reference's own golden vectors: pretrained_models/IQN/seed_3/eval_config.json (reset KAT,
  *       bit-for-bit) and the 27 000 recorded evaluation episodes (tests/golden/episodes_*.npz),

@@ -183,3 +183,4 @@ def test_update_tail_matches_three_launch_path(weights, B):
     iqn_ops.pack_tc(b["flat"], fresh)
     assert torch.equal(b["ptc"], fresh)
     assert int(tail.sync[:8].view(torch.int64).item()) == 3          # three launches completed (device-side epoch)
+    assert tail.error() == 0
