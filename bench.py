@@ -253,14 +253,33 @@ def run_b200(args):
     while (reps * K) % N_BATCHES != 0 and reps < 4096:
         reps += 1
     n_launch = reps * K
-    graph = torch.cuda.CUDAGraph()
+    # The env batches are independent, so the launches alternate between N_STREAMS capture streams (launch i -> stream
+    # i % N_STREAMS, batch i % N_BATCHES: a batch always stays on one stream, so its own steps remain ordered): every stream
+    # is a chain of programmatic dependent launches, and the CTAs of the next launch fill the SM slots a draining launch
+    # frees instead of idling at the grid dependency of a one-wave kernel.  `timing.single_stream` reports the same graph
+    # captured on ONE stream beside it.
+    n_streams = max(1, args.streams)
+    assert N_BATCHES % n_streams == 0, "--streams must divide the number of rotating batches"
     side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(n_launch):
-                one_step(W + i)
-    torch.cuda.current_stream().wait_stream(side)
+    lanes = [side] + [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
+
+    def capture(n_lanes):
+        gr = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(gr, stream=side):
+                for s_ in lanes[1:n_lanes]:
+                    s_.wait_stream(side)
+                for i in range(n_launch):
+                    with torch.cuda.stream(lanes[i % n_lanes]):
+                        one_step(W + i)
+                for s_ in lanes[1:n_lanes]:
+                    side.wait_stream(s_)
+        torch.cuda.current_stream().wait_stream(side)
+        return gr
+
+    graph = capture(n_streams)
+    graph_1s = capture(1) if n_streams > 1 else None
     stream = torch.cuda.current_stream()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     graph.replay(); torch.cuda.synchronize()
@@ -297,6 +316,15 @@ def run_b200(args):
         barrier()
         per_replay = sorted(evs[r].elapsed_time(evs[r + 1]) for r in range(n_replay))
         ms_region = evs[0].elapsed_time(evs[n_replay])
+        ms_1s = None
+        if graph_1s is not None:                     # the single-stream period of the same launches (reported, not the value)
+            graph_1s.replay(); torch.cuda.synchronize()
+            e1s = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            e1s[0].record(stream)
+            for r in range(5):
+                graph_1s.replay(); e1s[r + 1].record(stream)
+            barrier()
+            ms_1s = sorted(e1s[r].elapsed_time(e1s[r + 1]) for r in range(5))[2] / n_launch
     ms_median = per_replay[len(per_replay) // 2]
     t = torch.tensor([ms_median / n_launch, ms_region / (n_launch * n_replay)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -387,12 +415,16 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "timing": {"launch": f"timed region = {n_replay} replays of ONE CUDA graph of {n_launch} mnv_step launches ({reps} x steps={K}), "
-                                 f"no eager launches; an event after every replay; ms_per_step = median replay / {n_launch}; "
+                                 f"no eager launches; the launches alternate between {n_streams} stream(s) (independent env batches, "
+                                 f"a batch stays on one stream); an event after every replay; ms_per_step = median replay / {n_launch}; "
                                  f"launch mode pdl={'2 (per call)' if params_pdl(params) else _lib.get_option('pdl')} "
                                  "(programmatic dependent launch, map tables fetched ahead of the grid dependency)",
                        "timed_region_ms": round(ms_region, 4), "ms_per_step_mean": ms_per_step_mean,
                        "ms_per_step_min": per_replay[0] / n_launch, "ms_per_step_max": per_replay[-1] / n_launch,
-                       "mix_steps": args.mix},
+                       "mix_steps": args.mix, "streams": n_streams,
+                       "single_stream": None if ms_1s is None else {
+                           "ms_per_step": ms_1s, "roofline_frac": E * abytes / (ms_1s * 1e-3) / 1e9 / peak,
+                           "what": "the same graph captured on ONE stream (every launch behind the grid dependency of the one before)"}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E == ENVS_PER_GPU else None,
                          "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
@@ -618,6 +650,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--streams", type=int, default=2, help="streams the rotating env batches' step launches alternate between (1, 2, 4 or 8)")
     ap.add_argument("--no-iqn", action="store_true", help="skip the IQN legs")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-map leg")
     ap.add_argument("--mix", type=int, default=200, help="auto-reset steps per env batch between the preload and the timed region")

@@ -26,7 +26,7 @@ def set_opts(spec):
         assert rc == 0, (k, v, rc)
 
 
-def period_us(E, steps, n_c=4, n_o=8, n_b=11, dev="cuda:0", n_sub=None, drift=False):
+def period_us(E, steps, n_c=4, n_o=8, n_b=11, dev="cuda:0", n_sub=None, drift=False, n_streams=1):
     per_env = 490 if n_b == 11 else 1490
     nb = max(2, min(8, int(300e6 // (E * per_env)) + 1))
     batches = []
@@ -50,10 +50,19 @@ def period_us(E, steps, n_c=4, n_o=8, n_b=11, dev="cuda:0", n_sub=None, drift=Fa
     graph = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
+    extra = [torch.cuda.Stream() for _ in range(n_streams - 1)]
     with torch.cuda.stream(side):
         with torch.cuda.graph(graph, stream=side):
+            # n_streams > 1: launch i goes to stream i % n_streams (the batches are independent), so that the CTAs of the
+            # next launch fill the SM slots the draining launch frees instead of waiting at the grid dependency
+            for s_ in extra:
+                s_.wait_stream(side)
+            lanes = [side] + extra
             for i in range(chunk):
-                one(i)
+                with torch.cuda.stream(lanes[i % n_streams]):
+                    one(i)
+            for s_ in extra:
+                side.wait_stream(s_)
     torch.cuda.current_stream().wait_stream(side)
     reps = max(1, steps // chunk)
     if drift:
@@ -119,6 +128,7 @@ def main():
     ap.add_argument("--dense", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--drift", action="store_true")
+    ap.add_argument("--streams", default="1", help="comma list: launches distributed round-robin over this many streams")
     ap.add_argument("--shape", default="", help="';'-separated 'n_sub,n_beams' overrides (timing only)")
     a = ap.parse_args()
     for spec in a.opts.split(";"):
@@ -132,10 +142,10 @@ def main():
             for E in [int(x) for x in a.envs.split(",")]:
                 us, nb = period_us(E, a.steps, 4, 32 if a.dense else 8, nbm, n_sub=ns)
                 print(f"   shape n_sub={ns} n_beams={nbm} E={E:7d} period={us:8.2f} us", flush=True)
-        for E in [int(x) for x in a.envs.split(",")]:
-            us, nb = period_us(E, a.steps, *((4, 32, 64) if a.dense else (4, 8, 11)), drift=a.drift)
+        for E, ns_ in [(int(x), int(y)) for x in a.envs.split(",") for y in a.streams.split(",")]:
+            us, nb = period_us(E, a.steps, *((4, 32, 64) if a.dense else (4, 8, 11)), drift=a.drift, n_streams=ns_)
             per = 1490 if a.dense else 490
-            print(f"   E={E:7d} batches={nb} period={us:8.2f} us  {E / us / 1e3:7.3f} G steps/s  {E * per / us / 1e3 / 6532.5 * 100:5.1f}% HBM", flush=True)
+            print(f"   E={E:7d} streams={ns_} batches={nb} period={us:8.2f} us  {E / us / 1e3:7.3f} G steps/s  {E * per / us / 1e3 / 6532.5 * 100:5.1f}% HBM", flush=True)
 
 
 if __name__ == "__main__":
