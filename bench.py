@@ -480,10 +480,17 @@ def dense_leg(args, dev, world, rank):
     graph = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())
+    n_streams = max(1, args.streams)                 # independent batches alternate between the capture streams (see run_b200)
+    lanes = [side] + [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
     with torch.cuda.stream(side):
         with torch.cuda.graph(graph, stream=side):
+            for s_ in lanes[1:]:
+                s_.wait_stream(side)
             for i in range(64):
-                env_ops.step(batches[i % nb].buf, params, action=actions[i])
+                with torch.cuda.stream(lanes[i % n_streams]):
+                    env_ops.step(batches[i % nb].buf, params, action=actions[i])
+            for s_ in lanes[1:]:
+                side.wait_stream(s_)
     torch.cuda.current_stream().wait_stream(side)
     graph.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -501,7 +508,7 @@ def dense_leg(args, dev, world, rank):
     inst = 23.30e6          # smsp__inst_executed.sum of one launch, profiles/r2_dense_kernel_v4_ncu_full.csv
     floor_us = inst / (148 * 4) / 1.965e3
     return {"workload": "dense map: 32 obstacles, 64 sonar beams, 16384 envs/GPU (BASELINE configs[4] per-GPU shard), mnv_env_dense_kernel",
-            "ms_per_step": ms, "env_steps_per_s": world * E / (ms * 1e-3), "algorithmic_bytes_per_env_step": ab,
+            "ms_per_step": ms, "env_steps_per_s": world * E / (ms * 1e-3), "streams": n_streams, "algorithmic_bytes_per_env_step": ab,
             "hbm_roofline_frac": E * ab / (ms * 1e-3) / 1e9 / peak, "bound": "issue (2048 ray-circle pairs per env-step), not HBM",
             "issue_bound": {"warp_instructions_per_launch": inst, "floor_us_at_1_ipc_per_scheduler": floor_us, "frac": floor_us / (ms * 1e3),
                             "note": "second roofline (SURVEY 8d): ncu smsp__inst_executed.sum of one launch / (592 schedulers x 1.965 GHz) / measured time"}}
@@ -598,19 +605,27 @@ def iqn_bench(args, dev, world):
     # rollout + learn (BASELINE configs[2]): act -> env step (+auto-reset) -> replay append -> 1 update of 1024 per vector step
     env = VecMarineNavEnv(E, seed=12345 + E * (int(os.environ.get("RANK", 0))), device=dev, num_cores=N_CORES, num_obs=N_OBS,
                           min_start_goal_dis=30.0, num_beams=N_BEAMS)
-    agent2 = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B, BUFFER_SIZE=4 * E)
     n_roll = 41                                                            # vector steps in the timed part (learn_vec's clock is GLOBAL transitions)
-    agent2.learn_vec(total_timesteps=E * world * 2, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E * world)
-    sync()
-    t0 = time.perf_counter()
-    start_ts = agent2.current_timestep
-    agent2.learn_vec(total_timesteps=start_ts + E * world * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E,
-                     target_update_interval=100 * E * world)
-    sync()
-    dt = time.perf_counter() - t0
-    steps_done = agent2.current_timestep - start_ts
-    out["rollout_learn_env_steps_per_s"] = steps_done / dt                 # learn_vec counts GLOBAL transitions (E x world per vector step)
-    out["rollout_learn_config"] = f"{E} envs/GPU, eps-greedy IQN act K=32 (tcgen05), fused env step + auto-reset, device replay, 1 update of {B} per vector step"
+    for mode, tag in ((True, ""), (False, "_eager")):
+        # graph=True: the vector step replayed as ONE CUDA graph (device control block for eps / counters / ring position);
+        # graph=False: the same work launched from Python, ~12 launches per vector step (reported beside it)
+        agent2 = IQNAgent(26, 9, seed=0, device=dev, BATCH_SIZE=B, BUFFER_SIZE=4 * E)
+        n_warm = 6 if mode else 2
+        agent2.learn_vec(total_timesteps=E * world * n_warm, train_env=env, batch_size=B, learning_starts=E, target_update_interval=100 * E * world,
+                         graph=mode)
+        sync()
+        t0 = time.perf_counter()
+        start_ts = agent2.current_timestep
+        agent2.learn_vec(total_timesteps=start_ts + E * world * (n_roll - 1), train_env=env, batch_size=B, learning_starts=E,
+                         target_update_interval=100 * E * world, graph=mode)
+        sync()
+        dt = time.perf_counter() - t0
+        steps_done = agent2.current_timestep - start_ts
+        out["rollout_learn" + tag + "_env_steps_per_s"] = steps_done / dt  # learn_vec counts GLOBAL transitions (E x world per vector step)
+        out["rollout_learn" + tag + "_updates"] = agent2.optimizer.step_count
+        del agent2
+    out["rollout_learn_config"] = (f"{E} envs/GPU, eps-greedy IQN act K=32 (tcgen05), fused env step + auto-reset, device replay, 1 update of {B} per "
+                                   "vector step; the vector step is ONE CUDA graph (learn_vec(graph=True)); `_eager` = launched from Python")
 
     if int(os.environ.get("RANK", 0)) == 0 and world == 1:
         # CPU baseline for the update: the numpy oracle (port of IQNAgent.train) on the host

@@ -36,6 +36,15 @@ class MnvResetParams(C.Structure):
     ]
 
 
+class MnvVstepCtl(C.Structure):
+    """mnv_vstep_ctl: what changes between two replays of a captured rollout + learn vector step (64 bytes)."""
+    _fields_ = [
+        ("act_eps", C.c_float), ("adam_step_size", C.c_float), ("adam_inv_sqrt_bc2", C.c_float), ("reserved", C.c_int32),
+        ("act_step", C.c_uint64), ("rpl_pos", C.c_int64), ("rpl_t", C.c_int64), ("rpl_head", C.c_int64), ("rpl_size", C.c_int64),
+        ("rpl_call", C.c_uint64),
+    ]
+
+
 class MarinenavError(RuntimeError):
     pass
 
@@ -79,6 +88,11 @@ _SIGNATURES = {
     "iqn_act_scratch_bytes": (C.c_int64, [_i64]),
     "iqn_act_tc": (C.c_int, [_vp] * 5 + [C.c_float] + [_vp] * 4 + [_i64, _i32, _vp]),
     "iqn_act_tc_sample": (C.c_int, [_vp] * 3 + [_i32, _vp, C.c_float, C.c_float, C.c_uint64, C.c_uint64] + [_vp] * 4 + [_i64, _vp]),
+    "rpl_append_ctl": (C.c_int, [_vp] * 5 + [_i64] + [_vp] * 5 + [_i64, _i32, _i32, C.c_double] + [_vp] * 5),
+    "rpl_sample_ctl": (C.c_int, [_vp] * 5 + [_i64, C.c_uint64, _i32] + [_vp] * 6 + [_i64, _i32, _vp, _vp]),
+    "iqn_update_tail_ctl": (C.c_int, [_vp] * 6 + [_i64] + [_vp] * 4 + [C.POINTER(C.c_void_p), _i32, _i32] + [C.c_float] * 4 + [_vp, _vp]),
+    "iqn_act_tc_sample_ctl": (C.c_int, [_vp] * 3 + [_i32, _vp, C.c_float, C.c_uint64] + [_vp] * 4 + [_i64, _vp, _vp]),
+    "iqn_draw_taus": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _vp, _vp]),
 }
 
 _lib = None

@@ -67,6 +67,8 @@ struct __align__(128) Smem {
     __nv_bfloat16 wc[kFeat * kK0s], w1[kW1El], w2[kW2El], w3[kW3El];
     GroupSmem g[2];
     uint32_t tmem_base;
+    float dyn_eps;                                       // eps / Philox step of this launch: by-value arguments, or (graph replays)
+    unsigned long long dyn_step;                         // the device control block -- read once, kept out of the register budget
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -345,6 +347,7 @@ struct ActArgs {
     const __nv_bfloat16* Wp; const __nv_bfloat16* feat; const float* taus; const float* cvar; float cvar_scalar;
     float* qmean; int32_t* greedy; int32_t* action; float* debug; long long B;
     unsigned long long seed, step; float eps; int sample;             // sample != 0: taus / epsilon-greedy from Philox(seed, step)
+    const mnv_vstep_ctl* ctl;                                         // != nullptr: eps / step from the device control block
     long long* timing;                                                // lab ("act_timing" option): clock64 stamps of CTA 0's phases
 };
 constexpr int kStamps = 12, kStampTiles = 64;
@@ -352,9 +355,9 @@ constexpr int kStamps = 12, kStampTiles = 64;
 // Random streams of the sampling mode, all from Philox4x32-10 keyed by `seed`, counter = (env, sub-stream, step):
 //   sub-stream 0..7: the 32 taus of the environment (4 per draw, torch.rand-style 24-bit uniforms, model.py:149)
 //   sub-stream 8:    .x -> the epsilon-greedy coin (greedy iff u > eps, agent.py:200), .y -> the random action (:203)
-__device__ __forceinline__ philox::u4 act_draw(const ActArgs& A, long long env, unsigned sub)
+__device__ __forceinline__ philox::u4 act_draw(const ActArgs& A, unsigned long long step, long long env, unsigned sub)
 {
-    return philox::philox4x32_10(philox::u4{(uint32_t)env, (uint32_t)((unsigned long long)env >> 32) ^ (sub << 24), (uint32_t)A.step, (uint32_t)(A.step >> 32)},
+    return philox::philox4x32_10(philox::u4{(uint32_t)env, (uint32_t)((unsigned long long)env >> 32) ^ (sub << 24), (uint32_t)step, (uint32_t)(step >> 32)},
                                   (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
 }
 
@@ -408,6 +411,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tg == 32) { mbar_init(&gs.bar_a, 1); mbar_init(&gs.bar_b, 1); }
+    if (t == 64) {
+        s.dyn_eps = A.ctl != nullptr ? A.ctl->act_eps : A.eps;
+        s.dyn_step = A.ctl != nullptr ? A.ctl->act_step : A.step;
+    }
     fence_async_smem();
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tc_fence_before();
@@ -435,7 +442,7 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         const int k = row % kTaus;
         float u;
         if (A.sample) {
-            const philox::u4 r = act_draw(A, b, (unsigned)(k >> 2));
+            const philox::u4 r = act_draw(A, s.dyn_step, b, (unsigned)(k >> 2));
             const uint32_t rk = (k & 3) == 0 ? r.x : ((k & 3) == 1 ? r.y : ((k & 3) == 2 ? r.z : r.w));
             u = philox::u01(rk);
         } else u = taus[b * kTaus + k];
@@ -651,9 +658,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
                 if (greedy != nullptr) greedy[b] = best;
                 if (A.action != nullptr) {                                                  // agent.py:200-203
                     int act = best;
-                    if (A.sample && A.eps > 0.f) {
-                        const philox::u4 r = act_draw(A, b, 8u);
-                        if (!(philox::u01(r.x) > A.eps)) act = (int)__umulhi(r.y, (uint32_t)kAct);
+                    const float eps = s.dyn_eps;
+                    if (A.sample && eps > 0.f) {
+                        const philox::u4 r = act_draw(A, s.dyn_step, b, 8u);
+                        if (!(philox::u01(r.x) > eps)) act = (int)__umulhi(r.y, (uint32_t)kAct);
                     }
                     A.action[b] = act;
                 }
@@ -755,4 +763,19 @@ extern "C" int iqn_act_tc_sample(const float* d_params, const void* d_packed_tc,
     A.cvar = adaptive_cvar ? d_cvar : nullptr; A.cvar_scalar = cvar_scalar; A.qmean = d_qmean; A.greedy = d_greedy; A.action = d_action; A.B = B;
     A.seed = seed; A.step = step; A.eps = eps; A.sample = 1;
     return launch_act(d_params, d_packed_tc, d_obs, adaptive_cvar ? d_cvar : nullptr, d_scratch, A, (cudaStream_t)stream, "iqn_act_tc_sample");
+}
+
+extern "C" int iqn_act_tc_sample_ctl(const float* d_params, const void* d_packed_tc, const float* d_obs, int32_t adaptive_cvar,
+                                     float* d_cvar, float cvar_scalar, uint64_t seed, int32_t* d_action, int32_t* d_greedy,
+                                     float* d_qmean, void* d_scratch, int64_t B, const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    if (B <= 0) { mnv_set_error("iqn_act_tc_sample_ctl: B must be > 0"); return MNV_E_SIZE; }
+    MNV_CHECK_PTR(d_params); MNV_CHECK_PTR(d_packed_tc); MNV_CHECK_PTR(d_obs); MNV_CHECK_PTR(d_scratch);
+    if (d_ctl == nullptr) { mnv_set_error("iqn_act_tc_sample_ctl: null control block"); return MNV_E_NULL; }
+    if (d_action == nullptr) { mnv_set_error("iqn_act_tc_sample_ctl: null action output"); return MNV_E_NULL; }
+    if (adaptive_cvar && d_cvar == nullptr) { mnv_set_error("iqn_act_tc_sample_ctl: adaptive CVaR needs the d_cvar buffer"); return MNV_E_NULL; }
+    ActArgs A{};
+    A.cvar = adaptive_cvar ? d_cvar : nullptr; A.cvar_scalar = cvar_scalar; A.qmean = d_qmean; A.greedy = d_greedy; A.action = d_action; A.B = B;
+    A.seed = seed; A.sample = 1; A.ctl = d_ctl;
+    return launch_act(d_params, d_packed_tc, d_obs, adaptive_cvar ? d_cvar : nullptr, d_scratch, A, (cudaStream_t)stream, "iqn_act_tc_sample_ctl");
 }

@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kTailThreads, 1)
 iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict__ v, float* __restrict__ PT,
                 __nv_bfloat16* __restrict__ Wtc, const float* __restrict__ gpart, const float* __restrict__ loss_part, int n_tiles,
                 float* __restrict__ loss, float* __restrict__ grad_out, float* __restrict__ grad_norm,
-                unsigned long long* __restrict__ sync, const __grid_constant__ TailPeers peers, const __grid_constant__ TailHyper H)
+                unsigned long long* __restrict__ sync, const __grid_constant__ TailPeers peers, const __grid_constant__ TailHyper H,
+                const mnv_vstep_ctl* __restrict__ ctl)
 {
     __shared__ float s_part[kGroups][kSlice];
     __shared__ float s_red[32];
@@ -190,8 +191,11 @@ iqn_tail_kernel(float* __restrict__ P, float* __restrict__ m, float* __restrict_
         const float mi = H.beta1 * m[i] + (1.f - H.beta1) * gi;
         const float vi = H.beta2 * v[i] + (1.f - H.beta2) * gi * gi;
         m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) * H.inv_sqrt_bc2 + H.eps;
-        const float pn = P[i] - H.step_size * (mi / denom);
+        // graph replays: Adam's bias corrections (host-computed per step, like H's) come from the control block
+        const float inv_sqrt_bc2 = ctl != nullptr ? ctl->adam_inv_sqrt_bc2 : H.inv_sqrt_bc2;
+        const float step_size = ctl != nullptr ? ctl->adam_step_size : H.step_size;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + H.eps;
+        const float pn = P[i] - step_size * (mi / denom);
         P[i] = pn;
         int pt, tc;
         packed_slots(i, pt, tc);
@@ -242,10 +246,10 @@ extern "C" int iqn_xchg_free(void* d_ptr)
     return 0;
 }
 
-extern "C" int iqn_update_tail(float* d_params, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
-                               const float* d_scratch, int64_t B, float* d_loss, float* d_grad, float* d_grad_norm,
-                               void* d_sync, void* const* peer_xchg, int32_t rank, int32_t world,
-                               float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, void* stream)
+static int tail_impl(float* d_params, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
+                     const float* d_scratch, int64_t B, float* d_loss, float* d_grad, float* d_grad_norm,
+                     void* d_sync, void* const* peer_xchg, int32_t rank, int32_t world,
+                     float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, const mnv_vstep_ctl* d_ctl, void* stream)
 {
     if (B <= 0) { mnv_set_error("iqn_update_tail: B must be > 0"); return MNV_E_SIZE; }
     if (step < 1) { mnv_set_error("iqn_update_tail: step must be >= 1"); return MNV_E_PARAM; }
@@ -278,6 +282,25 @@ extern "C" int iqn_update_tail(float* d_params, float* d_m, float* d_v, float* d
     attr[0].val.programmaticStreamSerializationAllowed = 1;           // griddepcontrol.wait until its partials are complete
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, iqn_tail_kernel, d_params, d_m, d_v, d_packed, (__nv_bfloat16*)d_packed_tc, gpart, lpart, (int)tiles,
-                       d_loss, d_grad, d_grad_norm, (unsigned long long*)d_sync, peers, H);
+                       d_loss, d_grad, d_grad_norm, (unsigned long long*)d_sync, peers, H, d_ctl);
     return mnv_launch_status("iqn_update_tail");
+}
+
+extern "C" int iqn_update_tail(float* d_params, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
+                               const float* d_scratch, int64_t B, float* d_loss, float* d_grad, float* d_grad_norm,
+                               void* d_sync, void* const* peer_xchg, int32_t rank, int32_t world,
+                               float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, void* stream)
+{
+    return tail_impl(d_params, d_m, d_v, d_packed, d_packed_tc, d_scratch, B, d_loss, d_grad, d_grad_norm, d_sync, peer_xchg, rank, world,
+                     max_norm, lr, beta1, beta2, eps, step, nullptr, stream);
+}
+
+extern "C" int iqn_update_tail_ctl(float* d_params, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
+                                   const float* d_scratch, int64_t B, float* d_loss, float* d_grad, float* d_grad_norm,
+                                   void* d_sync, void* const* peer_xchg, int32_t rank, int32_t world,
+                                   float max_norm, float beta1, float beta2, float eps, const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    if (d_ctl == nullptr) { mnv_set_error("iqn_update_tail_ctl: null control block"); return MNV_E_NULL; }
+    return tail_impl(d_params, d_m, d_v, d_packed, d_packed_tc, d_scratch, B, d_loss, d_grad, d_grad_norm, d_sync, peer_xchg, rank, world,
+                     max_norm, 0.f, beta1, beta2, eps, 1, d_ctl, stream);
 }

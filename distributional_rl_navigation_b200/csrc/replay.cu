@@ -35,8 +35,10 @@ __global__ void __launch_bounds__(kWarps * 32)
 rpl_append_kernel(Ring R, long long pos, const float* __restrict__ obs, const int32_t* __restrict__ action,
                   const float* __restrict__ reward, const float* __restrict__ next_obs, const uint8_t* __restrict__ done,
                   long long E, int row_len, int n_step, double gamma, long long t,
-                  float* __restrict__ win_obs, int32_t* __restrict__ win_action, float* __restrict__ win_reward)
+                  float* __restrict__ win_obs, int32_t* __restrict__ win_action, float* __restrict__ win_reward,
+                  const mnv_vstep_ctl* __restrict__ ctl)
 {
+    if (ctl != nullptr) { pos = ctl->rpl_pos; t = ctl->rpl_t; }       // graph replays: the ring position lives in device memory
     const int lane = threadIdx.x & 31;
     const long long e = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (e >= E) return;
@@ -90,8 +92,9 @@ __device__ __forceinline__ long long draw_index(unsigned long long seed, unsigne
 
 __global__ void __launch_bounds__(kDrawThreads)
 rpl_draw_kernel(long long* __restrict__ picks, long long B, long long size, unsigned long long seed, unsigned long long call,
-                int without_replacement)
+                int without_replacement, const mnv_vstep_ctl* __restrict__ ctl)
 {
+    if (ctl != nullptr) { size = ctl->rpl_size; call = ctl->rpl_call; }
     extern __shared__ long long s_pick[];                              // [B]
     __shared__ int s_changed;
     unsigned round_of[kMaxPicksPerThread];
@@ -131,8 +134,10 @@ rpl_draw_kernel(long long* __restrict__ picks, long long B, long long size, unsi
 __global__ void __launch_bounds__(kWarps * 32)
 rpl_gather_kernel(Ring R, long long head, long long size, const long long* __restrict__ picks,
                   float* __restrict__ o_states, int64_t* __restrict__ o_actions, float* __restrict__ o_rewards,
-                  float* __restrict__ o_next, float* __restrict__ o_dones, long long B, int row_len)
+                  float* __restrict__ o_next, float* __restrict__ o_dones, long long B, int row_len,
+                  const mnv_vstep_ctl* __restrict__ ctl)
 {
+    if (ctl != nullptr) { head = ctl->rpl_head; size = ctl->rpl_size; }
     const int lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -142,6 +147,22 @@ rpl_gather_kernel(Ring R, long long head, long long size, const long long* __res
     copy_row(o_states + b * row_len, R.states + slot * row_len, row_len, lane);
     copy_row(o_next + b * row_len, R.next_states + slot * row_len, row_len, lane);
     if (lane == 0) { o_actions[b] = R.actions[slot]; o_rewards[b] = R.rewards[slot]; o_dones[b] = R.dones[slot]; }
+}
+
+// The 2 x B x 8 quantile samples of one update (target taus first, Q9): 4 uniforms per Philox draw.
+__global__ void __launch_bounds__(256)
+iqn_draw_taus_kernel(float* __restrict__ taus, long long n, unsigned long long seed, unsigned long long call,
+                     const mnv_vstep_ctl* __restrict__ ctl)
+{
+    if (ctl != nullptr) call = ctl->rpl_call;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // draw q covers taus[4 q .. 4 q + 3]
+    if (4 * q >= n) return;
+    const unsigned long long key = seed ^ 0x7A75ull;
+    const philox::u4 r = philox::philox4x32_10(philox::u4{(uint32_t)q, 0x7Au ^ (uint32_t)((unsigned long long)q >> 32 << 8), (uint32_t)call, (uint32_t)(call >> 32)},
+                                                (uint32_t)key, (uint32_t)(key >> 32));
+    const float u[4] = {philox::u01(r.x), philox::u01(r.y), philox::u01(r.z), philox::u01(r.w)};
+    for (int k = 0; k < 4; ++k)
+        if (4 * q + k < n) taus[4 * q + k] = u[k];
 }
 
 int check_ring(const char* fn, const float* s, const int64_t* a, const float* r, const float* n, const float* d, int64_t cap, int32_t row_len)
@@ -154,10 +175,10 @@ int check_ring(const char* fn, const float* s, const int64_t* a, const float* r,
 
 }  // namespace
 
-extern "C" int rpl_append(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
-                          int64_t capacity, int64_t pos, const float* d_obs, const int32_t* d_action, const float* d_reward,
-                          const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
-                          int64_t t, float* d_win_obs, int32_t* d_win_action, float* d_win_reward, void* stream)
+static int append_impl(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
+                       int64_t capacity, int64_t pos, const float* d_obs, const int32_t* d_action, const float* d_reward,
+                       const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
+                       int64_t t, float* d_win_obs, int32_t* d_win_action, float* d_win_reward, const mnv_vstep_ctl* d_ctl, void* stream)
 {
     int rc = check_ring("rpl_append", d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, row_len);
     if (rc) return rc;
@@ -168,8 +189,43 @@ extern "C" int rpl_append(float* d_states, int64_t* d_actions, float* d_rewards,
     Ring R{d_states, d_actions, d_rewards, d_next_states, d_dones, capacity};
     const unsigned grid = (unsigned)((E + kWarps - 1) / kWarps);
     rpl_append_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(R, pos, d_obs, d_action, d_reward, d_next_obs, d_done, E, row_len,
-                                                                      n_step, gamma, t, d_win_obs, d_win_action, d_win_reward);
+                                                                      n_step, gamma, t, d_win_obs, d_win_action, d_win_reward, d_ctl);
     return mnv_launch_status("rpl_append");
+}
+
+extern "C" int rpl_append(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
+                          int64_t capacity, int64_t pos, const float* d_obs, const int32_t* d_action, const float* d_reward,
+                          const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
+                          int64_t t, float* d_win_obs, int32_t* d_win_action, float* d_win_reward, void* stream)
+{
+    return append_impl(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, pos, d_obs, d_action, d_reward, d_next_obs,
+                       d_done, E, row_len, n_step, gamma, t, d_win_obs, d_win_action, d_win_reward, nullptr, stream);
+}
+
+extern "C" int rpl_append_ctl(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
+                              int64_t capacity, const float* d_obs, const int32_t* d_action, const float* d_reward,
+                              const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
+                              float* d_win_obs, int32_t* d_win_action, float* d_win_reward, const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    if (d_ctl == nullptr) { mnv_set_error("rpl_append_ctl: null control block"); return MNV_E_NULL; }
+    return append_impl(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, 0, d_obs, d_action, d_reward, d_next_obs,
+                       d_done, E, row_len, n_step, gamma, 0, d_win_obs, d_win_action, d_win_reward, d_ctl, stream);
+}
+
+static int gather_impl(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
+                       const float* d_dones, int64_t capacity, int64_t head, int64_t size, const int64_t* d_indices,
+                       float* d_out_states, int64_t* d_out_actions, float* d_out_rewards, float* d_out_next_states,
+                       float* d_out_dones, int64_t B, int32_t row_len, const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    int rc = check_ring("rpl_gather", d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, row_len);
+    if (rc) return rc;
+    if (d_indices == nullptr || d_out_states == nullptr || d_out_actions == nullptr || d_out_rewards == nullptr || d_out_next_states == nullptr || d_out_dones == nullptr) { mnv_set_error("rpl_gather: null pointer"); return MNV_E_NULL; }
+    if (B <= 0 || (d_ctl == nullptr && (size <= 0 || size > capacity || head < 0 || head >= capacity))) { mnv_set_error("rpl_gather: bad B / size / head"); return MNV_E_SIZE; }
+    Ring R{const_cast<float*>(d_states), const_cast<int64_t*>(d_actions), const_cast<float*>(d_rewards), const_cast<float*>(d_next_states), const_cast<float*>(d_dones), capacity};
+    const unsigned grid = (unsigned)((B + kWarps - 1) / kWarps);
+    rpl_gather_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(R, head, size, reinterpret_cast<const long long*>(d_indices), d_out_states, d_out_actions,
+                                                                      d_out_rewards, d_out_next_states, d_out_dones, B, row_len, d_ctl);
+    return mnv_launch_status("rpl_gather");
 }
 
 extern "C" int rpl_gather(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
@@ -177,15 +233,29 @@ extern "C" int rpl_gather(const float* d_states, const int64_t* d_actions, const
                           float* d_out_states, int64_t* d_out_actions, float* d_out_rewards, float* d_out_next_states,
                           float* d_out_dones, int64_t B, int32_t row_len, void* stream)
 {
-    int rc = check_ring("rpl_gather", d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, row_len);
+    return gather_impl(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, head, size, d_indices, d_out_states,
+                       d_out_actions, d_out_rewards, d_out_next_states, d_out_dones, B, row_len, nullptr, stream);
+}
+
+static int sample_impl(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
+                       const float* d_dones, int64_t capacity, int64_t head, int64_t size, uint64_t seed, uint64_t call,
+                       int32_t without_replacement, int64_t* d_indices, float* d_out_states, int64_t* d_out_actions,
+                       float* d_out_rewards, float* d_out_next_states, float* d_out_dones, int64_t B, int32_t row_len,
+                       const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    if (d_indices == nullptr) { mnv_set_error("rpl_sample: null index buffer"); return MNV_E_NULL; }
+    if (B <= 0 || B > (int64_t)kDrawThreads * kMaxPicksPerThread) { mnv_set_error("rpl_sample: B=%lld outside [1, %d]", (long long)B, kDrawThreads * kMaxPicksPerThread); return MNV_E_SIZE; }
+    if (d_ctl == nullptr && (size <= 0 || (without_replacement && B > size))) { mnv_set_error("rpl_sample: %lld picks from %lld stored transitions", (long long)B, (long long)size); return MNV_E_SIZE; }
+    const size_t smem = (size_t)B * sizeof(long long);
+    if (smem > 48 * 1024) {
+        cudaError_t a = cudaFuncSetAttribute(rpl_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (a != cudaSuccess) { mnv_set_error("rpl_sample: cudaFuncSetAttribute: %s", cudaGetErrorString(a)); return (int)a; }
+    }
+    rpl_draw_kernel<<<1, kDrawThreads, smem, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(d_indices), B, size, seed, call, without_replacement, d_ctl);
+    int rc = mnv_launch_status("rpl_sample(draw)");
     if (rc) return rc;
-    if (d_indices == nullptr || d_out_states == nullptr || d_out_actions == nullptr || d_out_rewards == nullptr || d_out_next_states == nullptr || d_out_dones == nullptr) { mnv_set_error("rpl_gather: null pointer"); return MNV_E_NULL; }
-    if (B <= 0 || size <= 0 || size > capacity || head < 0 || head >= capacity) { mnv_set_error("rpl_gather: bad B / size / head"); return MNV_E_SIZE; }
-    Ring R{const_cast<float*>(d_states), const_cast<int64_t*>(d_actions), const_cast<float*>(d_rewards), const_cast<float*>(d_next_states), const_cast<float*>(d_dones), capacity};
-    const unsigned grid = (unsigned)((B + kWarps - 1) / kWarps);
-    rpl_gather_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(R, head, size, reinterpret_cast<const long long*>(d_indices), d_out_states, d_out_actions,
-                                                                      d_out_rewards, d_out_next_states, d_out_dones, B, row_len);
-    return mnv_launch_status("rpl_gather");
+    return gather_impl(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, head, size, d_indices, d_out_states, d_out_actions,
+                       d_out_rewards, d_out_next_states, d_out_dones, B, row_len, d_ctl, stream);
 }
 
 extern "C" int rpl_sample(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
@@ -193,17 +263,25 @@ extern "C" int rpl_sample(const float* d_states, const int64_t* d_actions, const
                           int32_t without_replacement, int64_t* d_indices, float* d_out_states, int64_t* d_out_actions,
                           float* d_out_rewards, float* d_out_next_states, float* d_out_dones, int64_t B, int32_t row_len, void* stream)
 {
-    if (d_indices == nullptr) { mnv_set_error("rpl_sample: null index buffer"); return MNV_E_NULL; }
-    if (B <= 0 || B > (int64_t)kDrawThreads * kMaxPicksPerThread) { mnv_set_error("rpl_sample: B=%lld outside [1, %d]", (long long)B, kDrawThreads * kMaxPicksPerThread); return MNV_E_SIZE; }
-    if (size <= 0 || (without_replacement && B > size)) { mnv_set_error("rpl_sample: %lld picks from %lld stored transitions", (long long)B, (long long)size); return MNV_E_SIZE; }
-    const size_t smem = (size_t)B * sizeof(long long);
-    if (smem > 48 * 1024) {
-        cudaError_t a = cudaFuncSetAttribute(rpl_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (a != cudaSuccess) { mnv_set_error("rpl_sample: cudaFuncSetAttribute: %s", cudaGetErrorString(a)); return (int)a; }
-    }
-    rpl_draw_kernel<<<1, kDrawThreads, smem, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(d_indices), B, size, seed, call, without_replacement);
-    int rc = mnv_launch_status("rpl_sample(draw)");
-    if (rc) return rc;
-    return rpl_gather(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, head, size, d_indices, d_out_states, d_out_actions,
-                      d_out_rewards, d_out_next_states, d_out_dones, B, row_len, stream);
+    return sample_impl(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, head, size, seed, call, without_replacement,
+                       d_indices, d_out_states, d_out_actions, d_out_rewards, d_out_next_states, d_out_dones, B, row_len, nullptr, stream);
+}
+
+extern "C" int rpl_sample_ctl(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
+                              const float* d_dones, int64_t capacity, uint64_t seed, int32_t without_replacement, int64_t* d_indices,
+                              float* d_out_states, int64_t* d_out_actions, float* d_out_rewards, float* d_out_next_states,
+                              float* d_out_dones, int64_t B, int32_t row_len, const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    if (d_ctl == nullptr) { mnv_set_error("rpl_sample_ctl: null control block"); return MNV_E_NULL; }
+    return sample_impl(d_states, d_actions, d_rewards, d_next_states, d_dones, capacity, 0, 0, seed, 0, without_replacement,
+                       d_indices, d_out_states, d_out_actions, d_out_rewards, d_out_next_states, d_out_dones, B, row_len, d_ctl, stream);
+}
+
+extern "C" int iqn_draw_taus(float* d_taus, int64_t n, uint64_t seed, uint64_t call, const mnv_vstep_ctl* d_ctl, void* stream)
+{
+    if (d_taus == nullptr) { mnv_set_error("iqn_draw_taus: null output"); return MNV_E_NULL; }
+    if (n <= 0) { mnv_set_error("iqn_draw_taus: n must be > 0"); return MNV_E_SIZE; }
+    const long long draws = (n + 3) / 4;
+    iqn_draw_taus_kernel<<<(unsigned)((draws + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_taus, n, seed, call, d_ctl);
+    return mnv_launch_status("iqn_draw_taus");
 }

@@ -15,7 +15,7 @@ import warnings
 import numpy as np
 import torch
 
-from . import _lib, distributed as mdist, iqn_ops
+from . import _lib, distributed as mdist, env_ops, iqn_ops
 from .iqn_model import ObsEncoder
 from .replay_buffer import DeviceReplayBuffer, ReplayBuffer
 
@@ -225,7 +225,7 @@ class IQNAgent:
         self._update(experiences, taus)
         return self._loss
 
-    def _update(self, experiences, taus):
+    def _update(self, experiences, taus, ctl=None):
         """loss.backward() ... optimizer.step() (agent.py:296-300) in two launches: the fused per-tile kernel (iqn_loss_partials)
         and the fused tail (iqn_update_tail: fixed-order sum of the tile partials, one-shot all-reduce of the gradient over peer
         memory when torch.distributed is initialised, clip_grad_norm_ 0.5, Adam, refresh of the kernel-side weight copies).
@@ -241,6 +241,17 @@ class IQNAgent:
             self._tail = iqn_ops.UpdateTail(self.device)
             if self._tail.peer_error is not None:
                 warnings.warn("IQNAgent: peer-memory gradient exchange unavailable (%s); using torch.distributed all_reduce" % self._tail.peer_error)
+        if ctl is not None:
+            # CUDA-graph replays (learn_vec(graph=True)): Adam's bias corrections come from the device control block and the
+            # caller advances opt.step_count per replay
+            if not (self.fused_tail and self._tail.world == mdist.world_size()):
+                raise _lib.MarinenavError("the captured update needs the fused tail (iqn_update_tail) on every rank")
+            iqn_ops.loss_partials(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus[0], taus[1],
+                                  gamma_n, self._scratch)
+            self._tail.step(L.flat, opt.m, opt.v, L.packed, L.packed_tc, self._scratch, B, 1, loss=self._loss,
+                            grad=self._grad if self.keep_grad else None, grad_norm=self._grad_norm, max_norm=0.5,
+                            beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps, ctl=ctl)
+            return
         if self.fused_tail and self._tail.world == mdist.world_size():
             iqn_ops.loss_partials(L.flat, L.packed, T.flat, T.packed, states, actions, rewards, next_states, dones, taus[0], taus[1],
                                   gamma_n, self._scratch)
@@ -394,7 +405,7 @@ class IQNAgent:
 
     def learn_vec(self, total_timesteps, train_env, eval_config=None, eval_freq=None, eval_log_path=None, batch_size=None,
                   updates_per_step=1, learning_starts=None, target_update_interval=None, buffer_size=None, verbose=False,
-                  on_step=None, sample_without_replacement=False, policy_lag=1):
+                  on_step=None, sample_without_replacement=False, policy_lag=1, graph=False):
         """Vectorised counterpart of learn(): E transitions per env.step, device replay buffer, `updates_per_step` IQN
         updates of `batch_size` per vector step once `learning_starts` transitions were collected.
 
@@ -412,7 +423,15 @@ class IQNAgent:
         snapshot (encoder weights + bf16 tensor-core tiles, two alternating buffers) the learner stream leaves behind after
         every vector step -- so that act(t) never waits for an update in flight and the learner runs entirely beside the
         env stream (act -> step -> reset).  Two vector steps of lag are far inside what the replay buffer's off-policy data
-        already tolerates.  policy_lag=0: act waits for the latest weights, like the reference's loop."""
+        already tolerates.  policy_lag=0: act waits for the latest weights, like the reference's loop.
+
+        graph=True: the whole vector step is ONE CUDA graph (two alternating captures), replayed with a 64-byte device control
+        block for what changes from step to step -- see _learn_vec_pipelined.  graph="eager" launches the same pipelined
+        sequence without capturing it (the parity reference of the graph path)."""
+        if graph:
+            return self._learn_vec_pipelined(total_timesteps, train_env, eval_config, eval_freq, eval_log_path, batch_size,
+                                             updates_per_step, learning_starts, target_update_interval, buffer_size, verbose, on_step,
+                                             sample_without_replacement, capture=(graph != "eager"))
         E = train_env.num_envs
         world = mdist.world_size()
         if world > 1:                                           # every rank must run the same number of all-reduces
@@ -511,4 +530,171 @@ class IQNAgent:
             if on_step is not None:
                 on_step(self)
         env_stream.wait_stream(learn_stream)
+        return [float(x.item()) for x in losses[::max(1, len(losses) // 200)]] if verbose else losses
+
+    # ---- the vector step as one CUDA graph ---------------------------------------------------------------------------------
+    def _learn_vec_pipelined(self, total_timesteps, train_env, eval_config, eval_freq, eval_log_path, batch_size, updates_per_step,
+                             learning_starts, target_update_interval, buffer_size, verbose, on_step, sample_without_replacement,
+                             capture=True):
+        """learn_vec with the vector step captured ONCE as a CUDA graph and replayed (a vector step is ~12 launches of 5 - 250 us:
+        launch-bound from Python).  One replay =
+
+            env branch:      control block H2D -> act (encode + tcgen05 kernel) -> fused env step -> replay append -> obs <- next_obs
+                             -> masked reset -> masked re-observe
+            learner branch:  (forked behind the control-block copy) sample -> taus -> loss/backward -> fused tail (all-reduce over
+                             peer memory, clip, Adam) -> weight snapshot for the NEXT step's act; joins at the end.
+
+        The learner of step k samples the ring as it was BEFORE step k's append (the append waits for the gather, so a full ring
+        is never overwritten under it) and runs entirely beside act(k); act(k) reads the snapshot the learner of step k-1 left
+        (two alternating snapshots = two alternating captures).  What changes between replays -- eps, the Philox counters, the
+        ring position, Adam's bias corrections -- lives in mnv_vstep_ctl blocks in device memory (include/marinenav_b200.h); the
+        host fills a pinned copy before every replay (at most two steps ahead of the GPU).  Differences to the eager loop: the
+        update of a step does not see that step's own transitions, learning starts one vector step later, and with several
+        updates per vector step the target network is synchronised at the end of the step in which the interval was crossed.
+        capture=False launches the identical sequence eagerly."""
+        import ctypes as C
+        E, dev = train_env.num_envs, self.device
+        world = mdist.world_size()
+        if world > 1:
+            lo_hi = torch.tensor([E, -E], dtype=torch.int64, device=dev)
+            torch.distributed.all_reduce(lo_hi, op=torch.distributed.ReduceOp.MIN)
+            if int(lo_hi[0]) != E or int(-lo_hi[1]) != E:
+                raise ValueError("learn_vec: every rank needs the same number of environments")
+        train_env.global_step_multiplier = world
+        B = batch_size or self.BATCH_SIZE
+        if updates_per_step == "reference":
+            updates_per_step = self.reference_updates_per_step(E * world, B)
+        U = int(updates_per_step)
+        learning_starts = self.learning_starts if learning_starts is None else learning_starts
+        target_update_interval = self.target_update_interval if target_update_interval is None else target_update_interval
+        if self.device_memory is None:
+            self.device_memory = DeviceReplayBuffer(buffer_size or self.BUFFER_SIZE, B, dev, seed=self.seed, gamma=self.GAMMA,
+                                                    n_step=self.n_step, num_envs=E)
+        mem = self.device_memory
+        if mem.n_step != self.n_step:
+            raise ValueError("learn_vec: the device replay buffer was built for n_step=%d, the agent uses %d" % (mem.n_step, self.n_step))
+        steps_per_update = (E * world) / float(U)
+        net, opt = self.qnetwork_local, self.optimizer
+        n_enc = iqn_ops.N_ENCODER_PARAMS
+        if self.fused_tail and self._tail is None:
+            self._tail = iqn_ops.UpdateTail(dev)
+        if not (self.fused_tail and self._tail.world == world):
+            raise _lib.MarinenavError("learn_vec(graph=True) needs the fused update tail on every rank; use graph=False")
+        st = getattr(self, "_pipe", None)
+        if st is None or st["key"] != (id(train_env), E, B, U):
+            with torch.cuda.device(dev):
+                pin = torch.zeros(2, U, C.sizeof(_lib.MnvVstepCtl), dtype=torch.uint8).pin_memory()
+                st = self._pipe = dict(
+                    key=(id(train_env), E, B, U), pin=pin,
+                    host=[(_lib.MnvVstepCtl * U).from_buffer(pin[k].numpy()) for k in range(2)],
+                    ctl=torch.zeros(2, U, C.sizeof(_lib.MnvVstepCtl), dtype=torch.uint8, device=dev),
+                    taus=torch.zeros(2, U, 2, B, 8, dtype=torch.float32, device=dev),
+                    action=torch.zeros(E, dtype=torch.int32, device=dev),
+                    snaps=[(net.flat[:n_enc].clone(), net.packed_tc.clone()) for _ in range(2)],
+                    done=[torch.cuda.Event(), torch.cuda.Event()], graphs={}, seen={}, vstep=0,
+                    side=torch.cuda.Stream(device=dev), learner=torch.cuda.Stream(device=dev))
+                need = iqn_ops.train_scratch_floats(B)
+                if self._scratch is None or self._scratch.numel() < need:
+                    self._scratch = torch.empty(need, dtype=torch.float32, device=dev)
+                iqn_ops._scratch_for(E, dev)
+        else:
+            for k in range(2):                                    # the weights may have changed since the last call (load_model, eager updates)
+                st["snaps"][k][0].copy_(net.flat[:n_enc]); st["snaps"][k][1].copy_(net.packed_tc)
+        b = train_env.buf
+        train_env.reset()
+        losses, next_eval = [], 0
+        seed_act, seed_tau = int(self.seed) + 0x5EED0000, int(self.seed) + 0x7A050000
+        ev_gathered = torch.cuda.Event()
+
+        def launch(par, update, p, rp, env_stream, learn_stream):
+            """The launches of one vector step (captured, or issued eagerly): `env_stream` is the current stream."""
+            ctl0 = st["ctl"][par].data_ptr()
+            st["ctl"][par].copy_(st["pin"][par], non_blocking=True)
+            learn_stream.wait_stream(env_stream)
+            if update:
+                with torch.cuda.stream(learn_stream):
+                    for u in range(U):
+                        cu = ctl0 + u * C.sizeof(_lib.MnvVstepCtl)
+                        batch = mem.sample(B, without_replacement=sample_without_replacement, ctl=cu, advance=False)
+                        taus = iqn_ops.draw_taus(st["taus"][par, u], seed_tau, ctl=cu)
+                        if u == U - 1:
+                            ev_gathered.record(learn_stream)
+                        self._update(batch, (taus[0], taus[1]), ctl=cu)
+                    nxt = st["snaps"][par ^ 1]                    # act of the NEXT step reads it (after the join)
+                    nxt[0].copy_(net.flat[:n_enc]); nxt[1].copy_(net.packed_tc)
+            w_flat, w_tc = st["snaps"][par]
+            iqn_ops.act_tc_sample(w_flat, w_tc, b["obs"], 0.0, seed_act, 0, action=st["action"], ctl=ctl0)
+            env_ops.step(b, p, action=st["action"], obs=b["next_obs"])
+            if update:
+                env_stream.wait_event(ev_gathered)                # a full ring: the append must not overwrite rows still being gathered
+            mem.add_batch(b["obs"], st["action"], b["reward"], b["next_obs"], b["done"], ctl=ctl0, advance=False)
+            b["obs"].copy_(b["next_obs"])
+            env_ops.reset(b, train_env.rng_key, train_env.rng_pos, rp, mask=b["done"])
+            env_ops.observe(b, p, mask=b["done"], velocity_from_state=True)
+            env_stream.wait_stream(learn_stream)
+
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            while self.current_timestep <= total_timesteps:
+                vstep = st["vstep"]
+                par = vstep & 1
+                update = bool(self.current_timestep >= learning_starts and mem.size > B)
+                p, rp = train_env.params(), train_env.reset_params()
+                st["done"][par].synchronize()                     # the replay that last read this pinned block has finished
+                eps = self.linear_eps(total_timesteps)
+                self._act_calls = getattr(self, "_act_calls", 0) + 1
+                for u in range(U):
+                    c = st["host"][par][u]
+                    c.act_eps, c.act_step = eps, self._act_calls
+                    mem.fill_ctl(c)
+                    c.rpl_call = mem.calls + u
+                    if update:
+                        c.adam_step_size, c.adam_inv_sqrt_bc2 = iqn_ops.adam_ctl_fields(opt.lr, opt.betas[0], opt.betas[1], opt.step_count + 1 + u)
+                key = (par, update, train_env._params_key, train_env._reset_key, bool(sample_without_replacement))
+                if not capture:
+                    launch(par, update, p, rp, cur, st["learner"])
+                else:
+                    seen = st["seen"].get(key, 0)
+                    st["seen"][key] = seen + 1
+                    if seen == 0:                                 # first encounter: eager (warm-up, every buffer gets allocated)
+                        launch(par, update, p, rp, cur, st["learner"])
+                    else:
+                        g = st["graphs"].get(key)
+                        if g is None:
+                            g = torch.cuda.CUDAGraph()
+                            side = st["side"]
+                            side.wait_stream(cur)
+                            with torch.cuda.stream(side):
+                                with torch.cuda.graph(g, stream=side):
+                                    launch(par, update, p, rp, side, st["learner"])
+                            cur.wait_stream(side)
+                            st["graphs"][key] = g
+                        g.replay()
+                st["done"][par].record(cur)
+                # host-side bookkeeping of what the launches did
+                st["vstep"] = vstep + 1
+                train_env.total_timesteps += E * train_env.global_step_multiplier
+                self.current_timestep += E * world
+                mem.advance_append(E)
+                do_eval = False
+                if update:
+                    mem.calls += U
+                    opt.step_count += U
+                    before = self.learning_timestep
+                    self.learning_timestep += steps_per_update * U
+                    if before == 0 or int(before // target_update_interval) != int(self.learning_timestep // target_update_interval):
+                        self.soft_update(self.qnetwork_local, self.qnetwork_target)      # agent.py:135-137
+                    if verbose:
+                        losses.append(self._loss.clone())
+                    do_eval = eval_config is not None and bool(eval_freq) and self.learning_timestep >= next_eval
+                if do_eval:
+                    if mdist.rank() == 0:
+                        self.evaluation_vec(eval_config, greedy=True, eval_log_path=eval_log_path)
+                        self.evaluation_vec(eval_config, greedy=False, eval_log_path=eval_log_path)
+                        if eval_log_path is not None:
+                            self.qnetwork_local.save(eval_log_path)
+                    mdist.barrier()
+                    next_eval += eval_freq
+                if on_step is not None:
+                    on_step(self)
         return [float(x.item()) for x in losses[::max(1, len(losses) // 200)]] if verbose else losses

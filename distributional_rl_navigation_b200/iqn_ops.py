@@ -1,6 +1,8 @@
 """Tensor-level wrappers over the IQN entry points of libmarinenav_b200 (include/marinenav_b200.h)."""
 import ctypes as C
+import math
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -166,11 +168,21 @@ class UpdateTail:
                     raise _lib.MarinenavError(f"UpdateTail: peer exchange unavailable: {self.peer_error}")
 
     def step(self, params, m, v, packed, packed_tc, scratch, B, step, loss=None, grad=None, grad_norm=None, lr=1e-4, max_norm=0.5,
-             beta1=0.9, beta2=0.999, eps=1e-8):
+             beta1=0.9, beta2=0.999, eps=1e-8, ctl=None):
+        """ctl (device address of an mnv_vstep_ctl): Adam's bias corrections come from the control block (iqn_update_tail_ctl,
+        CUDA-graph replays); `step` and `lr` are then ignored -- see adam_ctl_fields()."""
         for t, n in ((params, "params"), (m, "m"), (v, "v")):
             _f32(t, N_PARAMS, n)
         if grad is not None:
             _f32(grad, N_PARAMS, "grad")
+        if ctl is not None:
+            rc = _lib.load().iqn_update_tail_ctl(_lib.ptr(params), _lib.ptr(m), _lib.ptr(v), _lib.ptr(packed), _lib.ptr(packed_tc),
+                                                 _lib.ptr(scratch), int(B), _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(grad_norm),
+                                                 _lib.ptr(self.sync), self._peer_array, self.rank, self.world,
+                                                 C.c_float(max_norm), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                                 C.c_void_p(ctl), _stream())
+            _lib.check(rc, "iqn_update_tail_ctl")
+            return
         rc = _lib.load().iqn_update_tail(_lib.ptr(params), _lib.ptr(m), _lib.ptr(v), _lib.ptr(packed), _lib.ptr(packed_tc),
                                          _lib.ptr(scratch), int(B), _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(grad_norm),
                                          _lib.ptr(self.sync), self._peer_array, self.rank, self.world,
@@ -235,8 +247,27 @@ def act_tc(params, packed_tc, obs, taus, cvar=1.0, want_qmean=False, want_greedy
     return qm, gr
 
 
+def adam_ctl_fields(lr, beta1, beta2, step):
+    """(adam_step_size, adam_inv_sqrt_bc2) of mnv_vstep_ctl for optimizer step `step` (>= 1): the arithmetic of
+    iqn_update_tail's by-value path (csrc/iqn_tail.cu) -- lr / beta1 / beta2 arrive there as floats, the bias corrections are
+    formed in double and rounded to float last (the ctypes float fields do that rounding)."""
+    lr, beta1, beta2 = (float(np.float32(x)) for x in (lr, beta1, beta2))
+    bc1, bc2 = 1.0 - math.pow(beta1, float(int(step))), 1.0 - math.pow(beta2, float(int(step)))
+    return lr / bc1, 1.0 / math.sqrt(bc2)
+
+
+def draw_taus(out, seed, call=0, ctl=None):
+    """The quantile samples of one update on the device (iqn_draw_taus): out f32 [2, B, 8] <- uniform [0, 1), reproducible per
+    (seed, call); out[0] = the target network's taus (drawn first, Q9), out[1] = the local network's."""
+    _f32(out, out.numel(), "taus")
+    rc = _lib.load().iqn_draw_taus(_lib.ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(call) & (2 ** 64 - 1),
+                                   None if ctl is None else C.c_void_p(ctl), _stream())
+    _lib.check(rc, "iqn_draw_taus")
+    return out
+
+
 def act_tc_sample(params, packed_tc, obs, eps, seed, step, cvar=1.0, adaptive=False, action=None, want_greedy=False, want_qmean=False,
-                  cvar_out=None):
+                  cvar_out=None, ctl=None):
     """IQNAgent.act / act_adaptive for an env batch with taus and the epsilon-greedy draw from the device Philox stream
     (seed, step): -> (action i32 [B], greedy i32 [B] | None, qmean f32 [B, 9] | None).  `params`: the flat parameter vector,
     or just its first N_ENCODER_PARAMS floats (the observation encoders -- all the pre-pass reads)."""
@@ -250,6 +281,12 @@ def act_tc_sample(params, packed_tc, obs, eps, seed, step, cvar=1.0, adaptive=Fa
     qm = torch.empty(B, N_ACTIONS, dtype=torch.float32, device=dev) if want_qmean else None
     if adaptive and cvar_out is None:
         cvar_out = torch.empty(B, dtype=torch.float32, device=dev)
+    if ctl is not None:                # eps / step from the device control block (CUDA-graph replays)
+        rc = _lib.load().iqn_act_tc_sample_ctl(_lib.ptr(params), _lib.ptr(packed_tc), _lib.ptr(obs), int(bool(adaptive)), _lib.ptr(cvar_out),
+                                               C.c_float(float(cvar)), int(seed) & (2 ** 64 - 1), _lib.ptr(action), _lib.ptr(gr), _lib.ptr(qm),
+                                               _lib.ptr(_scratch_for(B, dev)), B, C.c_void_p(ctl), _stream())
+        _lib.check(rc, "iqn_act_tc_sample_ctl")
+        return action, gr, qm
     rc = _lib.load().iqn_act_tc_sample(_lib.ptr(params), _lib.ptr(packed_tc), _lib.ptr(obs), int(bool(adaptive)), _lib.ptr(cvar_out),
                                        C.c_float(float(cvar)), C.c_float(float(eps)), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
                                        _lib.ptr(action), _lib.ptr(gr), _lib.ptr(qm), _lib.ptr(_scratch_for(B, dev)), B, _stream())

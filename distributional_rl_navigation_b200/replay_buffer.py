@@ -114,8 +114,21 @@ class DeviceReplayBuffer:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def add_batch(self, states, actions, rewards, next_states, dones):
-        """Append the transitions of one vector step (device tensors: f32 [E, D], i32 [E], f32 [E], f32 [E, D], u8 [E])."""
+    def fill_ctl(self, c):
+        """Write the ring state the NEXT add_batch / sample would pass by value into the mnv_vstep_ctl `c` (host struct)."""
+        c.rpl_pos, c.rpl_t, c.rpl_head, c.rpl_size, c.rpl_call = self.pos, self.t, self.head, self.size, self.calls
+
+    def advance_append(self, E):
+        """Host-side bookkeeping of one add_batch (called by add_batch; by the graph trainer after a replay)."""
+        if self.t >= self.n_step - 1:                            # the windows are full: E folded transitions were stored
+            self.pos = (self.pos + E) % self.capacity
+            self.size = min(self.capacity, self.size + E)
+        self.t += 1
+
+    def add_batch(self, states, actions, rewards, next_states, dones, ctl=None, advance=True):
+        """Append the transitions of one vector step (device tensors: f32 [E, D], i32 [E], f32 [E], f32 [E, D], u8 [E]).
+        ctl (device address of an mnv_vstep_ctl): pos / t come from the control block (rpl_append_ctl, CUDA-graph replays);
+        advance=False leaves the host counters alone (a captured launch runs at replay time, not now)."""
         E = states.shape[0]
         if E > self.capacity:
             raise ValueError("batch larger than the buffer")
@@ -135,15 +148,19 @@ class DeviceReplayBuffer:
         w = self._win or (None, None, None)
         p = _lib.ptr
         with torch.cuda.device(self.device):
-            rc = _lib.load().rpl_append(p(self.states), p(self.actions), p(self.rewards), p(self.next_states), p(self.dones),
-                                        self.capacity, self.pos, p(states), p(actions.contiguous()), p(rewards), p(next_states),
-                                        p(dones.contiguous()), E, self.state_dim, self.n_step, self.gamma, self.t,
-                                        p(w[0]), p(w[1]), p(w[2]), self._stream())
+            if ctl is not None:
+                rc = _lib.load().rpl_append_ctl(p(self.states), p(self.actions), p(self.rewards), p(self.next_states), p(self.dones),
+                                                self.capacity, p(states), p(actions.contiguous()), p(rewards), p(next_states),
+                                                p(dones.contiguous()), E, self.state_dim, self.n_step, self.gamma,
+                                                p(w[0]), p(w[1]), p(w[2]), C.c_void_p(ctl), self._stream())
+            else:
+                rc = _lib.load().rpl_append(p(self.states), p(self.actions), p(self.rewards), p(self.next_states), p(self.dones),
+                                            self.capacity, self.pos, p(states), p(actions.contiguous()), p(rewards), p(next_states),
+                                            p(dones.contiguous()), E, self.state_dim, self.n_step, self.gamma, self.t,
+                                            p(w[0]), p(w[1]), p(w[2]), self._stream())
         _lib.check(rc, "rpl_append")
-        if self.t >= self.n_step - 1:                            # the windows are full: E folded transitions were stored
-            self.pos = (self.pos + E) % self.capacity
-            self.size = min(self.capacity, self.size + E)
-        self.t += 1
+        if advance:
+            self.advance_append(E)
 
     def _outputs(self, B):
         o = self._out.get(B)
@@ -157,17 +174,24 @@ class DeviceReplayBuffer:
         o[0] ^= 1
         return o[1][o[0]]
 
-    def sample(self, batch_size=None, without_replacement=False, indices=None):
-        """-> (states [B, D], actions i64 [B], rewards [B], next_states [B, D], dones [B]); self.last_indices = the picks."""
+    def sample(self, batch_size=None, without_replacement=False, indices=None, ctl=None, advance=True):
+        """-> (states [B, D], actions i64 [B], rewards [B], next_states [B, D], dones [B]); self.last_indices = the picks.
+        ctl (device address of an mnv_vstep_ctl): head / size / call come from the control block (rpl_sample_ctl)."""
         B = int(batch_size or self.batch_size)
-        if self.size == 0:
+        if self.size == 0 and ctl is None:
             raise ValueError("sample from an empty buffer")
         o = self._outputs(B)
         p = _lib.ptr
         ring = (p(self.states), p(self.actions), p(self.rewards), p(self.next_states), p(self.dones))
         outs = (p(o["s"]), p(o["a"]), p(o["r"]), p(o["n"]), p(o["d"]))
         with torch.cuda.device(self.device):
-            if indices is not None:
+            if ctl is not None:
+                rc = _lib.load().rpl_sample_ctl(*ring, self.capacity, self.seed, int(bool(without_replacement)), p(o["idx"]), *outs, B,
+                                                self.state_dim, C.c_void_p(ctl), self._stream())
+                _lib.check(rc, "rpl_sample_ctl")
+                if advance:
+                    self.calls += 1
+            elif indices is not None:
                 o["idx"].copy_(torch.as_tensor(indices, dtype=torch.int64).reshape(B))
                 rc = _lib.load().rpl_gather(*ring, self.capacity, self.head, self.size, p(o["idx"]), *outs, B, self.state_dim, self._stream())
                 _lib.check(rc, "rpl_gather")

@@ -276,6 +276,47 @@ int     iqn_act_tc_sample(const float* d_params, const void* d_packed_tc, const 
                           float* d_cvar, float cvar_scalar, float eps, uint64_t seed, uint64_t step,
                           int32_t* d_action, int32_t* d_greedy, float* d_qmean, void* d_scratch, int64_t B, void* stream);
 
+/* ============================ vector-step control block (CUDA-graph replays) ================================
+ * A rollout + learn vector step (act -> env step -> replay append -> sample -> update, agent.py:94-173 vectorised) is a
+ * chain of ~12 launches of 5 - 250 us each: launch-bound from Python.  The trainer therefore captures it ONCE as a CUDA
+ * graph and replays it; what changes from step to step -- the exploration rate, the Philox counters, the ring position of
+ * the replay buffer, Adam's bias corrections -- cannot be a by-value kernel argument any more (a graph freezes those), so
+ * the `_ctl` entry points below read them from this 64-byte block in DEVICE memory.  The host fills a pinned copy before
+ * every replay and the graph's first node copies it in.  Each `_ctl` function is its by-value counterpart with the named
+ * scalars taken from the block (same kernels, same results for equal values; range checks on them are the caller's). */
+typedef struct mnv_vstep_ctl {
+    float    act_eps;              /* iqn_act_tc_sample: eps */
+    float    adam_step_size;       /* iqn_update_tail: lr / (1 - beta1^step), computed in double like the by-value path */
+    float    adam_inv_sqrt_bc2;    /* iqn_update_tail: 1 / sqrt(1 - beta2^step) */
+    int32_t  reserved;
+    uint64_t act_step;             /* iqn_act_tc_sample: step */
+    int64_t  rpl_pos, rpl_t;       /* rpl_append: pos, t */
+    int64_t  rpl_head, rpl_size;   /* rpl_sample: head, size */
+    uint64_t rpl_call;             /* rpl_sample / iqn_draw_taus: call */
+} mnv_vstep_ctl;
+
+int rpl_append_ctl(float* d_states, int64_t* d_actions, float* d_rewards, float* d_next_states, float* d_dones,
+                   int64_t capacity, const float* d_obs, const int32_t* d_action, const float* d_reward,
+                   const float* d_next_obs, const uint8_t* d_done, int64_t E, int32_t row_len, int32_t n_step, double gamma,
+                   float* d_win_obs, int32_t* d_win_action, float* d_win_reward, const mnv_vstep_ctl* d_ctl, void* stream);
+int rpl_sample_ctl(const float* d_states, const int64_t* d_actions, const float* d_rewards, const float* d_next_states,
+                   const float* d_dones, int64_t capacity, uint64_t seed, int32_t without_replacement, int64_t* d_indices,
+                   float* d_out_states, int64_t* d_out_actions, float* d_out_rewards, float* d_out_next_states,
+                   float* d_out_dones, int64_t B, int32_t row_len, const mnv_vstep_ctl* d_ctl, void* stream);
+int iqn_update_tail_ctl(float* d_params, float* d_m, float* d_v, float* d_packed, void* d_packed_tc,
+                        const float* d_scratch, int64_t B, float* d_loss, float* d_grad, float* d_grad_norm,
+                        void* d_sync, void* const* peer_xchg, int32_t rank, int32_t world,
+                        float max_norm, float beta1, float beta2, float eps, const mnv_vstep_ctl* d_ctl, void* stream);
+int iqn_act_tc_sample_ctl(const float* d_params, const void* d_packed_tc, const float* d_obs, int32_t adaptive_cvar,
+                          float* d_cvar, float cvar_scalar, uint64_t seed, int32_t* d_action, int32_t* d_greedy,
+                          float* d_qmean, void* d_scratch, int64_t B, const mnv_vstep_ctl* d_ctl, void* stream);
+
+/* The quantile samples of one update drawn on the device: d_taus f32 [n] (n = 2 * B * 8: the target network's taus first,
+ * then the local network's -- the draw order of agent.py:279-283, Q9) = uniform [0, 1) multiples of 2^-24 (torch.rand's
+ * float32 grid) from Philox4x32-10(key = seed ^ 0x7A75, counter = (i / 4, 0x7A, call)), call = d_ctl->rpl_call if d_ctl != NULL.
+ * One launch; reproducible per (seed, call). */
+int iqn_draw_taus(float* d_taus, int64_t n, uint64_t seed, uint64_t call, const mnv_vstep_ctl* d_ctl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
