@@ -362,8 +362,8 @@ def run_b200(args):
     # ---- e2e: public API with HOST buffers (H2D actions, D2H obs/reward/done/info, auto-reset) every step: K steps per
     #      repetition, repeated until >= ~0.1 s, median repetition ----
     host_actions = np.random.RandomState(7 + rank).randint(0, 9, size=(W + K, E)).astype(np.int32)
-    for i in range(W):
-        env0.step_host(host_actions[i])
+    for i in range(max(W, 20)):                         # host_transport="auto" measures the transports in its first 18 calls
+        env0.step_host(host_actions[i % (W + K)])
     barrier()
     e2e_reps, e2e_times, t_all = 0, [], time.perf_counter()
     while e2e_reps < 3 or (time.perf_counter() - t_all < 0.15 and e2e_reps < 200):
@@ -379,22 +379,25 @@ def run_b200(args):
     e2e_value = world * E * K / float(te.item())
     checksum = float(np.asarray(rew, np.float64).sum())
     e2e_bytes = (env0.h2d_bytes_per_step(), env0.d2h_bytes_per_step(), env0.host_api_description(), env0.host_transport)
-    # the other host transport of step_host, same loop (documents the trade-off; the headline e2e is the default one above)
-    other = "compact" if env0.host_transport == "dense" else "dense"
-    env0.host_transport = other
-    for i in range(W):
-        env0.step_host(host_actions[i])
-    ot = []
-    for _ in range(max(3, min(e2e_reps, 10))):
-        t0 = time.perf_counter()
-        for i in range(W, W + K):
+    # the other host transports of step_host, same loop (documents the trade-off; the headline e2e is the default one above)
+    e2e_other = []
+    for other in ("hybrid", "dense", "compact"):
+        if other == e2e_bytes[3]:
+            continue
+        env0.host_transport = other
+        for i in range(W):
             env0.step_host(host_actions[i])
-        torch.cuda.synchronize()
-        ot.append(time.perf_counter() - t0)
-    to = torch.tensor([sorted(ot)[len(ot) // 2]], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(to, op=dist.ReduceOp.MAX)
-    e2e_other = {"host_transport": other, "value": world * E * K / float(to.item()), "d2h_bytes_per_step": env0.d2h_bytes_per_step() * world}
+        ot = []
+        for _ in range(max(3, min(e2e_reps, 10))):
+            t0 = time.perf_counter()
+            for i in range(W, W + K):
+                env0.step_host(host_actions[i])
+            torch.cuda.synchronize()
+            ot.append(time.perf_counter() - t0)
+        to = torch.tensor([sorted(ot)[len(ot) // 2]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(to, op=dist.ReduceOp.MAX)
+        e2e_other.append({"host_transport": other, "value": world * E * K / float(to.item()), "d2h_bytes_per_step": env0.d2h_bytes_per_step() * world})
     env0.host_transport = e2e_bytes[3]
 
     for env in batches[1:]:
@@ -440,7 +443,8 @@ def run_b200(args):
                                                "masked mnv_observe, CUDA graph of 16 steps, median of 12 replays"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes[0] * world,
                     "d2h_bytes_per_step": e2e_bytes[1] * world, "checksum": checksum,
-                    "repetitions": e2e_reps, "api": e2e_bytes[2], "host_transport": e2e_bytes[3], "other_transport": e2e_other},
+                    "repetitions": e2e_reps, "api": e2e_bytes[2], "host_transport": e2e_bytes[3], "other_transport": e2e_other,
+                    "auto_calibration_s_per_step": env0.host_transport_calibration},
             "gpu_launches": n_launch * n_replay,
             "clocks": clk.summary(),
         }

@@ -22,6 +22,8 @@ def load():
         L.mnvh_threads.restype, L.mnvh_threads.argtypes = C.c_int, [C.c_void_p]
         L.mnvh_rescan.restype, L.mnvh_rescan.argtypes = None, [C.c_void_p, C.c_void_p]
         L.mnvh_expand.restype, L.mnvh_expand.argtypes = None, [C.c_void_p] * 7
+        L.mnvh_expand_early.restype, L.mnvh_expand_early.argtypes = None, [C.c_void_p] * 7
+        L.mnvh_rescan_skipped.restype, L.mnvh_rescan_skipped.argtypes = None, [C.c_void_p] * 3
         _lib = L
     return _lib
 
@@ -59,6 +61,13 @@ class Expander:
 
     def expand(self, obs_ptr, head_ptr, skip_ptr, mask_ptr, dir_ptr, vals_ptr):
         self._L.mnvh_expand(self._p, obs_ptr, head_ptr, skip_ptr, mask_ptr, dir_ptr, vals_ptr)
+
+    def expand_early(self, obs_ptr, head_ptr, skip_ptr, mask_ptr, dir_ptr, vals_ptr):
+        """expand() while the rows flagged in skip are still on their way: they are left for rescan_skipped()."""
+        self._L.mnvh_expand_early(self._p, obs_ptr, head_ptr, skip_ptr, mask_ptr, dir_ptr, vals_ptr)
+
+    def rescan_skipped(self, obs_ptr, skip_ptr):
+        self._L.mnvh_rescan_skipped(self._p, obs_ptr, skip_ptr)
 
     def close(self):
         if self._p:

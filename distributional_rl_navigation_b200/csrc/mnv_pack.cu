@@ -8,7 +8,9 @@
 //     mask  u32 [E][W]                     W = ceil(n_beams / 32): bit b of environment e <=> beam b has a return
 //     dir   u32 [ceil(E / 32)]             where the returns of environments 32 g .. 32 g + 31 start in `vals`
 //     count u32 [4]                        count[0] = number of returns (may exceed `capacity`: the tail is then not written
-//                                          and the host falls back to the dense block for that step)
+//                                          and the host falls back to the dense block for that step); count[3] = launch
+//                                          sequence number (+1 per launch: a host that polls a copy of it in pinned memory
+//                                          knows that the packet of THIS launch has landed)
 //     vals  f32 [capacity][2]              (x, y) of the returns of a group, environment by environment, beam by beam
 // into ONE contiguous buffer that ships with one copy (~1.9 MB); a native multi-threaded helper (csrc_host/mnv_host.c)
 // expands it into the dense [E][obs_dim] array on the host with one sequential sweep per thread.  One warp = one group of
@@ -26,6 +28,7 @@ mnv_pack_obs_kernel(const float* __restrict__ obs, long long E, int D, float4* _
     extern __shared__ __align__(16) float s_rows[];                // [kPackWarps][32 * D]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long g = (long long)blockIdx.x * kPackWarps + w, e0 = g * 32;
+    if (blockIdx.x == 0 && threadIdx.x == 0) count[3] += 1u;      // launch sequence number (not cleared by the memset)
     if (e0 >= E) return;
     float* rows = s_rows + w * 32 * D;
     const long long left = E - e0;
@@ -83,7 +86,7 @@ extern "C" int mnv_pack_obs(const float* d_obs, int64_t E, int32_t obs_dim, floa
         mnv_set_error("mnv_pack_obs: bad sizes (E=%lld, obs_dim=%d, capacity=%lld)", (long long)E, obs_dim, (long long)capacity);
         return MNV_E_SIZE;
     }
-    cudaError_t err = cudaMemsetAsync(d_count, 0, 4 * sizeof(uint32_t), (cudaStream_t)stream);
+    cudaError_t err = cudaMemsetAsync(d_count, 0, 3 * sizeof(uint32_t), (cudaStream_t)stream);     // count[3] = sequence number: kept
     if (err != cudaSuccess) { mnv_set_error("mnv_pack_obs: memset: %s", cudaGetErrorString(err)); return (int)err; }
     const long long warps = (E + 31) / 32;
     const unsigned grid = (unsigned)((warps + kPackWarps - 1) / kPackWarps);

@@ -56,9 +56,11 @@ static void work(mnvh_pool* p, int t)
     uint32_t* pm = p->prev_mask;
     for (int64_t g = p->g_lo[t]; g < p->g_hi[t]; ++g) {
         const int64_t e0 = g * 32, e1 = e0 + 32 < E ? e0 + 32 : E;
-        if (j->rescan_only) {
-            for (int64_t e = e0; e < e1; ++e)
+        if (j->rescan_only == 1 || j->rescan_only == 3) {         /* 1: every row; 3: only the rows flagged in skip */
+            for (int64_t e = e0; e < e1; ++e) {
+                if (j->rescan_only == 3 && !j->skip[e]) continue;
                 for (int w = 0; w < W; ++w) pm[e * W + w] = row_mask(obs + e * D + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
+            }
             continue;
         }
         const float* v = j->vals + 2 * (size_t)j->dir[g];
@@ -67,7 +69,8 @@ static void work(mnvh_pool* p, int t)
             if (j->skip != NULL && j->skip[e]) {                  /* written by the GPU: pick up what the row holds */
                 for (int w = 0; w < W; ++w) {
                     v += 2 * __builtin_popcount(j->mask[e * W + w]);
-                    pm[e * W + w] = row_mask(row + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
+                    if (j->rescan_only != 2)                     /* 2: the GPU's row arrives later, mnvh_rescan_skipped follows */
+                        pm[e * W + w] = row_mask(row + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
                 }
                 continue;
             }
@@ -99,7 +102,7 @@ static void* worker(void* a_)
         int spins = 0;
         while (atomic_load_explicit(&p->generation, memory_order_acquire) == seen) {
             if (atomic_load_explicit(&p->stop, memory_order_relaxed)) return NULL;
-            if (++spins < 4000) { __builtin_ia32_pause(); }
+            if (++spins < 30000) { __builtin_ia32_pause(); }           /* ~1 ms: a step loop (200 - 400 us per step) keeps them hot */
             else { struct timespec ts = {0, 20000}; nanosleep(&ts, NULL); }
         }
         seen = atomic_load_explicit(&p->generation, memory_order_acquire);
@@ -162,4 +165,31 @@ void mnvh_expand(mnvh_pool* p, float* obs, const float* head, const uint8_t* ski
 {
     p->job = (job_t){obs, head, skip, mask, dir, vals, 0};
     run(p);
+}
+
+/* mnvh_expand for a packet that arrives BEFORE the caller's own writes of the rows flagged in skip have landed (the hybrid
+ * transport expands while the GPU still works): those rows are neither written nor re-scanned here ... */
+void mnvh_expand_early(mnvh_pool* p, float* obs, const float* head, const uint8_t* skip, const uint32_t* mask, const uint32_t* dir,
+                       const float* vals)
+{
+    p->job = (job_t){obs, head, skip, mask, dir, vals, 2};
+    run(p);
+}
+
+/* ... and this picks them up once they have: re-scan of the rows flagged in skip. */
+void mnvh_rescan_skipped(mnvh_pool* p, float* obs, const uint8_t* skip)
+{
+    if (skip == NULL) return;
+    /* a few hundred rows among E flags: not worth waking the pool -- the caller scans the flags 8 at a time */
+    const int D = p->D, nb = p->n_beams, W = p->W;
+    const int64_t E = p->E;
+    for (int64_t e = 0; e < E; ) {
+        if (e + 8 <= E) {
+            uint64_t w8; memcpy(&w8, skip + e, 8);
+            if (w8 == 0) { e += 8; continue; }
+        }
+        if (skip[e])
+            for (int w = 0; w < W; ++w) p->prev_mask[e * W + w] = row_mask(obs + e * D + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
+        ++e;
+    }
 }

@@ -7,6 +7,7 @@ stream seeded with ``seed + e`` -> its maps are the ones ``MarineNavEnv(seed=see
 """
 import math
 import os
+import time
 
 import numpy as np
 import torch
@@ -29,19 +30,27 @@ class VecMarineNavEnv:
         # tables_written() fences device-side edits (the facade's setters).  MNV_PDL in the environment overrides (lab use).
         self.pdl_prefetch = bool(pdl_prefetch) and os.environ.get("MNV_PDL") is None
         # How step_host ships the observation block to the host (same results either way):
-        #   "dense"    one 6.8 MB device -> host copy of the f32 [E, obs_dim] block (the DMA engine writes the rows): fastest
-        #              when this process has the PCIe link and the host memory system to itself (measured 200 us per
-        #              65 536-env step vs 223 us compact on the 16-vCPU single-GPU box);
+        #   "dense"    one 6.8 MB device -> host copy of the f32 [E, obs_dim] block (the DMA engine writes the rows; no host
+        #              work): ~200 us per 65 536-env step on a single-GPU box (the copy alone is 149 us at 48 GB/s);
         #   "compact"  ~2 MB packet (head + list of sonar returns, mnv_pack_obs) expanded by host threads (libmnv_host.so):
-        #              4x fewer bytes over PCIe, which is what binds when the GPUs of a node share the host (8 ranks dense:
-        #              547 us per step);
-        #   "auto"     compact iff several ranks share this node (LOCAL_WORLD_SIZE > 1).  MNV_HOST_TRANSPORT overrides.
+        #              3.5x fewer bytes over PCIe, paid with host CPU time: 170 us with 8 expander threads, 212 us with 4;
+        #   "hybrid"   the first 62.5 % of the environments (MNV_HOST_HYBRID_FRACTION) travel compact, the rest dense, in that
+        #              order: the host threads expand the packet WHILE the DMA engine still writes the dense rows, so the link
+        #              and the host cores work at the same time (the packet's arrival is signalled through a sequence number
+        #              in pinned memory): 170 - 184 us with 8 / 4 threads -- the choice when a rank has few cores;
+        #   "auto"     MEASURED: the first 18 step_host calls run 6 steps on each transport (identical results, whichever
+        #              carries them), the fastest median stays.  Which one wins depends on the host: cores per rank, how many
+        #              GPUs share the memory system.  MNV_HOST_TRANSPORT overrides.
         t = os.environ.get("MNV_HOST_TRANSPORT", host_transport)
+        self._auto_cal = None
         if t == "auto":
-            t = "compact" if int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1 else "dense"
-        if t not in ("dense", "compact"):
-            raise ValueError(f"host_transport must be 'auto', 'dense' or 'compact' (got {t!r})")
+            t = "compact"
+            order = ("compact", "hybrid", "dense")
+            self._auto_cal = dict(order=order, per=6, calls=0, times={k: [] for k in order})
+        if t not in ("dense", "compact", "hybrid"):
+            raise ValueError(f"host_transport must be 'auto', 'dense', 'compact' or 'hybrid' (got {t!r})")
         self.host_transport = t
+        self.host_transport_calibration = None      # {"dense": median seconds per step, "compact": ...} once "auto" has measured
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
         self.sd = seed
@@ -214,7 +223,37 @@ class VecMarineNavEnv:
             self._host_graphs = {}
             self._expander = _hostlib.Expander(E, D)
             self._host_dirty = False                  # True: the pinned dense block was written outside the expander
+            self._hyb = None
         return self._pinned
+
+    def _hybrid(self):
+        """Buffers of the hybrid transport: a packet (mnv_pack_obs layout) for the first Ec environments, its pinned mirror,
+        an expander for those rows and the pinned copy of the packet's count block the host polls."""
+        if self._hyb is None:
+            from . import _hostlib
+            E, D, nb = self.num_envs, self.obs_dim, self.num_beams
+            frac = min(1.0, max(0.0, float(os.environ.get("MNV_HOST_HYBRID_FRACTION", "0.625"))))
+            Ec = E if frac >= 1.0 else min(E, max(32, int(E * frac) // 32 * 32))
+            W, Gc = (nb + 31) // 32, (Ec + 31) // 32
+            seg = lambda n: (n + 15) // 16 * 16
+            o_mask = 16 * Ec
+            o_dir = o_mask + seg(4 * W * Ec)
+            o_cnt = o_dir + seg(4 * Gc)
+            o_vals = o_cnt + 16
+            cap = max(1024, Ec * nb // 8)
+            tier1 = min(cap, max(512, Ec * nb // 16))
+            dev = torch.zeros(o_vals + 8 * cap, dtype=torch.uint8, device=self.device)
+            pk = torch.zeros(dev.numel(), dtype=torch.uint8).pin_memory()
+            seq = torch.zeros(16, dtype=torch.uint8).pin_memory()
+            self._hyb = dict(
+                Ec=Ec, dev=dev, pin=pk, cap=cap, tier1=tier1, tier1_bytes=o_vals + 8 * tier1, o_vals=o_vals,
+                head=dev[:o_mask].view(torch.float32).view(Ec, 4), mask=dev[o_mask:o_mask + 4 * W * Ec].view(torch.int32).view(Ec, W),
+                dir=dev[o_dir:o_dir + 4 * Gc].view(torch.int32), count=dev[o_cnt:o_vals].view(torch.int32),
+                vals=dev[o_vals:].view(torch.float32).view(cap, 2),
+                p_head=pk[:o_mask], p_mask=pk[o_mask:o_dir], p_dir=pk[o_dir:o_cnt], p_vals=pk[o_vals:],
+                count_np=pk[o_cnt:o_vals].view(torch.int32).numpy(), seq_pin=seq, seq_np=seq.view(torch.int32).numpy().view(np.uint32),
+                expander=_hostlib.Expander(Ec, D), next_seq=1, valid=False)
+        return self._hyb
 
     def _capture_host_step(self, auto_reset):
         """One CUDA graph for the whole host-boundary step.  Stream A: fused step (actions read zero-copy from the pinned host
@@ -226,6 +265,8 @@ class VecMarineNavEnv:
         array up to date from the packet, skipping those rows.  The copy runs under the reset, the host pays one graph
         launch and touches only the slots that change."""
         pin, b = self._pin(), self.buf
+        if self.host_transport == "hybrid":
+            self._hybrid()                          # allocate OUTSIDE the capture (a captured torch.zeros would re-zero it at every replay)
         params = self.params()
         rp = self.reset_params() if auto_reset else None
         cur = torch.cuda.current_stream()
@@ -241,6 +282,18 @@ class VecMarineNavEnv:
                     if self.host_transport == "compact":
                         env_ops.pack_obs(b["next_obs"], b["packet_head"], b["packet_mask"], b["packet_dir"], b["packet_count"], b["packet_vals"])
                         pin["packet"][:n1].copy_(b["host_packet"][:n1], non_blocking=True)
+                    elif self.host_transport == "hybrid":
+                        # compact part first (reward | done | info, then the packet of environments [0, Ec)), then a copy of the
+                        # packet's count block -- its sequence number tells the polling host that the packet has landed --
+                        # and only then the dense rows of environments [Ec, E): the host expands under that copy
+                        h = self._hybrid()
+                        Ec, nh = h["Ec"], h["tier1_bytes"]
+                        env_ops.pack_obs(b["next_obs"][:Ec], h["head"], h["mask"], h["dir"], h["count"], h["vals"])
+                        pin["rdi_pack"].copy_(b["rdi_pack"], non_blocking=True)
+                        h["pin"][:nh].copy_(h["dev"][:nh], non_blocking=True)
+                        h["seq_pin"].copy_(h["count"].view(torch.uint8), non_blocking=True)
+                        if Ec < self.num_envs:
+                            pin["obs"][Ec:].copy_(b["next_obs"][Ec:], non_blocking=True)
                     else:
                         pin["obs"].copy_(b["next_obs"], non_blocking=True); pin["rdi_pack"].copy_(b["rdi_pack"], non_blocking=True)
                 b["obs"].copy_(b["next_obs"])
@@ -261,12 +314,33 @@ class VecMarineNavEnv:
         torch.cuda.current_stream(self.device).synchronize()
         self._expander.rescan(pin["obs"].data_ptr())
         self._host_dirty = False
+        if self._hyb is not None:
+            self._hyb["valid"] = False
 
     def step_host(self, actions, auto_reset=True, graph=True):
         """numpy int actions [E] -> (obs f32 [E,D], reward f32 [E], done bool [E], info u8 [E]) numpy views of pinned buffers
         (valid until the next call; read-only: the observation array is updated in place from step to step).  obs holds the
         first observation of the next episode for finished environments, like step().  graph=False runs the same operations
         eagerly on one stream with a dense copy (the parity reference of the graph path)."""
+        cal = self._auto_cal
+        if cal is None or not graph:
+            return self._step_host(actions, auto_reset, graph)
+        # host_transport="auto" with several ranks on the node: time both transports under the load the ranks produce together
+        k, per = cal["calls"], cal["per"]
+        self.host_transport = cal["order"][k // per]
+        t0 = time.perf_counter()
+        out = self._step_host(actions, auto_reset, graph)
+        if k % per:                                                # the first call of a block captures the graph / rescans
+            cal["times"][self.host_transport].append(time.perf_counter() - t0)
+        cal["calls"] = k + 1
+        if cal["calls"] == per * len(cal["order"]):
+            med = {t: sorted(v)[len(v) // 2] for t, v in cal["times"].items()}
+            self.host_transport_calibration = med
+            self.host_transport = min(med, key=med.get)
+            self._auto_cal = None
+        return out
+
+    def _step_host(self, actions, auto_reset, graph):
         pin = self._pin()
         np.copyto(pin["action_np"], np.asarray(actions), casting="unsafe")       # 9 us; torch's CPU copy_ costs 14 - 500 us here
         with torch.cuda.device(self.device):
@@ -276,6 +350,8 @@ class VecMarineNavEnv:
                 pin["obs"].copy_(obs, non_blocking=True); pin["rdi_pack"].copy_(self.buf["rdi_pack"], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 self._host_dirty = True
+                if self._hyb is not None:
+                    self._hyb["valid"] = False
                 return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
             self.params()
             if auto_reset:
@@ -285,10 +361,15 @@ class VecMarineNavEnv:
             if entry is None:
                 self._host_graphs.clear()                         # parameters changed: the old graph holds stale constants
                 entry = self._host_graphs[key] = self._capture_host_step(auto_reset)
+            if self.host_transport == "hybrid":
+                self._step_host_hybrid(entry[0], pin, auto_reset)
+                return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
             compact = self.host_transport == "compact"
             if compact and self._host_dirty:
                 self._expander.rescan(pin["obs"].data_ptr())
                 self._host_dirty = False
+            if self._hyb is not None:
+                self._hyb["valid"] = False                        # the rows of the hybrid expander are rewritten behind its back
             entry[0].replay()
             self.total_timesteps += self.num_envs * self.global_step_multiplier
             torch.cuda.current_stream().synchronize()
@@ -307,6 +388,43 @@ class VecMarineNavEnv:
                                       pin["mask"].data_ptr(), pin["dir"].data_ptr(), pin["vals"].data_ptr())
         return pin["obs"].numpy(), pin["reward"].numpy(), pin["done"].numpy().view(np.bool_), pin["info"].numpy()
 
+    def _step_host_hybrid(self, graph, pin, auto_reset):
+        """Replay + host half of the hybrid transport: wait (polling the sequence number in pinned memory) until the packet of
+        environments [0, Ec) has landed, expand it while the dense rows of [Ec, E) are still in flight, then wait for the
+        stream and pick up the rows the GPU re-observed."""
+        h = self._hybrid()
+        obs_ptr = pin["obs"].data_ptr()
+        if not h["valid"]:                                        # first use / another transport wrote the rows: rebuild the bookkeeping
+            h["expander"].rescan(obs_ptr)
+            h["valid"] = True
+        self._host_dirty = True                                   # (the full-size expander of "compact" loses track of the rows)
+        expect = h["next_seq"]
+        graph.replay()
+        self.total_timesteps += self.num_envs * self.global_step_multiplier
+        seq_np, spins = h["seq_np"], 0
+        while int(seq_np[3]) != expect:
+            spins += 1
+            if spins > 200000:                                    # ~0.1 s: something else is wrong -- let the stream tell
+                torch.cuda.current_stream().synchronize()
+                if int(seq_np[3]) != expect:
+                    raise _lib.MarinenavError(f"step_host(hybrid): packet sequence {int(seq_np[3])}, expected {expect}")
+        h["next_seq"] = (expect + 1) & 0xFFFFFFFF
+        n_hits = int(h["count_np"][0])
+        skip = pin["done"].data_ptr() if auto_reset else None
+        if n_hits > h["cap"]:                                     # more returns than the list holds: dense block this once
+            torch.cuda.current_stream().synchronize()
+            self._refresh_host_dense()
+            return
+        if n_hits > h["tier1"]:                                   # the rest of the list (rare: > 6.25 % of the beam slots)
+            lo, hi = h["tier1_bytes"], h["o_vals"] + 8 * n_hits
+            h["pin"][lo:hi].copy_(h["dev"][lo:hi], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h["expander"].expand_early(obs_ptr, h["p_head"].data_ptr(), skip, h["p_mask"].data_ptr(), h["p_dir"].data_ptr(),
+                                   h["p_vals"].data_ptr())
+        torch.cuda.current_stream().synchronize()
+        if auto_reset:
+            h["expander"].rescan_skipped(obs_ptr, skip)
+
     def tables_written(self):
         """Call after writing buf['goal'|'cores'|'obstacles'] with a device-side kernel (e.g. indexed assignment) if a step
         may follow directly: the step kernel reads these tables ahead of its stream dependency ("pdl" = 2)."""
@@ -320,9 +438,13 @@ class VecMarineNavEnv:
         return pin["obs"].numpy()
 
     def host_api_description(self):
-        how = ("the observation block travels as head + list of sonar returns (mnv_pack_obs) and is expanded into the dense numpy "
-               f"array by libmnv_host.so on {self._expander.n_threads if self._pinned else '?'} host threads") \
-            if self.host_transport == "compact" else "dense device -> host copy of the observation block under the masked reset"
+        nthr = self._expander.n_threads if self._pinned else "?"
+        how = {"compact": "the observation block travels as head + list of sonar returns (mnv_pack_obs) and is expanded into the dense "
+                          f"numpy array by libmnv_host.so on {nthr} host threads",
+               "hybrid": f"environments [0, {self._hybrid()['Ec'] if self._pinned else '?'}) travel as head + list of sonar returns and are "
+                         f"expanded by libmnv_host.so on {nthr} host threads WHILE the dense rows of the other environments are still "
+                         "being copied",
+               "dense": "dense device -> host copy of the observation block under the masked reset"}[self.host_transport]
         return ("VecMarineNavEnv.step_host (numpy in/out, pinned staging, auto-reset; one two-stream CUDA graph per step; "
                 f"host_transport={self.host_transport}: {how})")
 
@@ -335,6 +457,9 @@ class VecMarineNavEnv:
         # re-observed environments (a few hundred x obs_dim x 4 bytes) come on top
         if self.host_transport == "compact":
             return self._pinned["tier1_bytes"]
+        if self.host_transport == "hybrid":
+            h = self._hybrid()
+            return h["tier1_bytes"] + 16 + (self.num_envs - h["Ec"]) * self.obs_dim * 4 + self._pinned["rdi_pack"].numel()
         return self.num_envs * self.obs_dim * 4 + self._pinned["rdi_pack"].numel()
 
     def close(self):

@@ -141,7 +141,8 @@ int mnv_scatter_rows_host(const uint8_t* d_mask, const float* d_rows, float* h_r
  *   d_head  f32 [E][4]              the 4 head values of every row
  *   d_mask  u32 [E][W]              W = ceil(n_beams / 32); bit b of environment e: beam b has a return
  *   d_dir   u32 [ceil(E / 32)]      where the returns of environments 32 g .. 32 g + 31 start in d_vals
- *   d_count u32 [4]                 d_count[0] = number of returns (may exceed `capacity`: the tail is then not written)
+ *   d_count u32 [4]                 d_count[0] = number of returns (may exceed `capacity`: the tail is then not written);
+ *                                   d_count[3] = launch sequence number, incremented by every call (zero it once)
  *   d_vals  f32 [capacity][2]       (x, y) of a group's returns, environment by environment, beam by beam
  * for ONE device -> host copy; libmnv_host.so (include/mnv_host.h) expands it into the dense block on the host.
  * One memset node + one kernel on `stream`. */

@@ -29,6 +29,13 @@ void mnvh_rescan(mnvh_pool* p, float* obs);
 void mnvh_expand(mnvh_pool* p, float* obs, const float* head, const uint8_t* skip, const uint32_t* mask, const uint32_t* dir,
                  const float* vals);
 
+/* The same for a packet that is expanded BEFORE the rows flagged in skip have been written by the caller (the hybrid
+ * transport of step_host expands the first packet while the GPU is still producing the re-observed rows): those rows are
+ * neither written nor re-scanned by mnvh_expand_early; mnvh_rescan_skipped(obs, skip) re-scans them once they have landed. */
+void mnvh_expand_early(mnvh_pool* p, float* obs, const float* head, const uint8_t* skip, const uint32_t* mask, const uint32_t* dir,
+                       const float* vals);
+void mnvh_rescan_skipped(mnvh_pool* p, float* obs, const uint8_t* skip);
+
 #ifdef __cplusplus
 }
 #endif

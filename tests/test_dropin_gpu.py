@@ -181,7 +181,7 @@ def test_learn_single_env_and_vectorised_smoke(tmp_path, golden_dir):
     assert torch.isfinite(agent3.qnetwork_local.flat).all()
 
 
-@pytest.mark.parametrize("transport", ["dense", "compact"])
+@pytest.mark.parametrize("transport", ["dense", "compact", "hybrid"])
 def test_step_host_matches_device_step(transport):
     """The overlapped host-buffer path returns exactly what the plain device path computes (incl. auto-reset rows)."""
     from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
@@ -204,7 +204,55 @@ def test_step_host_matches_device_step(transport):
     assert n_done > 0
 
 
-@pytest.mark.parametrize("transport", ["dense", "compact"])
+def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch):
+    """host_transport="auto" with several ranks on the node: the first 18 calls run on the three transports (6 each), the
+    fastest median stays -- and every call returns exactly what the plain device path computes, whichever transport carried it
+    (also across the switches: each transport's host-side bookkeeping is rebuilt when another one has written the rows)."""
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    monkeypatch.delenv("MNV_HOST_TRANSPORT", raising=False)
+    E = 3000
+    a = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)        # "auto"
+    b = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+    assert a._auto_cal is not None and a.host_transport_calibration is None
+    a.reset_host(); b.reset()
+    rng = np.random.RandomState(0)
+    used = []
+    for t in range(30):
+        if t == 24:
+            a.host_transport = "compact" if a.host_transport != "compact" else "hybrid"      # a manual switch after the calibration
+        act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)
+        obs_h, rew_h, done_h, info_h = a.step_host(act)
+        used.append(a.host_transport)
+        obs_d, rew_d, done_d, info_d = b.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(obs_h, obs_d.cpu().numpy()), t
+        assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy().astype(bool))
+    cal = a.host_transport_calibration
+    assert a._auto_cal is None and set(cal) == {"dense", "compact", "hybrid"} and all(v > 0 for v in cal.values())
+    assert used[17] == min(cal, key=cal.get) and len(set(used[18:24])) == 1
+    assert used[:5] == ["compact"] * 5 and used[6:11] == ["hybrid"] * 5 and used[12:17] == ["dense"] * 5
+
+
+def test_step_host_hybrid_fraction_and_small_batches(monkeypatch):
+    """The compact share of the hybrid transport (MNV_HOST_HYBRID_FRACTION) incl. the corner cases: everything compact,
+    one group of 32 compact, a batch smaller than one group."""
+    from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
+    for E, frac in ((1000, "1.0"), (1000, "0.01"), (20, "0.5"), (777, "0.3")):        # default share: 0.625
+        monkeypatch.setenv("MNV_HOST_HYBRID_FRACTION", frac)
+        a = VecMarineNavEnv(E, seed=3, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0, host_transport="hybrid")
+        b = VecMarineNavEnv(E, seed=3, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
+        a.reset_host(); b.reset()
+        rng = np.random.RandomState(1)
+        for t in range(25):
+            act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)
+            obs_h, rew_h, done_h, info_h = a.step_host(act)
+            obs_d, rew_d, done_d, info_d = b.step(torch.from_numpy(act).cuda())
+            assert np.array_equal(obs_h, obs_d.cpu().numpy()), (E, frac, t)
+            assert np.array_equal(done_h, done_d.cpu().numpy().astype(bool))
+        assert a._hybrid()["Ec"] == {"1.0": E, "0.01": 32, "0.5": 20, "0.3": 224}[frac]
+
+
+@pytest.mark.parametrize("transport", ["dense", "compact", "hybrid"])
 def test_step_host_graph_equals_eager_and_survives_patch_overflow(transport):
     """graph=True (two-stream CUDA graph, re-observed rows written zero-copy into the pinned array; dense block or compact
     packet + native host expander) == graph=False (eager, one stream), also when every episode ends in the same step and

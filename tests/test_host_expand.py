@@ -73,6 +73,29 @@ def test_expand_follows_dense_blocks(E, nb, threads):
     ex.close()
 
 
+@pytest.mark.parametrize("E,nb,threads", [(1000, 11, 3), (4097, 11, 8), (300, 64, 4)])
+def test_expand_early_then_rescan_skipped(E, nb, threads):
+    """The hybrid transport's order: the packet is expanded BEFORE the GPU's rows (auto-reset) have landed in the dense array;
+    they land afterwards and rescan_skipped() picks them up -- the following steps must still produce the dense blocks."""
+    rs = np.random.RandomState(7 * E + threads)
+    ex = _hostlib.Expander(E, 4 + 2 * nb, n_threads=threads, cpu_first=-1)
+    out = dense_block(rs, E, nb, 0.3)
+    ex.rescan(ptr(out))
+    for step in range(10):
+        nxt = dense_block(rs, E, nb, [0.04, 0.5, 0.0, 1.0][step % 4])
+        head, mask, dir_, vals = pack(nxt, rs)
+        skip = (rs.rand(E) < (0.1 if step % 2 else 0.0)).astype(np.uint8)
+        fresh = dense_block(rs, E, nb, 0.6)
+        nxt[skip != 0] = fresh[skip != 0]
+        before = out.copy()
+        ex.expand_early(ptr(out), ptr(head), ptr(skip), ptr(mask), ptr(dir_), ptr(vals))
+        np.testing.assert_array_equal(out[skip != 0], before[skip != 0])         # flagged rows untouched so far
+        out[skip != 0] = fresh[skip != 0]                                        # ... now the "GPU" writes them
+        ex.rescan_skipped(ptr(out), ptr(skip))
+        np.testing.assert_array_equal(out, nxt)
+    ex.close()
+
+
 def test_default_thread_split_by_local_rank(monkeypatch):
     import os
     n_cpu = len(os.sched_getaffinity(0))
