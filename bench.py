@@ -362,7 +362,7 @@ def run_b200(args):
     # ---- e2e: public API with HOST buffers (H2D actions, D2H obs/reward/done/info, auto-reset) every step: K steps per
     #      repetition, repeated until >= ~0.1 s, median repetition ----
     host_actions = np.random.RandomState(7 + rank).randint(0, 9, size=(W + K, E)).astype(np.int32)
-    for i in range(max(W, 20)):                         # host_transport="auto" measures the transports in its first 18 calls
+    for i in range(max(W, 36)):                         # host_transport="auto" measures the transports in its first 33 calls
         env0.step_host(host_actions[i % (W + K)])
     barrier()
     e2e_reps, e2e_times, t_all = 0, [], time.perf_counter()
@@ -566,9 +566,26 @@ def iqn_bench(args, dev, world):
     ms = torch.tensor([e0.elapsed_time(e1) / n_upd], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_eager = float(ms.item())
+    # the same updates as ONE CUDA graph per n_upd updates (IQNAgent.capture_updates: Adam's bias corrections from a device
+    # control block): no Python between the launches -- with replicas, no rank is late for the gradient exchange
+    replay = agent.capture_updates([(st[i % n_sets], ac[i % n_sets], rw[i % n_sets], ns[i % n_sets], dn[i % n_sets]) for i in range(n_upd)],
+                                   [(tt[i % n_sets], tl[i % n_sets]) for i in range(n_upd)])
+    replay(); sync()
+    n_rep = 4
+    e0.record()
+    for _ in range(n_rep):
+        replay()
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1) / (n_rep * n_upd)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     out["updates_per_s"] = 1e3 / ms
     out["update_ms"] = ms
+    out["update_ms_eager_launches"] = ms_eager
+    out["update_launch"] = f"{n_rep} replays of one CUDA graph of {n_upd} updates (IQNAgent.capture_updates); `update_ms_eager_launches` = the same updates launched from Python"
     peer = agent._tail is not None and agent._tail.world == world
     out["update_config"] = (f"batch {B} per GPU, N=N'=8, 3xTF32 mma.sync (fp32-level accuracy); two launches: iqn_loss_partials + iqn_update_tail "
                             "(tile-partial sum" + (", one-shot all-reduce of the 35785-float gradient over peer memory (NVLink)" if world > 1 and peer else "")

@@ -396,6 +396,51 @@ class IQNAgent:
         self._log_evaluation(greedy, action_data, list(ret.cpu().numpy()), list((last_info == 3).cpu().numpy()),
                              list(env.dt * env.N * length_h.astype(np.float64)), energy, eval_log_path, verbose)
 
+    def capture_updates(self, batches, taus):
+        """n = len(batches) consecutive updates (train_async on each (experiences, (taus_target, taus_local)) pair, in order) as
+        ONE CUDA graph: returns replay(), which runs the n updates again on whatever the batch tensors hold then and advances
+        the optimizer's step count by n.  Adam's bias corrections change with every step, so they come from a table of n
+        mnv_vstep_ctl blocks the graph copies in first (include/marinenav_b200.h).  With data-parallel replicas this takes the
+        host out of the lock-step between the ranks: the gradient exchange inside iqn_update_tail makes every update wait for
+        the slowest rank, and a rank that launches from Python is late whenever its interpreter is."""
+        import ctypes as C
+        n, dev, opt = len(batches), self.device, self.optimizer
+        B = batches[0][0].shape[0]
+        need = iqn_ops.train_scratch_floats(B)
+        with torch.cuda.device(dev):
+            if self._scratch is None or self._scratch.numel() < need:
+                self._scratch = torch.empty(need, dtype=torch.float32, device=dev)
+            if self.fused_tail and self._tail is None:
+                self._tail = iqn_ops.UpdateTail(dev)
+            if not (self.fused_tail and self._tail.world == mdist.world_size()):
+                raise _lib.MarinenavError("capture_updates needs the fused update tail (iqn_update_tail) on every rank")
+            size = C.sizeof(_lib.MnvVstepCtl)
+            pin = torch.zeros(n, size, dtype=torch.uint8).pin_memory()
+            host = (_lib.MnvVstepCtl * n).from_buffer(pin.numpy())
+            ctl = torch.zeros(n, size, dtype=torch.uint8, device=dev)
+            done = torch.cuda.Event()
+            cur, side = torch.cuda.current_stream(dev), torch.cuda.Stream(device=dev)
+            g = torch.cuda.CUDAGraph()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    ctl.copy_(pin, non_blocking=True)
+                    for u in range(n):
+                        self._update(batches[u], taus[u], ctl=ctl.data_ptr() + u * size)
+            cur.wait_stream(side)
+
+        def replay():
+            done.synchronize()                                   # the previous replay has read the pinned table
+            for u in range(n):
+                host[u].adam_step_size, host[u].adam_inv_sqrt_bc2 = iqn_ops.adam_ctl_fields(opt.lr, opt.betas[0], opt.betas[1],
+                                                                                             opt.step_count + 1 + u)
+            g.replay()
+            done.record(torch.cuda.current_stream(dev))
+            opt.step_count += n
+            return self._loss
+        replay.graph, replay.keep = g, (pin, ctl, batches, taus)
+        return replay
+
     def reference_updates_per_step(self, num_envs, batch_size=None):
         """The reference's replay ratio in vector form: agent.py:127-136 trains once on BATCH_SIZE = 32 samples every
         UPDATE_EVERY = 4 transitions, i.e. 8 sampled transitions per collected one; a vector step collects num_envs (x world

@@ -38,7 +38,7 @@ class VecMarineNavEnv:
         #              order: the host threads expand the packet WHILE the DMA engine still writes the dense rows, so the link
         #              and the host cores work at the same time (the packet's arrival is signalled through a sequence number
         #              in pinned memory): 170 - 184 us with 8 / 4 threads -- the choice when a rank has few cores;
-        #   "auto"     MEASURED: the first 18 step_host calls run 6 steps on each transport (identical results, whichever
+        #   "auto"     MEASURED: the first 33 step_host calls run 11 steps on each transport (identical results, whichever
         #              carries them), the fastest median stays.  Which one wins depends on the host: cores per rank, how many
         #              GPUs share the memory system.  MNV_HOST_TRANSPORT overrides.
         t = os.environ.get("MNV_HOST_TRANSPORT", host_transport)
@@ -46,7 +46,7 @@ class VecMarineNavEnv:
         if t == "auto":
             t = "compact"
             order = ("compact", "hybrid", "dense")
-            self._auto_cal = dict(order=order, per=6, calls=0, times={k: [] for k in order})
+            self._auto_cal = dict(order=order, per=11, calls=0, times={k: [] for k in order})
         if t not in ("dense", "compact", "hybrid"):
             raise ValueError(f"host_transport must be 'auto', 'dense', 'compact' or 'hybrid' (got {t!r})")
         self.host_transport = t

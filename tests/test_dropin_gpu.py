@@ -205,7 +205,7 @@ def test_step_host_matches_device_step(transport):
 
 
 def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch):
-    """host_transport="auto" with several ranks on the node: the first 18 calls run on the three transports (6 each), the
+    """host_transport="auto" with several ranks on the node: the first 33 calls run on the three transports (11 each), the
     fastest median stays -- and every call returns exactly what the plain device path computes, whichever transport carried it
     (also across the switches: each transport's host-side bookkeeping is rebuilt when another one has written the rows)."""
     from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
@@ -218,8 +218,8 @@ def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch
     a.reset_host(); b.reset()
     rng = np.random.RandomState(0)
     used = []
-    for t in range(30):
-        if t == 24:
+    for t in range(44):
+        if t == 38:
             a.host_transport = "compact" if a.host_transport != "compact" else "hybrid"      # a manual switch after the calibration
         act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)
         obs_h, rew_h, done_h, info_h = a.step_host(act)
@@ -229,8 +229,8 @@ def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch
         assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy().astype(bool))
     cal = a.host_transport_calibration
     assert a._auto_cal is None and set(cal) == {"dense", "compact", "hybrid"} and all(v > 0 for v in cal.values())
-    assert used[17] == min(cal, key=cal.get) and len(set(used[18:24])) == 1
-    assert used[:5] == ["compact"] * 5 and used[6:11] == ["hybrid"] * 5 and used[12:17] == ["dense"] * 5
+    assert used[32] == min(cal, key=cal.get) and len(set(used[33:38])) == 1
+    assert used[:10] == ["compact"] * 10 and used[11:21] == ["hybrid"] * 10 and used[22:32] == ["dense"] * 10
 
 
 def test_step_host_hybrid_fraction_and_small_batches(monkeypatch):

@@ -185,3 +185,26 @@ def test_learn_vec_graph_follows_the_schedules():
                     on_step=on_step)
     assert eps_seen[0] == 1.0 and eps_seen[-1] == pytest.approx(0.05) and all(a >= b for a, b in zip(eps_seen, eps_seen[1:]))
     assert upd[5] == 0 and upd[-1] == 20 - 6                                       # no update before learning_starts, one per step after
+
+
+@pytest.mark.gpu
+def test_capture_updates_matches_eager_updates():
+    """IQNAgent.capture_updates: n updates as one CUDA graph (Adam's bias corrections from the control-block table), replayed
+    twice == the same 2 n updates launched one by one."""
+    from distributional_rl_navigation_b200.iqn_agent import IQNAgent
+    g = torch.Generator(device=DEV); g.manual_seed(8)
+    B, n = 128, 5
+    batches = [(torch.randn(B, 26, device=DEV, generator=g), torch.randint(0, 9, (B,), device=DEV, generator=g),
+                torch.randn(B, device=DEV, generator=g), torch.randn(B, 26, device=DEV, generator=g),
+                (torch.rand(B, device=DEV, generator=g) < 0.1).float()) for _ in range(n)]
+    taus = [(torch.rand(B, 8, device=DEV, generator=g), torch.rand(B, 8, device=DEV, generator=g)) for _ in range(n)]
+    a, b = IQNAgent(26, 9, seed=4, device=DEV, BATCH_SIZE=B), IQNAgent(26, 9, seed=4, device=DEV, BATCH_SIZE=B)
+    replay = a.capture_updates(batches, taus)
+    replay(); replay()
+    for _ in range(2):
+        for u in range(n):
+            b.train_async(batches[u], taus[u])
+    torch.cuda.synchronize()
+    assert a.optimizer.step_count == b.optimizer.step_count == 2 * n
+    assert torch.equal(a.qnetwork_local.flat, b.qnetwork_local.flat) and torch.equal(a.optimizer.v, b.optimizer.v)
+    assert torch.equal(a.qnetwork_local.packed_tc, b.qnetwork_local.packed_tc) and torch.equal(a._loss, b._loss)
