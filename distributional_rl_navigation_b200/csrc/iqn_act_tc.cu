@@ -144,6 +144,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Split form for software-pipelined epilogues: the load is asynchronous until tcgen05.wait::ld, so the next block's load can be
+// in flight while this block is converted and stored.  The wait names the registers as in/out operands: that is what orders
+// the consumers behind it for the compiler (a plain "memory" clobber does not order register reads).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+
 // 32 consecutive columns of this thread's row with ONE round trip to TMEM
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 {
@@ -351,6 +376,10 @@ struct ActArgs {
     long long* timing;                                                // lab ("act_timing" option): clock64 stamps of CTA 0's phases
 };
 constexpr int kStamps = 12, kStampTiles = 64;
+#ifndef MNV_E1_PIPELINED
+#define MNV_E1_PIPELINED 1
+#endif
+constexpr bool mnv_e1_pipelined = MNV_E1_PIPELINED != 0;
 
 // Random streams of the sampling mode, all from Philox4x32-10 keyed by `seed`, counter = (env, sub-stream, step):
 //   sub-stream 0..7: the 32 taus of the environment (4 per draw, torch.rand-style 24-bit uniforms, model.py:149)
@@ -497,6 +526,55 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         for (int q = 0; q < W / 8; ++q) store_relu_chunk(gs.a1, row, (n0 >> 3) + q, kK1, v + q * 8, feat + n0 + q * 8);
     };
 
+    // epilogue 1, software-pipelined: the thread's 104 D1 columns as blocks of 16 (8) columns through two register sets; the
+    // TMEM load of block k + 1 is in flight while block k is converted (relu, x feat, bf16) and stored
+    auto e1_taddr = [&](int n0) { return tmem + lane_base + (n0 < kN1a ? kD1a + (uint32_t)n0 : kD1b + (uint32_t)(n0 - kN1a)); };
+    auto e1_store = [&](const uint32_t (&r)[16], int n0, int width, const __nv_bfloat16* feat) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (debug != nullptr && tile == (long long)blockIdx.x * 2 + g && blockIdx.x == 0 && g == 0)
+            for (int j = 0; j < width; ++j) debug[row * kFeat + n0 + j] = v[j];
+        store_relu_chunk(gs.a1, row, n0 >> 3, kK1, v, feat + n0);
+        if (width == 16) store_relu_chunk(gs.a1, row, (n0 >> 3) + 1, kK1, v + 8, feat + n0 + 8);
+    };
+    auto epilogue1 = [&](const __nv_bfloat16* feat) {
+        // half 0: features [0, 104) = 6 x 16 + 8; half 1: [104, 208) = 5 x 16 + 8 (-> 192: the D1a | D1b boundary) + 16
+        uint32_t ra[16], rb[16];
+        const int base = half * 104;
+        tmem_ld16_async(e1_taddr(base), ra);
+        tmem_wait_ld(ra);
+        tmem_ld16_async(e1_taddr(base + 16), rb);
+        e1_store(ra, base, 16, feat);
+        tmem_wait_ld(rb);
+        tmem_ld16_async(e1_taddr(base + 32), ra);
+        e1_store(rb, base + 16, 16, feat);
+        tmem_wait_ld(ra);
+        tmem_ld16_async(e1_taddr(base + 48), rb);
+        e1_store(ra, base + 32, 16, feat);
+        tmem_wait_ld(rb);
+        tmem_ld16_async(e1_taddr(base + 64), ra);
+        e1_store(rb, base + 48, 16, feat);
+        tmem_wait_ld(ra);
+        if (half == 0) {
+            tmem_ld16_async(e1_taddr(80), rb);
+            e1_store(ra, 64, 16, feat);
+            tmem_wait_ld(rb);
+            tmem_ld8_async(e1_taddr(96), ra);
+            e1_store(rb, 80, 16, feat);
+            tmem_wait_ld(ra);
+            e1_store(ra, 96, 8, feat);
+        } else {
+            tmem_ld8_async(e1_taddr(184), rb);
+            e1_store(ra, 168, 16, feat);
+            tmem_wait_ld(rb);
+            tmem_ld16_async(e1_taddr(192), ra);
+            e1_store(rb, 184, 8, feat);
+            tmem_wait_ld(ra);
+            e1_store(ra, 192, 16, feat);
+        }
+    };
+
     float n_tau = load_tau(tile);
     uint4 n_feat = load_feat(tile);
     // ================= MMA-issuing warp of the group: waits at the hand-off points, one elected lane issues =================
@@ -560,7 +638,10 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         stamp(1);
         {
             const __nv_bfloat16* feat = gs.feat + (row / kTaus) * kFeat;
-            if (half == 0) {
+            if (mnv_e1_pipelined) {
+                epilogue1(feat);
+                if (half == 1) store_bias_step(gs.a1, row, kFeat / 8, kK1);
+            } else if (half == 0) {
                 e1_block(std::integral_constant<int, 32>{}, 0, feat); e1_block(std::integral_constant<int, 32>{}, 32, feat);
                 e1_block(std::integral_constant<int, 32>{}, 64, feat); e1_block(std::integral_constant<int, 8>{}, 96, feat);
             } else {

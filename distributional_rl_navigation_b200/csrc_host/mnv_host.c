@@ -29,6 +29,8 @@ typedef struct mnvh_pool {
     int n_threads; int64_t E; int D, n_beams, W;
     pthread_t* tid;
     uint32_t* prev_mask;                        /* [E][W]: beam slots currently non-zero in the dense array */
+    int32_t* skipped; int64_t* n_skipped;       /* rows mnvh_expand_early left for mnvh_rescan_skipped: worker t's rows start at
+                                                   skipped[32 * g_lo[t]], n_skipped[8 * t] of them */
     int64_t* g_lo; int64_t* g_hi;               /* group range of every worker */
     int cpu_first, pin;
     job_t job;
@@ -54,6 +56,8 @@ static void work(mnvh_pool* p, int t)
     const int64_t E = p->E;
     float* obs = j->obs;
     uint32_t* pm = p->prev_mask;
+    int32_t* my_skipped = p->skipped + 32 * p->g_lo[t];
+    int64_t n_my = 0;
     for (int64_t g = p->g_lo[t]; g < p->g_hi[t]; ++g) {
         const int64_t e0 = g * 32, e1 = e0 + 32 < E ? e0 + 32 : E;
         if (j->rescan_only == 1 || j->rescan_only == 3) {         /* 1: every row; 3: only the rows flagged in skip */
@@ -72,6 +76,7 @@ static void work(mnvh_pool* p, int t)
                     if (j->rescan_only != 2)                     /* 2: the GPU's row arrives later, mnvh_rescan_skipped follows */
                         pm[e * W + w] = row_mask(row + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
                 }
+                if (j->rescan_only == 2) my_skipped[n_my++] = (int32_t)e;
                 continue;
             }
             memcpy(row, j->head + 4 * e, 16);
@@ -85,6 +90,7 @@ static void work(mnvh_pool* p, int t)
             }
         }
     }
+    if (j->rescan_only == 2) p->n_skipped[8 * t] = n_my;
 }
 
 static void* worker(void* a_)
@@ -128,6 +134,8 @@ mnvh_pool* mnvh_create(int n_threads, int64_t E, int obs_dim, int cpu_first)
     p->n_threads = n_threads; p->E = E; p->D = obs_dim; p->n_beams = (obs_dim - 4) / 2; p->W = (p->n_beams + 31) / 32;
     p->pin = cpu_first >= 0; p->cpu_first = cpu_first;
     p->prev_mask = (uint32_t*)calloc((size_t)E * p->W, sizeof(uint32_t));
+    p->skipped = (int32_t*)calloc((size_t)groups * 32, sizeof(int32_t));
+    p->n_skipped = (int64_t*)calloc((size_t)n_threads * 8, sizeof(int64_t));
     p->g_lo = (int64_t*)calloc(n_threads, sizeof(int64_t)); p->g_hi = (int64_t*)calloc(n_threads, sizeof(int64_t));
     for (int t = 0; t < n_threads; ++t) { p->g_lo[t] = groups * t / n_threads; p->g_hi[t] = groups * (t + 1) / n_threads; }
     p->tid = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
@@ -147,7 +155,7 @@ void mnvh_destroy(mnvh_pool* p)
     if (p == NULL) return;
     atomic_store(&p->stop, 1);
     for (int t = 1; t < p->n_threads; ++t) pthread_join(p->tid[t], NULL);
-    free(p->prev_mask); free(p->g_lo); free(p->g_hi); free(p->tid); free(p);
+    free(p->prev_mask); free(p->skipped); free(p->n_skipped); free(p->g_lo); free(p->g_hi); free(p->tid); free(p);
 }
 
 int mnvh_threads(const mnvh_pool* p) { return p ? p->n_threads : 0; }
@@ -179,17 +187,15 @@ void mnvh_expand_early(mnvh_pool* p, float* obs, const float* head, const uint8_
 /* ... and this picks them up once they have: re-scan of the rows flagged in skip. */
 void mnvh_rescan_skipped(mnvh_pool* p, float* obs, const uint8_t* skip)
 {
-    if (skip == NULL) return;
-    /* a few hundred rows among E flags: not worth waking the pool -- the caller scans the flags 8 at a time */
+    (void)skip;
+    /* the rows mnvh_expand_early skipped (each worker listed its own): a few hundred, not worth waking the pool */
     const int D = p->D, nb = p->n_beams, W = p->W;
-    const int64_t E = p->E;
-    for (int64_t e = 0; e < E; ) {
-        if (e + 8 <= E) {
-            uint64_t w8; memcpy(&w8, skip + e, 8);
-            if (w8 == 0) { e += 8; continue; }
-        }
-        if (skip[e])
+    for (int t = 0; t < p->n_threads; ++t) {
+        const int32_t* rows = p->skipped + 32 * p->g_lo[t];
+        for (int64_t k = 0; k < p->n_skipped[8 * t]; ++k) {
+            const int64_t e = rows[k];
             for (int w = 0; w < W; ++w) p->prev_mask[e * W + w] = row_mask(obs + e * D + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
-        ++e;
+        }
+        p->n_skipped[8 * t] = 0;
     }
 }

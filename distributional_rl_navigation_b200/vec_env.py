@@ -38,15 +38,17 @@ class VecMarineNavEnv:
         #              order: the host threads expand the packet WHILE the DMA engine still writes the dense rows, so the link
         #              and the host cores work at the same time (the packet's arrival is signalled through a sequence number
         #              in pinned memory): 170 - 184 us with 8 / 4 threads -- the choice when a rank has few cores;
-        #   "auto"     MEASURED: the first 33 step_host calls run 11 steps on each transport (identical results, whichever
-        #              carries them), the fastest median stays.  Which one wins depends on the host: cores per rank, how many
+        #   "auto"     MEASURED: after 64 calls, 33 step_host calls run 11 steps on each transport (identical results, whichever
+        #              carries them), the fastest median stays -- until the next measurement 4096 calls later.  Which one wins depends on the host: cores per rank, how many
         #              GPUs share the memory system.  MNV_HOST_TRANSPORT overrides.
         t = os.environ.get("MNV_HOST_TRANSPORT", host_transport)
         self._auto_cal = None
         if t == "auto":
-            t = "compact"
+            t = "hybrid"
             order = ("compact", "hybrid", "dense")
-            self._auto_cal = dict(order=order, per=11, calls=0, times={k: [] for k in order})
+            # measured after the first 64 calls (right after a reset of all environments the robots see ~2x the sonar returns
+            # of a running rollout, which is not what the choice should be made on) and again every 4096 calls
+            self._auto_cal = dict(order=order, per=11, calls=-64, every=4096, times={k: [] for k in order})
         if t not in ("dense", "compact", "hybrid"):
             raise ValueError(f"host_transport must be 'auto', 'dense', 'compact' or 'hybrid' (got {t!r})")
         self.host_transport = t
@@ -327,6 +329,9 @@ class VecMarineNavEnv:
             return self._step_host(actions, auto_reset, graph)
         # host_transport="auto" with several ranks on the node: time both transports under the load the ranks produce together
         k, per = cal["calls"], cal["per"]
+        if k < 0:                                                  # not yet (or between two measurements): the current choice
+            cal["calls"] = k + 1
+            return self._step_host(actions, auto_reset, graph)
         self.host_transport = cal["order"][k // per]
         t0 = time.perf_counter()
         out = self._step_host(actions, auto_reset, graph)
@@ -337,7 +342,7 @@ class VecMarineNavEnv:
             med = {t: sorted(v)[len(v) // 2] for t, v in cal["times"].items()}
             self.host_transport_calibration = med
             self.host_transport = min(med, key=med.get)
-            self._auto_cal = None
+            cal["calls"], cal["times"] = -cal["every"], {t: [] for t in cal["order"]}
         return out
 
     def _step_host(self, actions, auto_reset, graph):
@@ -399,6 +404,8 @@ class VecMarineNavEnv:
             h["valid"] = True
         self._host_dirty = True                                   # (the full-size expander of "compact" loses track of the rows)
         expect = h["next_seq"]
+        trace = h.get("trace")                                    # lab (scripts/lab/auto_transport_trace.py): phase stamps of this call
+        t_a = time.perf_counter()
         graph.replay()
         self.total_timesteps += self.num_envs * self.global_step_multiplier
         seq_np, spins = h["seq_np"], 0
@@ -409,6 +416,7 @@ class VecMarineNavEnv:
                 if int(seq_np[3]) != expect:
                     raise _lib.MarinenavError(f"step_host(hybrid): packet sequence {int(seq_np[3])}, expected {expect}")
         h["next_seq"] = (expect + 1) & 0xFFFFFFFF
+        t_b = time.perf_counter()
         n_hits = int(h["count_np"][0])
         skip = pin["done"].data_ptr() if auto_reset else None
         if n_hits > h["cap"]:                                     # more returns than the list holds: dense block this once
@@ -421,9 +429,13 @@ class VecMarineNavEnv:
             torch.cuda.current_stream().synchronize()
         h["expander"].expand_early(obs_ptr, h["p_head"].data_ptr(), skip, h["p_mask"].data_ptr(), h["p_dir"].data_ptr(),
                                    h["p_vals"].data_ptr())
+        t_c = time.perf_counter()
         torch.cuda.current_stream().synchronize()
+        t_d = time.perf_counter()
         if auto_reset:
             h["expander"].rescan_skipped(obs_ptr, skip)
+        if trace is not None:
+            trace.append((spins, n_hits, t_b - t_a, t_c - t_b, t_d - t_c, time.perf_counter() - t_d))
 
     def tables_written(self):
         """Call after writing buf['goal'|'cores'|'obstacles'] with a device-side kernel (e.g. indexed assignment) if a step

@@ -205,8 +205,8 @@ def test_step_host_matches_device_step(transport):
 
 
 def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch):
-    """host_transport="auto" with several ranks on the node: the first 33 calls run on the three transports (11 each), the
-    fastest median stays -- and every call returns exactly what the plain device path computes, whichever transport carried it
+    """host_transport="auto" with several ranks on the node: 33 calls run on the three transports (11 each), the
+    fastest median stays until the next measurement -- and every call returns exactly what the plain device path computes, whichever transport carried it
     (also across the switches: each transport's host-side bookkeeping is rebuilt when another one has written the rows)."""
     from distributional_rl_navigation_b200.vec_env import VecMarineNavEnv
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
@@ -215,22 +215,28 @@ def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch
     a = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)        # "auto"
     b = VecMarineNavEnv(E, seed=11, device="cuda:0", num_cores=4, num_obs=8, min_start_goal_dis=30.0)
     assert a._auto_cal is not None and a.host_transport_calibration is None
+    a._auto_cal["calls"], a._auto_cal["every"] = -3, 9            # (production: first measurement after 64 calls, then every 4096)
     a.reset_host(); b.reset()
     rng = np.random.RandomState(0)
     used = []
-    for t in range(44):
-        if t == 38:
-            a.host_transport = "compact" if a.host_transport != "compact" else "hybrid"      # a manual switch after the calibration
+    for t in range(3 + 33 + 9 + 33 + 4):
+        if t == 40:
+            a.host_transport = "compact" if a.host_transport != "compact" else "hybrid"      # a manual switch between two measurements
         act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)
         obs_h, rew_h, done_h, info_h = a.step_host(act)
         used.append(a.host_transport)
         obs_d, rew_d, done_d, info_d = b.step(torch.from_numpy(act).cuda())
         assert np.array_equal(obs_h, obs_d.cpu().numpy()), t
         assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy().astype(bool))
-    cal = a.host_transport_calibration
-    assert a._auto_cal is None and set(cal) == {"dense", "compact", "hybrid"} and all(v > 0 for v in cal.values())
-    assert used[32] == min(cal, key=cal.get) and len(set(used[33:38])) == 1
-    assert used[:10] == ["compact"] * 10 and used[11:21] == ["hybrid"] * 10 and used[22:32] == ["dense"] * 10
+        if t == 36:
+            cal = dict(a.host_transport_calibration)
+            assert set(cal) == {"dense", "compact", "hybrid"} and all(v > 0 for v in cal.values())
+            assert used[35] == min(cal, key=cal.get)
+    assert used[:3] == ["hybrid"] * 3                                # the default until the first measurement
+    assert used[3:13] == ["compact"] * 10 and used[14:24] == ["hybrid"] * 10 and used[25:35] == ["dense"] * 10
+    assert used[45:55] == ["compact"] * 10 and used[67:77] == ["dense"] * 10          # the second measurement, 9 calls later
+    cal2 = a.host_transport_calibration
+    assert used[-1] == min(cal2, key=cal2.get) and a._auto_cal["calls"] < 0
 
 
 def test_step_host_hybrid_fraction_and_small_batches(monkeypatch):
