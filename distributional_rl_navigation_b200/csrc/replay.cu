@@ -12,6 +12,8 @@
 //   rpl_gather   the same gather for caller-provided indices (parity harnesses inject the reference's random.sample picks).
 // Logical index i counts from the OLDEST stored transition (memory[i] of the reference's deque); the ring slot is
 // (head + i) mod capacity.
+#include <algorithm>
+
 #include "mnv_common.cuh"
 #include "philox.cuh"
 
@@ -70,6 +72,36 @@ rpl_append_kernel(Ring R, long long pos, const float* __restrict__ obs, const in
     if (lane == 0) {
         R.actions[slot] = (int64_t)a0;
         R.rewards[slot] = (float)ret;
+        R.dones[slot] = done[e] ? 1.0f : 0.0f;
+    }
+}
+
+// n_step == 1: no window, and the ring slots of one vector step are consecutive -- (pos + e) mod capacity -- so the append is two
+// flat block copies (E x row_len floats each, wrapping at the end of the ring) plus E (action, reward, done) triples: 8-byte
+// vectors, every lane busy (the warp-per-row form above keeps 13 of 32 lanes busy on a 104-byte row).
+__global__ void __launch_bounds__(256)
+rpl_append_flat_kernel(Ring R, long long pos, const float* __restrict__ obs, const int32_t* __restrict__ action,
+                       const float* __restrict__ reward, const float* __restrict__ next_obs, const uint8_t* __restrict__ done,
+                       long long E, int row_len, const mnv_vstep_ctl* __restrict__ ctl)
+{
+    if (ctl != nullptr) pos = ctl->rpl_pos;
+    const long long n2 = E * row_len / 2, ring2 = R.capacity * row_len / 2, base2 = pos * row_len / 2;   // row_len is even here
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float2* __restrict__ s2 = reinterpret_cast<const float2*>(obs);
+    const float2* __restrict__ n2p = reinterpret_cast<const float2*>(next_obs);
+    float2* d_s = reinterpret_cast<float2*>(R.states);
+    float2* d_n = reinterpret_cast<float2*>(R.next_states);
+    for (long long i = i0; i < n2; i += stride) {
+        long long d = base2 + i;
+        if (d >= ring2) d -= ring2;
+        d_s[d] = s2[i];
+        d_n[d] = n2p[i];
+    }
+    for (long long e = i0; e < E; e += stride) {
+        long long slot = pos + e;
+        if (slot >= R.capacity) slot -= R.capacity;
+        R.actions[slot] = (int64_t)action[e];
+        R.rewards[slot] = reward[e];
         R.dones[slot] = done[e] ? 1.0f : 0.0f;
     }
 }
@@ -187,6 +219,12 @@ static int append_impl(float* d_states, int64_t* d_actions, float* d_rewards, fl
     if (pos < 0 || pos >= capacity || n_step < 1 || t < 0) { mnv_set_error("rpl_append: bad pos / n_step / t"); return MNV_E_PARAM; }
     if (n_step > 1 && (d_win_obs == nullptr || d_win_action == nullptr || d_win_reward == nullptr)) { mnv_set_error("rpl_append: n_step > 1 needs the window buffers"); return MNV_E_NULL; }
     Ring R{d_states, d_actions, d_rewards, d_next_states, d_dones, capacity};
+    if (n_step == 1 && (row_len & 1) == 0 && ((reinterpret_cast<uintptr_t>(d_obs) | reinterpret_cast<uintptr_t>(d_next_obs)) & 7u) == 0) {
+        const long long n2 = E * row_len / 2;
+        const unsigned grid = (unsigned)std::min<long long>((n2 + 255) / 256, 148ll * 8);
+        rpl_append_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(R, pos, d_obs, d_action, d_reward, d_next_obs, d_done, E, row_len, d_ctl);
+        return mnv_launch_status("rpl_append");
+    }
     const unsigned grid = (unsigned)((E + kWarps - 1) / kWarps);
     rpl_append_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(R, pos, d_obs, d_action, d_reward, d_next_obs, d_done, E, row_len,
                                                                       n_step, gamma, t, d_win_obs, d_win_action, d_win_reward, d_ctl);

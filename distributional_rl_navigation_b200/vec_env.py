@@ -51,7 +51,7 @@ class VecMarineNavEnv:
             self._auto_cal = dict(order=order, per=11, calls=-64, every=4096, times={k: [] for k in order})
         if t not in ("dense", "compact", "hybrid"):
             raise ValueError(f"host_transport must be 'auto', 'dense', 'compact' or 'hybrid' (got {t!r})")
-        self.host_transport = t
+        self._transport = t
         self.host_transport_calibration = None      # {"dense": median seconds per step, "compact": ...} once "auto" has measured
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
@@ -92,6 +92,22 @@ class VecMarineNavEnv:
             self.rng_pos = torch.zeros(E, dtype=torch.int32, device=self.device)
         self._pinned = None
         self.seed(seed)
+
+    @property
+    def host_transport(self):
+        """The transport step_host uses now ("dense" | "compact" | "hybrid").  Assigning one of them fixes it (and ends the
+        measurements of "auto"); assigning "auto" starts measuring again."""
+        return self._transport
+
+    @host_transport.setter
+    def host_transport(self, t):
+        if t == "auto":
+            order = ("compact", "hybrid", "dense")
+            self._auto_cal = dict(order=order, per=11, calls=-64, every=4096, times={k: [] for k in order})
+            return
+        if t not in ("dense", "compact", "hybrid"):
+            raise ValueError(f"host_transport must be 'auto', 'dense', 'compact' or 'hybrid' (got {t!r})")
+        self._transport, self._auto_cal = t, None
 
     # ---- gym-style surface -------------------------------------------------------------------------------------
     @property
@@ -332,7 +348,7 @@ class VecMarineNavEnv:
         if k < 0:                                                  # not yet (or between two measurements): the current choice
             cal["calls"] = k + 1
             return self._step_host(actions, auto_reset, graph)
-        self.host_transport = cal["order"][k // per]
+        self._transport = cal["order"][k // per]
         t0 = time.perf_counter()
         out = self._step_host(actions, auto_reset, graph)
         if k % per:                                                # the first call of a block captures the graph / rescans
@@ -341,7 +357,7 @@ class VecMarineNavEnv:
         if cal["calls"] == per * len(cal["order"]):
             med = {t: sorted(v)[len(v) // 2] for t, v in cal["times"].items()}
             self.host_transport_calibration = med
-            self.host_transport = min(med, key=med.get)
+            self._transport = min(med, key=med.get)
             cal["calls"], cal["times"] = -cal["every"], {t: [] for t in cal["order"]}
         return out
 

@@ -10,8 +10,9 @@ env = VecMarineNavEnv(E, seed=0, device="cuda:0", num_cores=4, num_obs=8, min_st
 env.reset_host()
 env._hybrid()["trace"] = []
 rows = []
-for i in range(60):
-    tr = env._auto_cal["order"][env._auto_cal["calls"] // env._auto_cal["per"]] if env._auto_cal else env.host_transport
+for i in range(110):
+    c = env._auto_cal
+    tr = c["order"][c["calls"] // c["per"]] if c and c["calls"] >= 0 else env.host_transport
     t0 = time.perf_counter(); env.step_host(acts[i % 64]); rows.append((tr, (time.perf_counter() - t0) * 1e6))
 print(" ".join(f"{t[0]}{us:.0f}" for t, us in rows))
 print("calibration:", env.host_transport_calibration, "->", env.host_transport)

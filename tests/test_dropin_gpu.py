@@ -220,8 +220,6 @@ def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch
     rng = np.random.RandomState(0)
     used = []
     for t in range(3 + 33 + 9 + 33 + 4):
-        if t == 40:
-            a.host_transport = "compact" if a.host_transport != "compact" else "hybrid"      # a manual switch between two measurements
         act = np.full(E, 8, np.int32) if t % 2 else rng.randint(0, 9, size=E).astype(np.int32)
         obs_h, rew_h, done_h, info_h = a.step_host(act)
         used.append(a.host_transport)
@@ -237,6 +235,15 @@ def test_step_host_auto_transport_measures_all_and_keeps_the_results(monkeypatch
     assert used[45:55] == ["compact"] * 10 and used[67:77] == ["dense"] * 10          # the second measurement, 9 calls later
     cal2 = a.host_transport_calibration
     assert used[-1] == min(cal2, key=cal2.get) and a._auto_cal["calls"] < 0
+    a.host_transport = "dense"                                       # an explicit choice ends the measurements ...
+    assert a._auto_cal is None and a.host_transport == "dense"
+    for t in range(3):
+        act = rng.randint(0, 9, size=E).astype(np.int32)
+        obs_h, _, _, _ = a.step_host(act)
+        obs_d, _, _, _ = b.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(obs_h, obs_d.cpu().numpy()) and a.host_transport == "dense"
+    a.host_transport = "auto"                                        # ... and "auto" starts them again
+    assert a._auto_cal is not None and a.host_transport == "dense"
 
 
 def test_step_host_hybrid_fraction_and_small_batches(monkeypatch):
