@@ -660,7 +660,6 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         stamp(3);
         if (has_next) {                                      // (D1a and A0 of this tile were consumed: layer 1 completed above)
             produce_a0(n_tau);
-            n_tau = load_tau(tile + 2 * tile_step);
             fence_async_smem();
             tc_fence_before();
             handoff_arrive(g, 1);
@@ -685,6 +684,9 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
         handoff_arrive(g, 2);
 
         // ---- layer 3: D3[128 x 64] = A2 . W2^T (issuing warp) ----
+        // the tau of the tile after next (a Philox draw in the sampling mode) is computed HERE, where the compute warps would
+        // only wait for layer 3 -- not in the A0 phase above, which is on the tile's critical path
+        if (has_next) n_tau = load_tau(tile + 2 * tile_step);
         stamp(6);
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
@@ -706,6 +708,12 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
 
         // ---- output layer: D4[128 x 16] = A3 . W3^T (+ layer 1b of the next tile; issuing warp), then mean over the 32 taus of
         //      each env (one warp) + argmax ----
+        // the epsilon-greedy draw of this warp's environment does not depend on D4: drawn while layer 4 runs
+        uint32_t eg_coin = 0u, eg_action = 0u;
+        if (half == 0 && A.sample && A.action != nullptr) {
+            const philox::u4 r = act_draw(A, s.dyn_step, env0 + (warp & 3), 8u);
+            eg_coin = r.x; eg_action = r.y;
+        }
         stamp(8);
         mbar_wait(&gs.bar_b, phase_b);
         phase_b ^= 1;
@@ -740,10 +748,7 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
                 if (A.action != nullptr) {                                                  // agent.py:200-203
                     int act = best;
                     const float eps = s.dyn_eps;
-                    if (A.sample && eps > 0.f) {
-                        const philox::u4 r = act_draw(A, s.dyn_step, b, 8u);
-                        if (!(philox::u01(r.x) > eps)) act = (int)__umulhi(r.y, (uint32_t)kAct);
-                    }
+                    if (A.sample && eps > 0.f && !(philox::u01(eg_coin) > eps)) act = (int)__umulhi(eg_action, (uint32_t)kAct);
                     A.action[b] = act;
                 }
             }
