@@ -729,13 +729,21 @@ iqn_act_tc_kernel(const __grid_constant__ ActArgs A)
             }
             if (dbg)
                 for (int j = 0; j < kN4; ++j) debug[kRows * (kFeat + 2 * kHid) + row * kN4 + j] = q[j];
+            // sums over the 32 rows (= lanes) of the 16 columns: transposed butterfly -- at every step a lane keeps one half of its
+            // columns and hands the other half to its partner (8 + 4 + 2 + 1 + 1 shuffles instead of 9 x 5); lane L ends with
+            // column L >> 1, lane 0 then collects the 9 actions (9 shuffles)
 #pragma unroll
-            for (int a = 0; a < kAct; ++a) {
-                float v = q[a];
+            for (int m = 8; m >= 1; m >>= 1) {
+                const bool up = (lane & (2 * m)) != 0;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                q[a] = v * (1.f / kTaus);                                                // get_qvals: mean over taus (model.py:190); bias inside D4
+                for (int j = 0; j < m; ++j) {
+                    const float send = up ? q[j] : q[j + m], keep = up ? q[j + m] : q[j];
+                    q[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * m);
+                }
             }
+            const float qsum = (q[0] + __shfl_xor_sync(0xffffffffu, q[0], 1)) * (1.f / kTaus);   // get_qvals: mean over taus (model.py:190); bias inside D4
+#pragma unroll
+            for (int a = 0; a < kAct; ++a) q[a] = __shfl_sync(0xffffffffu, qsum, 2 * a);
             const long long b = env0 + (warp & 3);
             if (lane == 0 && b < B) {
                 int best = 0; float bv = q[0];
