@@ -51,7 +51,7 @@ def create_eval_configs(eval_env):
     return eval_config
 
 
-def run_trial(device, params, num_envs, batch_size, updates_per_step=1):
+def run_trial(device, params, num_envs, batch_size, updates_per_step=1, graph=False):
     import marinenav_env  # noqa: F401  (registers 'marinenav_env-v0')
     from distributional_rl_navigation_b200 import distributed as mdist
     from distributional_rl_navigation_b200 import marinenav_env as impl
@@ -87,7 +87,7 @@ def run_trial(device, params, num_envs, batch_size, updates_per_step=1):
                          seed=params["seed"] + 100, BATCH_SIZE=batch_size)
         model.learn_vec(total_timesteps=params["total_timesteps"], train_env=train_env, eval_config=eval_config,
                         eval_freq=params["eval_freq"], eval_log_path=log_dir, batch_size=batch_size,
-                        updates_per_step=updates_per_step, sample_without_replacement=True)
+                        updates_per_step=updates_per_step, sample_without_replacement=True, graph=graph)
     train_env.close(); eval_env.close()
     return exp_dir, model
 
@@ -100,6 +100,8 @@ def main():
     ap.add_argument("--batch-size", type=int, default=1024)
     ap.add_argument("--updates-per-step", default="1", help="IQN updates per vector step, or 'reference' = the reference's replay "
                     "ratio (one update of 32 per 4 transitions, agent.py:127-136) in vector form")
+    ap.add_argument("--graph", action="store_true", help="vectorised trainer: replay the whole vector step as ONE CUDA graph "
+                    "(learn_vec(graph=True): pipelined learner, device control block)")
     args = ap.parse_args()
     ups = args.updates_per_step if args.updates_per_step == "reference" else int(args.updates_per_step)
     params = json.load(args.config_file)
@@ -109,7 +111,7 @@ def main():
         args.device = "cuda:%d" % int(os.environ["LOCAL_RANK"])
     for p in trials:
         p["training_time"] = stamp
-        exp_dir, _ = run_trial(args.device, p, args.num_envs, args.batch_size, ups)
+        exp_dir, _ = run_trial(args.device, p, args.num_envs, args.batch_size, ups, graph=args.graph)
         print("trial done:", exp_dir)
 
 
