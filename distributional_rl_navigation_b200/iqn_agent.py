@@ -625,12 +625,15 @@ class IQNAgent:
             self._tail = iqn_ops.UpdateTail(dev)
         if not (self.fused_tail and self._tail.world == world):
             raise _lib.MarinenavError("learn_vec(graph=True) needs the fused update tail on every rank; use graph=False")
+        # everything a capture bakes in by address: env buffers, both networks, the Adam moments, the replay ring
+        pipe_key = (id(train_env), E, B, U, train_env.buf["state"].data_ptr(), net.flat.data_ptr(), net.packed_tc.data_ptr(),
+                    self.qnetwork_target.flat.data_ptr(), opt.m.data_ptr(), mem.states.data_ptr())
         st = getattr(self, "_pipe", None)
-        if st is None or st["key"] != (id(train_env), E, B, U):
+        if st is None or st["key"] != pipe_key:
             with torch.cuda.device(dev):
                 pin = torch.zeros(2, U, C.sizeof(_lib.MnvVstepCtl), dtype=torch.uint8).pin_memory()
                 st = self._pipe = dict(
-                    key=(id(train_env), E, B, U), pin=pin,
+                    key=pipe_key, pin=pin,
                     host=[(_lib.MnvVstepCtl * U).from_buffer(pin[k].numpy()) for k in range(2)],
                     ctl=torch.zeros(2, U, C.sizeof(_lib.MnvVstepCtl), dtype=torch.uint8, device=dev),
                     taus=torch.zeros(2, U, 2, B, 8, dtype=torch.float32, device=dev),
