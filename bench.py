@@ -433,6 +433,10 @@ def run_b200(args):
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if E == ENVS_PER_GPU else None,
                          "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": "mnv_env_kernel<4,8,true,true>",
+                         "launch_streams": n_streams,
+                         "frac_single_stream": None if ms_1s is None else E * abytes / (ms_1s * 1e-3) / 1e9 / peak,
+                         "note": f"achieved = algorithmic bytes per launch / period of back-to-back launches of independent env batches on {n_streams} "
+                                 "stream(s); frac_single_stream = the same launches behind one another on ONE stream",
                          "issue_bound": {"warp_instructions_per_launch": NCU_WARP_INST_PER_LAUNCH,
                                          "floor_us_at_1_ipc_per_scheduler": NCU_WARP_INST_PER_LAUNCH / (148 * 4) / 1.965e3,
                                          "frac": NCU_WARP_INST_PER_LAUNCH / (148 * 4) / 1.965e3 / (ms_per_step * 1e3) if E == ENVS_PER_GPU else None,
