@@ -60,11 +60,9 @@ static void work(mnvh_pool* p, int t)
     int64_t n_my = 0;
     for (int64_t g = p->g_lo[t]; g < p->g_hi[t]; ++g) {
         const int64_t e0 = g * 32, e1 = e0 + 32 < E ? e0 + 32 : E;
-        if (j->rescan_only == 1 || j->rescan_only == 3) {         /* 1: every row; 3: only the rows flagged in skip */
-            for (int64_t e = e0; e < e1; ++e) {
-                if (j->rescan_only == 3 && !j->skip[e]) continue;
+        if (j->rescan_only == 1) {                                /* job kinds: 0 expand, 1 rescan every row, 2 expand early */
+            for (int64_t e = e0; e < e1; ++e)
                 for (int w = 0; w < W; ++w) pm[e * W + w] = row_mask(obs + e * D + 4, 32 * w, 32 * w + 32 < nb ? 32 * w + 32 : nb);
-            }
             continue;
         }
         const float* v = j->vals + 2 * (size_t)j->dir[g];
